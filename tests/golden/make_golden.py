@@ -1,0 +1,221 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference); the GPU box uses the committed
+``*.npz`` files.  Recipe = SURVEY.md Appendix A: stub the three absent top-level imports
+(faiss / matplotlib / torchmetrics -- none is on the hot path), chdir into the reference
+(relative ``configs/`` and ``dataset/`` paths), build the reference model classes with either
+the real amazon-toys datasets or a 5-attribute fake dataset for synthetic catalogs.
+
+For every case the reference model's state_dict is loaded into the oracle restatement
+(``oracle/dr4sr_oracle.py``) and both are run; the script asserts they agree bit-for-bit before
+anything is written, so a fixture pins the reference *and* the oracle.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+REF = '/root/reference'
+
+for _n in ('faiss', 'matplotlib', 'matplotlib.pyplot', 'torchmetrics', 'torchmetrics.functional'):
+    sys.modules[_n] = types.ModuleType(_n)
+sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+sys.modules['torchmetrics'].functional = sys.modules['torchmetrics.functional']
+os.chdir(REF)
+sys.path.insert(0, REF)
+sys.path.insert(1, REPO)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+import utils as ref_utils                      # noqa: E402  (runs set_detect_anomaly(True), utils/utils.py:11)
+from utils import load_config, seed_everything  # noqa: E402
+import wandb                                    # noqa: E402
+
+from oracle import dr4sr_oracle as orc          # noqa: E402
+from dr4sr_b200.data.synthetic import synthetic_batch   # noqa: E402
+
+wandb.init(mode='disabled')
+torch.autograd.set_detect_anomaly(False)
+torch.set_num_threads(8)
+
+
+class FakeDataset:
+    def __init__(self, num_items: int) -> None:
+        self.num_items = num_items
+        self.num_users = 1000
+        self.domain_name_list = ['syn']
+        self.domain_user_mapping = {'syn': [1]}
+        self.domain_item_mapping = {'syn': list(range(1, num_items))}
+
+
+def ref_model(name: str, N: int, D: int, dropout: float = 0.0, seed: int = 2023, hidden: int | None = None):
+    cfg = load_config({'model': name, 'dataset': 'amazon-toys'})
+    cfg['train']['device'] = 'cpu'
+    cfg['model']['embed_dim'] = D
+    cfg['model']['dropout_rate'] = dropout
+    if hidden is not None:
+        cfg['model']['hidden_size'] = hidden
+    seed_everything(seed)
+    cls = ref_utils.get_model_class(cfg['model'])
+    m = cls(cfg, [FakeDataset(N)] * 3)
+    m._init_model(None)
+    if name == 'FMLP':                      # dropout p is hard-coded 0.5 (fmlp.py:13, layers.py:744,762)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = dropout
+    m.set_eval_domain('syn')
+    return m, cfg
+
+
+def to_np(d):
+    return {k: (v.detach().cpu().numpy().copy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
+
+
+ALIASES = ('query_encoder.item_encoder.weight', 'query_encoder.0.1.weight')   # second names of item_embedding.weight
+
+
+def pack(prefix, d):
+    return {f'{prefix}/{k}': v for k, v in to_np(d).items() if k not in ALIASES}
+
+
+def run_case(name: str, oracle_cls, okw: dict, N: int, D: int, B: int, layout: str, seed: int, out: str, steps: int = 3):
+    L = 50
+    ref, cfg = ref_model(name, N, D, hidden=okw.get('hidden_size'))
+    o = oracle_cls(N, embed_dim=D, **okw)
+    missing = o.load_state_dict(ref.state_dict(), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    batch = synthetic_batch(B, L, N, seed=seed, layout=layout)
+    fx = {}
+    fx.update(pack('param', ref.state_dict()))
+    fx.update(pack('batch', batch))
+
+    # ---- train-mode forward / loss / gradients (dropout 0) ----
+    ref.train(); o.train()
+    loss_r, q_r = ref.training_step(batch={k: v.clone() for k, v in batch.items()}, reduce=True, return_query=True)
+    loss_o, q_o = o.training_step(batch, reduce=True, return_query=True)
+    assert torch.equal(q_r, q_o), 'oracle query != reference query'
+    assert torch.equal(loss_r, loss_o), 'oracle loss != reference loss'
+    per_r = ref.training_step(batch={k: v.clone() for k, v in batch.items()}, reduce=False)
+    per_o = o.training_step(batch, reduce=False)
+    assert torch.equal(per_r, per_o)
+    ref.optimizer.zero_grad()
+    loss_r.backward()
+    loss_o.backward()
+    grads = {}
+    for (k, p), (k2, p2) in zip(ref.named_parameters(), o.named_parameters()):
+        assert k == k2
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        g2 = p2.grad if p2.grad is not None else torch.zeros_like(p2)
+        # CPU index_put_(accumulate=True) adds atomically from several threads: the table gradient's
+        # summation order is not reproducible run to run, so gradients are pinned to 1e-5 relative
+        assert torch.allclose(g, g2, rtol=1e-5, atol=1e-9), f'grad mismatch {k}: {(g - g2).abs().max()}'
+        grads[k] = g
+    fx['train/query'] = q_r.detach().numpy()
+    fx['train/loss'] = loss_r.detach().numpy()
+    fx['train/loss_per_pos'] = per_r.detach().numpy()
+    fx.update(pack('grad', grads))
+
+    # ---- `steps` Adam steps on the same batch (dense Adam, basemodel.py:195-199) ----
+    opt_o = o.make_adam(lr=cfg['train']['learning_rate'], weight_decay=cfg['train']['weight_decay'])
+    o.zero_grad()
+    losses = []
+    for s in range(steps):
+        ref.optimizer.zero_grad()
+        l = ref.training_step(batch={k: v.clone() for k, v in batch.items()})
+        l.backward(); ref.optimizer.step()
+        opt_o.zero_grad()
+        l2 = o.training_step(batch)
+        l2.backward(); opt_o.step()
+        assert torch.allclose(l, l2, rtol=1e-6, atol=0)
+        losses.append(float(l.detach()))
+    for (k, p), (_, p2) in zip(ref.named_parameters(), o.named_parameters()):
+        assert torch.allclose(p, p2, rtol=0, atol=2e-6), f'post-Adam mismatch {k}: {(p - p2).abs().max()}'
+    fx['adam/losses'] = np.asarray(losses, dtype=np.float64)
+    fx['adam/weight_decay'] = np.asarray(cfg['train']['weight_decay'], dtype=np.float64)
+    fx['adam/lr'] = np.asarray(cfg['train']['learning_rate'], dtype=np.float64)
+    fx.update(pack('param_after', ref.state_dict()))
+
+    # ---- eval forward + full-catalog top-k (parameters = after the Adam steps) ----
+    ref.eval(); o.eval()
+    ev = synthetic_batch(B, L, N, seed=seed + 1, layout=layout, eval_mode=True, with_neg=False)
+    with torch.no_grad():
+        k = min(100, N - 60)
+        s_r, i_r = ref.topk(ev, k, ev['user_hist'])
+        s_o, i_o = o.topk(ev, k, ref.domain_item_mapping['syn'])
+        assert torch.allclose(s_r, s_o, rtol=1e-5, atol=1e-7)
+        o.load_state_dict(ref.state_dict())      # re-sync after the tolerance-level Adam drift
+        s_o, i_o = o.topk(ev, k, ref.domain_item_mapping['syn'])
+        assert torch.equal(i_r, i_o) and torch.equal(s_r, s_o)
+        fx['eval/query'] = ref.forward(ev).numpy()
+    fx.update(pack('evalbatch', ev))
+    fx['eval/topk_scores'] = s_r.numpy()
+    fx['eval/topk_ids'] = i_r.numpy()
+    np.savez_compressed(os.path.join(HERE, out), **fx)
+    print(f'{out}: loss0={losses[0]:.6f} loss{steps - 1}={losses[-1]:.6f} '
+          f'({sum(v.nbytes for v in fx.values()) / 1e6:.2f} MB raw)')
+
+
+def toys_checkpoint_case(n_users_topk: int = 256):
+    """Known answer: shipped SASRec checkpoint on amazon-toys val."""
+    cfg = load_config({'model': 'SASRec', 'dataset': 'amazon-toys'})
+    cfg['train']['device'] = 'cpu'
+    seed_everything(cfg['train']['seed'])
+    ds = ref_utils.prepare_datasets(cfg)
+    m = ref_utils.prepare_model(cfg, ds)
+    m._init_model(ds[0])
+    ck = torch.load('dataset/amazon-toys/toy/pre-trained_embedding.ckpt', weights_only=False, map_location='cpu')
+    m.load_state_dict(ck['parameters'])
+    m.eval()
+    m.set_eval_domain('toy'); ds[1].set_eval_domain('toy')
+    o = orc.OracleSASRec(ds[0].num_items, embed_dim=64)
+    o.load_state_dict(ck['parameters'])
+    o.eval()
+    uid, hist, tgt, slen, label, dom, _ = ds[1].data['toy']
+    batch = {'user_id': uid, 'in_item_id': hist, 'item_id': tgt, 'seqlen': slen, 'user_hist': hist}
+    ndcg, rec, ids_all = [], [], []
+    with torch.no_grad():
+        for s in range(0, len(uid), 2048):
+            b = {k: v[s:s + 2048] for k, v in batch.items()}
+            sc_r, id_r = m.topk(b, 100, b['user_hist'])
+            sc_o, id_o = o.topk(b, 100, m.domain_item_mapping['toy'])
+            assert torch.equal(id_r, id_o)
+            hit = orc.hit_matrix(id_r, b['item_id'])
+            ndcg.append(orc.ndcg_at_k(hit, 20)); rec.append(orc.recall_at_k(hit, 20))
+            ids_all.append(id_r)
+    ndcg, rec, ids_all = torch.cat(ndcg), torch.cat(rec), torch.cat(ids_all)
+    stored = ck['metric']
+    print('toys ckpt: ndcg@20', float(ndcg.mean()), 'recall@20', float(rec.mean()), 'stored', stored)
+    assert abs(float(ndcg.mean()) - float(stored['ndcg@20'])) < 5e-7
+    assert abs(float(rec.mean()) - float(stored['recall@20'])) < 5e-7
+    dom_items = np.asarray(sorted(m.domain_item_mapping['toy']), dtype=np.int32)
+    fx = {f'param/{k}': v.numpy() for k, v in ck['parameters'].items() if k not in ALIASES}
+    fx.update({
+        'val/in_item_id': hist.numpy().astype(np.int16), 'val/item_id': tgt.numpy().astype(np.int16),
+        'val/seqlen': slen.numpy().astype(np.int16), 'domain_items': dom_items,
+        'metric/ndcg@20': np.float64(stored['ndcg@20']), 'metric/recall@20': np.float64(stored['recall@20']),
+        'top100_first_users': ids_all[:n_users_topk].numpy().astype(np.int16),
+        'top20_all_users': ids_all[:, :20].numpy().astype(np.int16),
+        'num_items': np.int64(ds[0].num_items),
+    })
+    np.savez_compressed(os.path.join(HERE, 'toys_ckpt.npz'), **fx)
+    print('toys_ckpt.npz written', os.path.getsize(os.path.join(HERE, 'toys_ckpt.npz')) / 1e6, 'MB')
+
+
+if __name__ == '__main__':
+    run_case('SASRec', orc.OracleSASRec, dict(dropout_rate=0.0), N=300, D=64, B=6, layout='post', seed=11,
+             out='sasrec_d64.npz')
+    run_case('SASRec', orc.OracleSASRec, dict(dropout_rate=0.0), N=1000, D=128, B=16, layout='post', seed=12,
+             out='sasrec_d128.npz')
+    run_case('GRU4Rec', orc.OracleGRU4Rec, dict(dropout_rate=0.0, hidden_size=64), N=300, D=64, B=6, layout='post', seed=13,
+             out='gru4rec_d64.npz')
+    run_case('GRU4Rec', orc.OracleGRU4Rec, dict(dropout_rate=0.0, hidden_size=128), N=600, D=128, B=8, layout='post', seed=14,
+             out='gru4rec_d128.npz')
+    run_case('FMLP', orc.OracleFMLP, dict(dropout_rate=0.0), N=300, D=64, B=6, layout='pre', seed=15,
+             out='fmlp_d64.npz')
+    toys_checkpoint_case()
