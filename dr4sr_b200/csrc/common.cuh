@@ -1,0 +1,100 @@
+// common.cuh -- shared device/host helpers for libdr4sr (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/dr4sr.h"
+
+namespace dr4sr {
+
+constexpr int kWarp = 32;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- error plumbing (no exceptions cross the C ABI) -------------------------------------------
+void set_cuda_error(cudaError_t e, const char* where);
+#define DR4SR_LAUNCH_CHECK(where)                         \
+  do {                                                    \
+    cudaError_t e__ = cudaGetLastError();                 \
+    if (e__ != cudaSuccess) {                             \
+      ::dr4sr::set_cuda_error(e__, where);                \
+      return DR4SR_ECUDA;                                 \
+    }                                                     \
+  } while (0)
+#define DR4SR_TRY(expr)                                   \
+  do {                                                    \
+    int rc__ = (expr);                                    \
+    if (rc__ != DR4SR_OK) return rc__;                    \
+  } while (0)
+
+inline cudaStream_t as_stream(dr4sr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- counter-based RNG --------------------------------------------------------------------------
+// One 32-bit draw per (stream key, element index): murmur3-style finaliser over a Weyl-scrambled
+// index.  Stateless, so the backward regenerates exactly the forward's dropout masks from
+// (seed, step, site) without storing them.  Mirrored bit-for-bit in tests/rng_mirror.py.
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+__host__ __device__ __forceinline__ uint32_t stream_key(uint64_t seed, uint64_t step, uint32_t site) {
+  uint32_t k = mix32((uint32_t)seed ^ 0x9E3779B9u);
+  k = mix32(k ^ (uint32_t)(seed >> 32));
+  k = mix32(k ^ (uint32_t)step);
+  k = mix32(k ^ (uint32_t)(step >> 32) ^ (site * 0x632BE5ABu));
+  return k;
+}
+__host__ __device__ __forceinline__ uint32_t draw32(uint32_t key, uint32_t idx) {
+  return mix32(idx * 0x9E3779B1u + key) ^ mix32(key ^ (idx >> 7));
+}
+// dropout: keep iff draw >= thresh, thresh = round(p * 2^32) (p == 0 -> thresh 0 keeps everything)
+__host__ __device__ __forceinline__ uint32_t drop_thresh(float p) {
+  double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)(t + 0.5);
+}
+struct Dropout {
+  uint32_t key, thresh;
+  float scale;  // 1/(1-p)
+  __device__ __forceinline__ float apply(float x, uint32_t idx) const {
+    return (thresh == 0u || draw32(key, idx) >= thresh) ? x * scale : 0.0f;
+  }
+  __device__ __forceinline__ float factor(uint32_t idx) const {
+    return (thresh == 0u || draw32(key, idx) >= thresh) ? scale : 0.0f;
+  }
+};
+inline Dropout make_dropout(float p, uint64_t seed, uint64_t step, uint32_t site, bool train) {
+  Dropout d;
+  d.key = stream_key(seed, step, site);
+  d.thresh = (train && p > 0.f) ? drop_thresh(p) : 0u;
+  d.scale = (train && p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
+  return d;
+}
+// dropout sites of the SASRec step (distinct streams)
+enum : uint32_t { SITE_EMBED = 1, SITE_ATTN_P = 16, SITE_ATTN_OUT = 17, SITE_FFN_H = 18, SITE_FFN_OUT = 19 };
+inline uint32_t layer_site(uint32_t site, int layer) { return site + 8u * (uint32_t)layer; }
+
+// ---- warp helpers -------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// exact-erf GELU and its derivative (torch 'gelu', approximate='none')
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+// numerically stable log-sigmoid / softplus / sigmoid, same branches as ATen
+__device__ __forceinline__ float log_sigmoid_f(float x) { return fminf(x, 0.0f) - log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace dr4sr

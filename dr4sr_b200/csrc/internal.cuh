@@ -1,0 +1,29 @@
+// internal.cuh -- launcher prototypes shared between the translation units of libdr4sr.
+#pragma once
+#include "common.cuh"
+
+namespace dr4sr {
+
+// attention over packed rows, one CTA per (sequence, head)  [attention.cu]
+int launch_attn_fwd(const float* qkv, const int64_t* in_ids, const int32_t* tok_off, float* out, int B, int L, int D,
+                    int n_head, Dropout drop, cudaStream_t st);
+int launch_attn_bwd(const float* qkv, const float* d_out, const int64_t* in_ids, const int32_t* tok_off, float* d_qkv,
+                    int B, int L, int D, int n_head, Dropout drop, cudaStream_t st);
+
+// LayerNorm backward over packed rows + column partials  [rowops.cu]
+//   dz = LN'(dy; z, stats, gamma);  partials[blk][0..D) = sum dy*xhat, [D..2D) = sum dy,
+//   [2D..3D) = sum dz * bias_drop.factor (gradient of the bias that sits under the dropout before this LN)
+constexpr int kLnBwdBlocks = 2 * kNumSMs;
+int launch_ln_bwd(const float* dy, const float* z, const float* stats, const float* gamma, float* dz, float* partials,
+                  int D, int T_cap, const int32_t* tok_dev, Dropout bias_drop, cudaStream_t st);
+// column sums of x[T, N] -> partials[blk][N]
+constexpr int kColsumBlocks = 2 * kNumSMs;
+int launch_colsum(const float* x, int N, int T_cap, const int32_t* tok_dev, float* partials, cudaStream_t st);
+
+// out[e] = sum_s src[s * stride + e] for up to kMaxSeg segments in one launch
+constexpr int kMaxSeg = 16;
+struct ReduceSeg { const float* src; float* dst; int n_split; int64_t stride; int n; };
+struct ReduceTable { ReduceSeg seg[kMaxSeg]; int count; };
+int launch_reduce_segments(const ReduceTable& tab, cudaStream_t st);
+
+}  // namespace dr4sr

@@ -1,0 +1,245 @@
+// loss_table.cu -- sampled scoring + BCE (forward and backward in one pass), embedding-gradient
+// scatter-add, dense Adam.  All HBM-bound: one warp per row, 16-byte lanes, no intermediate [T,D]
+// gathers are materialised (the reference writes E[item_id], E[neg_item] and their products to HBM).
+#include "internal.cuh"
+
+namespace dr4sr {
+namespace {
+
+// One warp per (b, t) slot of the dense [B, L] target grid.
+//   t <  len : q = packed row; s+ = <q,E+>, s- = <q,E->  (skipped when item_id == 0)
+//   t >= len : the reference's 'origin' pooling has zeroed q, so a non-pad target there contributes
+//              (-logsig(0) + softplus(0)) / n and no gradient.
+__global__ void __launch_bounds__(256) score_bce_kernel(const float* __restrict__ q, const float* __restrict__ table,
+                                                        const int64_t* __restrict__ item_id, const int64_t* __restrict__ neg_item,
+                                                        const int32_t* __restrict__ tok_off, const int32_t* __restrict__ counts,
+                                                        int B, int L, int D, const float* __restrict__ loss_weight,
+                                                        const float* __restrict__ upstream, float* __restrict__ loss_pos,
+                                                        float* __restrict__ dscore, float* __restrict__ dq) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_valid = counts[1];
+  const float inv_n = 1.0f / (float)n_valid;
+  const float up = upstream ? *upstream : 1.0f;
+  const int total = B * L;
+  for (int slot = blockIdx.x * 8 + warp; slot < total; slot += gridDim.x * 8) {
+    const int b = slot / L, t = slot % L;
+    const int off = tok_off[b], len = tok_off[b + 1] - off;
+    const int64_t pid = item_id[slot];
+    const bool in_seq = t < len;
+    const int row = off + t;
+    if (pid == 0) {
+      if (lane == 0) loss_pos[slot] = 0.f;
+      if (in_seq) {
+        if (lane < 2) dscore[2 * (size_t)row + lane] = 0.f;
+        if (dq) for (int c = lane * 4; c < D; c += 128) *reinterpret_cast<float4*>(dq + (size_t)row * D + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      continue;
+    }
+    if (!in_seq) {
+      if (lane == 0) loss_pos[slot] = (0.69314718055994531f + 0.69314718055994531f) * inv_n;
+      continue;
+    }
+    const int64_t nid = neg_item[slot];
+    const float* qr = q + (size_t)row * D;
+    const float* ep = table + (size_t)pid * D;
+    const float* en = table + (size_t)nid * D;
+    float sp = 0.f, sn = 0.f;
+    float4 qv[2], pv[2], nv[2];   // D <= 256
+    int k = 0;
+    for (int c = lane * 4; c < D; c += 128, ++k) {
+      qv[k] = *reinterpret_cast<const float4*>(qr + c);
+      pv[k] = *reinterpret_cast<const float4*>(ep + c);
+      nv[k] = *reinterpret_cast<const float4*>(en + c);
+      sp += (qv[k].x * pv[k].x + qv[k].y * pv[k].y) + (qv[k].z * pv[k].z + qv[k].w * pv[k].w);
+      sn += (qv[k].x * nv[k].x + qv[k].y * nv[k].y) + (qv[k].z * nv[k].z + qv[k].w * nv[k].w);
+    }
+    sp = warp_sum(sp);
+    sn = warp_sum(sn);
+    const float w = (loss_weight ? loss_weight[slot] : 1.0f);
+    if (lane == 0) loss_pos[slot] = (-log_sigmoid_f(sp) + softplus_f(sn)) * inv_n;
+    const float dsp = -sigmoid_f(-sp) * inv_n * w * up;
+    const float dsn = sigmoid_f(sn) * inv_n * w * up;
+    if (lane == 0) { dscore[2 * (size_t)row] = dsp; dscore[2 * (size_t)row + 1] = dsn; }
+    if (dq) {
+      k = 0;
+      for (int c = lane * 4; c < D; c += 128, ++k) {
+        float4 o;
+        o.x = dsp * pv[k].x + dsn * nv[k].x; o.y = dsp * pv[k].y + dsn * nv[k].y;
+        o.z = dsp * pv[k].z + dsn * nv[k].z; o.w = dsp * pv[k].w + dsn * nv[k].w;
+        *reinterpret_cast<float4*>(dq + (size_t)row * D + c) = o;
+      }
+    }
+  }
+}
+
+// fixed-shape tree: every thread strides the array, then a block reduction; single CTA => deterministic
+__global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = warp_sum(s);
+  __shared__ float part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = part[threadIdx.x];
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// dE[in_id] += dx0 ; dE[item_id] += ds+ q ; dE[neg] += ds- q.  One warp per packed row, vector reds into L2.
+__global__ void __launch_bounds__(256) table_grad_kernel(const float* __restrict__ dx0, const float* __restrict__ q,
+                                                         const float* __restrict__ dscore, const int64_t* __restrict__ in_ids,
+                                                         const int64_t* __restrict__ item_id, const int64_t* __restrict__ neg_item,
+                                                         const int32_t* __restrict__ tok_off, const int32_t* __restrict__ row_seq,
+                                                         const int32_t* __restrict__ counts, int L, int D, float* __restrict__ tg) {
+  const int T = counts[0];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 8 + warp; row < T; row += gridDim.x * 8) {
+    const int b = row_seq[row];
+    const int t = row - tok_off[b];
+    const size_t slot = (size_t)b * L + t;
+    const int64_t iid = in_ids[slot];
+    if (dx0 && iid != 0) {   // padding_idx = 0 receives no gradient (nn.Embedding)
+      for (int c = lane * 4; c < D; c += 128)
+        red_add_v4(tg + (size_t)iid * D + c, *reinterpret_cast<const float4*>(dx0 + (size_t)row * D + c));
+    }
+    const int64_t pid = item_id ? item_id[slot] : 0;
+    if (pid != 0) {
+      const float dsp = dscore[2 * (size_t)row], dsn = dscore[2 * (size_t)row + 1];
+      const int64_t nid = neg_item[slot];
+      for (int c = lane * 4; c < D; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(q + (size_t)row * D + c);
+        red_add_v4(tg + (size_t)pid * D + c, make_float4(dsp * v.x, dsp * v.y, dsp * v.z, dsp * v.w));
+        red_add_v4(tg + (size_t)nid * D + c, make_float4(dsn * v.x, dsn * v.y, dsn * v.z, dsn * v.w));
+      }
+    }
+  }
+}
+
+// dP[t] = sum over sequences with len > t of dx0[(b,t)]: grid (L, D/128 chunks); fixed order over b.
+__global__ void __launch_bounds__(128) pos_grad_kernel(const float* __restrict__ dx0, const int32_t* __restrict__ tok_off, int B,
+                                                       int D, float* __restrict__ pos_grad) {
+  const int t = blockIdx.x;
+  const int col = blockIdx.y * 128 + threadIdx.x;
+  if (col >= D) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 3 < B; b += 4) {
+    const int o0 = tok_off[b], o1 = tok_off[b + 1], o2 = tok_off[b + 2], o3 = tok_off[b + 3], o4 = tok_off[b + 4];
+    if (o1 - o0 > t) s0 += dx0[(size_t)(o0 + t) * D + col];
+    if (o2 - o1 > t) s1 += dx0[(size_t)(o1 + t) * D + col];
+    if (o3 - o2 > t) s2 += dx0[(size_t)(o2 + t) * D + col];
+    if (o4 - o3 > t) s3 += dx0[(size_t)(o3 + t) * D + col];
+  }
+  for (; b < B; ++b) {
+    const int o0 = tok_off[b];
+    if (tok_off[b + 1] - o0 > t) s0 += dx0[(size_t)(o0 + t) * D + col];
+  }
+  pos_grad[(size_t)t * D + col] = (s0 + s1) + (s2 + s3);
+}
+
+// torch.optim.Adam (_single_tensor_adam op order): g += wd p; m = lerp(m, g, 1-b1);
+// v = b2 v + (1-b2) g g; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n4, int64_t n, float step_size,
+                                                   float inv_bc2_sqrt, float b1, float b2, float eps, float wd, int zero_grad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gk = G[k];
+      if (wd != 0.f) gk = fmaf(wd, P[k], gk);
+      M[k] = M[k] + (gk - M[k]) * (1.0f - b1);
+      V[k] = V[k] * b2 + (1.0f - b2) * gk * gk;
+      const float denom = sqrtf(V[k]) * inv_bc2_sqrt + eps;
+      P[k] = P[k] - step_size * (M[k] / denom);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // scalar tail (n not a multiple of 4)
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gk = g[i];
+    if (wd != 0.f) gk = fmaf(wd, p[i], gk);
+    const float mk = m[i] + (gk - m[i]) * (1.0f - b1);
+    const float vk = v[i] * b2 + (1.0f - b2) * gk * gk;
+    p[i] = p[i] - step_size * (mk / (sqrtf(vk) * inv_bc2_sqrt + eps));
+    m[i] = mk; v[i] = vk;
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+}  // namespace
+}  // namespace dr4sr
+
+using namespace dr4sr;
+
+extern "C" int dr4sr_score_bce(const float* q_packed, const float* table, const int64_t* item_id, const int64_t* neg_item,
+                               const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                               int32_t D, const float* loss_weight, const float* upstream, float* loss_pos, float* dscore,
+                               float* dq_packed, dr4sr_stream_t stream) {
+  (void)row_seq;
+  if (!q_packed || !table || !item_id || !neg_item || !tok_off || !counts || !loss_pos || !dscore) return DR4SR_EINVAL;
+  if (D % 4 || D > 256) return DR4SR_EINVAL;
+  const int total = B * L;
+  const int blocks = ceil_div(total, 8) < 8 * kNumSMs ? ceil_div(total, 8) : 8 * kNumSMs;
+  score_bce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(q_packed, table, item_id, neg_item, tok_off, counts, B, L, D,
+                                                           loss_weight, upstream, loss_pos, dscore, dq_packed);
+  DR4SR_LAUNCH_CHECK("score_bce_kernel");
+  return DR4SR_OK;
+}
+
+extern "C" int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t stream) {
+  if (!x || !out || n < 0) return DR4SR_EINVAL;
+  sum_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, out);
+  DR4SR_LAUNCH_CHECK("sum_kernel");
+  return DR4SR_OK;
+}
+
+extern "C" int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, const float* dscore,
+                                const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
+                                const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                                int32_t D, int64_t N, float* table_grad, float* pos_grad, dr4sr_stream_t stream) {
+  (void)N;
+  if (!in_item_id || !tok_off || !row_seq || !counts || !table_grad || D % 4) return DR4SR_EINVAL;
+  if (item_id && (!q_packed || !dscore || !neg_item)) return DR4SR_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  const int T_cap = B * L;
+  const int blocks = ceil_div(T_cap, 8) < 8 * kNumSMs ? ceil_div(T_cap, 8) : 8 * kNumSMs;
+  table_grad_kernel<<<blocks, 256, 0, st>>>(dx0_packed, q_packed, dscore, in_item_id, item_id, neg_item, tok_off, row_seq,
+                                            counts, L, D, table_grad);
+  DR4SR_LAUNCH_CHECK("table_grad_kernel");
+  if (pos_grad && dx0_packed) {
+    pos_grad_kernel<<<dim3(L, ceil_div(D, 128)), 128, 0, st>>>(dx0_packed, tok_off, B, D, pos_grad);
+    DR4SR_LAUNCH_CHECK("pos_grad_kernel");
+  }
+  return DR4SR_OK;
+}
+
+extern "C" int dr4sr_adam(float* p, float* g, float* m, float* v, int64_t n, int64_t step, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int32_t zero_grad, dr4sr_stream_t stream) {
+  if (!p || !g || !m || !v || n < 0 || step < 1) return DR4SR_EINVAL;
+  if (n == 0) return DR4SR_OK;
+  if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return DR4SR_EINVAL;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  const int64_t n4 = n / 4;
+  int64_t want = (n4 + 255) / 256;
+  const int blocks = (int)(want < 1 ? 1 : (want > 16 * kNumSMs ? 16 * kNumSMs : want));
+  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, step_size, inv_bc2_sqrt, beta1, beta2, eps,
+                                                     weight_decay, zero_grad);
+  DR4SR_LAUNCH_CHECK("adam_kernel");
+  return DR4SR_OK;
+}

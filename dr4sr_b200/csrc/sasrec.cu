@@ -1,0 +1,317 @@
+// sasrec.cu -- SASRec encoder forward / backward over packed rows (orchestration of the kernels).
+//
+// Replaces SASRecQueryEncoder.forward (reference model/sasrec.py:39-75) = embedding + learned
+// positions + dropout -> 2 x post-norm TransformerEncoderLayer (model/sasrec.py:21-34) -> pooling,
+// and its autograd backward.  Spec: SURVEY.md Appendix C.1, C.2, C.5.
+#include "gemm_simt.cuh"
+#include "internal.cuh"
+
+namespace dr4sr {
+namespace {
+
+constexpr int kSplit = 32;   // token splits of the weight-gradient GEMMs (partials reduced in fixed order)
+
+struct LayerOffsets {   // offsets (floats) inside one layer's slice of the flat parameter buffer
+  size_t in_w, in_b, out_w, out_b, w1, b1, w2, b2, g1, be1, g2, be2, total;
+};
+LayerOffsets layer_offsets(int D, int F) {
+  LayerOffsets o;
+  size_t p = 0;
+  o.in_w = p; p += (size_t)3 * D * D;
+  o.in_b = p; p += (size_t)3 * D;
+  o.out_w = p; p += (size_t)D * D;
+  o.out_b = p; p += D;
+  o.w1 = p; p += (size_t)F * D;
+  o.b1 = p; p += F;
+  o.w2 = p; p += (size_t)D * F;
+  o.b2 = p; p += D;
+  o.g1 = p; p += D;
+  o.be1 = p; p += D;
+  o.g2 = p; p += D;
+  o.be2 = p; p += D;
+  o.total = p;
+  return o;
+}
+
+struct Workspace {
+  // saved activations
+  float* x0;
+  struct Layer { float *qkv, *attn, *z1, *st1, *x1, *pre, *z2, *st2, *x2; } layer[8];
+  // backward scratch
+  float *g0, *g1, *g2, *dqkv, *dpre;
+  float *part_w;     // [kSplit][3DD + DD + FD + DF] weight-gradient partials of the current layer
+  float *part_ln2, *part_ln1;   // [kLnBwdBlocks][3D]
+  float *part_cs_in, *part_cs_b1;   // [kColsumBlocks][3D], [kColsumBlocks][F]
+  size_t bytes;
+};
+
+inline size_t align_up(size_t x) { return (x + 63) & ~(size_t)63; }   // 256-byte granules (in floats: 64)
+
+Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
+  Workspace w{};
+  float* p = reinterpret_cast<float*>(base);
+  size_t off = 0;
+  const size_t T = (size_t)c.B * c.L, D = c.D, F = c.F;
+  auto take = [&](size_t n) { float* r = p ? p + off : nullptr; off += align_up(n); return r; };
+  w.x0 = take(T * D);
+  for (int l = 0; l < c.n_layer; ++l) {
+    auto& y = w.layer[l];
+    y.qkv = take(T * 3 * D); y.attn = take(T * D); y.z1 = take(T * D); y.st1 = take(T * 2); y.x1 = take(T * D);
+    y.pre = take(T * F); y.z2 = take(T * D); y.st2 = take(T * 2); y.x2 = take(T * D);
+  }
+  w.g0 = take(T * D); w.g1 = take(T * D); w.g2 = take(T * D); w.dqkv = take(T * 3 * D); w.dpre = take(T * F);
+  w.part_w = take((size_t)kSplit * (3 * D * D + D * D + 2 * F * D));
+  w.part_ln2 = take((size_t)kLnBwdBlocks * 3 * D);
+  w.part_ln1 = take((size_t)kLnBwdBlocks * 3 * D);
+  w.part_cs_in = take((size_t)kColsumBlocks * 3 * D);
+  w.part_cs_b1 = take((size_t)kColsumBlocks * F);
+  w.bytes = off * sizeof(float);
+  return w;
+}
+
+int check_cfg(const dr4sr_sasrec_cfg* c) {
+  if (!c) return DR4SR_EINVAL;
+  if (c->B <= 0 || c->L <= 0 || c->L > 64 || c->n_layer < 1 || c->n_layer > 8) return DR4SR_EINVAL;
+  if (c->D != 64 && c->D != 128) return DR4SR_EINVAL;            // LN-epilogue tiles are instantiated for these
+  if (c->F % 64 || c->F <= 0 || c->F > 1024) return DR4SR_EINVAL;
+  if (c->n_head <= 0 || c->D % c->n_head || (c->D / c->n_head) % 4) return DR4SR_EINVAL;
+  if (c->dropout_p < 0.f || c->dropout_p >= 1.f) return DR4SR_EINVAL;
+  return DR4SR_OK;
+}
+
+// y = LN(drop(A W^T + b) + res), rows complete inside a CTA (BN == D)
+int gemm_ln(GemmArgs& g, int D, cudaStream_t st) {
+  if (D == 128) return launch_gemm<64, 128, true, true, true>(g, st);
+  return launch_gemm<64, 64, true, true, true>(g, st);
+}
+int gemm_nt(GemmArgs& g, cudaStream_t st) {
+  if (g.N >= 256) return launch_gemm<128, 128, true, true, false>(g, st);
+  if (g.N > 64) return launch_gemm<64, 128, true, true, false>(g, st);
+  return launch_gemm<64, 64, true, true, false>(g, st);
+}
+int gemm_nn(GemmArgs& g, cudaStream_t st) {
+  if (g.N >= 256) return launch_gemm<128, 128, true, false, false>(g, st);
+  if (g.N > 64) return launch_gemm<64, 128, true, false, false>(g, st);
+  return launch_gemm<64, 64, true, false, false>(g, st);
+}
+int gemm_tn(GemmArgs& g, float* partial, cudaStream_t st) {   // C partials [kSplit][M*N]
+  g.C = partial; g.n_split = kSplit; g.split_stride = (int64_t)g.M * g.N; g.ldc = g.N;
+  return launch_gemm<64, 64, false, false, false>(g, st);
+}
+
+__global__ void __launch_bounds__(256) gather_last_kernel(const float* __restrict__ x, const int32_t* __restrict__ tok_off, int B,
+                                                          int D, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
+    const int end = tok_off[b + 1], len = end - tok_off[b];
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (len > 0) v = *reinterpret_cast<const float4*>(x + (size_t)(end - 1) * D + c);
+      *reinterpret_cast<float4*>(out + (size_t)b * D + c) = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_dense_kernel(const float* __restrict__ x, const int32_t* __restrict__ tok_off, int B,
+                                                           int L, int D, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int slot = blockIdx.x * 8 + warp; slot < B * L; slot += gridDim.x * 8) {
+    const int b = slot / L, t = slot % L;
+    const int off = tok_off[b], len = tok_off[b + 1] - off;
+    for (int c = lane * 4; c < D; c += 128) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < len) v = *reinterpret_cast<const float4*>(x + (size_t)(off + t) * D + c);
+      *reinterpret_cast<float4*>(out + (size_t)slot * D + c) = v;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace dr4sr
+
+using namespace dr4sr;
+
+extern "C" size_t dr4sr_sasrec_param_count(const dr4sr_sasrec_cfg* c) {
+  if (check_cfg(c) != DR4SR_OK) return 0;
+  return (size_t)c->L * c->D + (size_t)c->n_layer * layer_offsets(c->D, c->F).total;
+}
+
+extern "C" size_t dr4sr_sasrec_workspace_bytes(const dr4sr_sasrec_cfg* c) {
+  if (check_cfg(c) != DR4SR_OK) return 0;
+  return carve(*c, nullptr).bytes;
+}
+
+extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, const float* params,
+                                const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                                const int32_t* counts, void* ws, size_t ws_bytes, int32_t train, float* q_packed,
+                                float* q_last, float* q_dense, dr4sr_stream_t stream) {
+  DR4SR_TRY(check_cfg(c));
+  if (!table || !params || !in_item_id || !tok_off || !row_seq || !counts || !ws) return DR4SR_EINVAL;
+  Workspace w = carve(*c, ws);
+  if (ws_bytes < w.bytes) return DR4SR_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int T = c->B * c->L, D = c->D, F = c->F;
+  const bool tr = train != 0;
+  const float p = c->dropout_p;
+  const LayerOffsets lo = layer_offsets(D, F);
+  const float* pos = params;
+
+  {  // K1: gather + positions + dropout
+    const Dropout drop = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
+    DR4SR_TRY(dr4sr_embed_fwd(table, pos, in_item_id, tok_off, row_seq, counts, c->B, c->L, D, tr ? p : 0.f, c->seed, c->step,
+                              w.x0, stream));
+    (void)drop;
+  }
+  const float* x = w.x0;
+  for (int l = 0; l < c->n_layer; ++l) {
+    const float* lp = params + (size_t)c->L * D + (size_t)l * lo.total;
+    auto& y = w.layer[l];
+    float* x2 = (l == c->n_layer - 1 && q_packed) ? q_packed : y.x2;
+    {  // QKV projection
+      GemmArgs g = gemm_args(x, D, lp + lo.in_w, D, y.qkv, 3 * D, T, 3 * D, D, counts);
+      g.bias = lp + lo.in_b;
+      DR4SR_TRY(gemm_nt(g, st));
+    }
+    DR4SR_TRY(launch_attn_fwd(y.qkv, in_item_id, tok_off, y.attn, c->B, c->L, D, c->n_head,
+                              make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr), st));
+    {  // out-proj + dropout + residual + LN1
+      GemmArgs g = gemm_args(y.attn, D, lp + lo.out_w, D, y.x1, D, T, D, D, counts);
+      g.bias = lp + lo.out_b; g.add = x; g.ldadd = D;
+      g.dropE = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_OUT, l), tr);
+      g.gamma = lp + lo.g1; g.beta = lp + lo.be1; g.ln_eps = c->ln_eps; g.Z = y.z1; g.stats = y.st1;
+      DR4SR_TRY(gemm_ln(g, D, st));
+    }
+    {  // FFN up-projection (pre-activation kept for the backward)
+      GemmArgs g = gemm_args(y.x1, D, lp + lo.w1, D, y.pre, F, T, F, D, counts);
+      g.bias = lp + lo.b1;
+      DR4SR_TRY(gemm_nt(g, st));
+    }
+    {  // gelu + dropout (prologue) -> down-projection + dropout + residual + LN2
+      GemmArgs g = gemm_args(y.pre, F, lp + lo.w2, F, x2, D, T, D, F, counts);
+      g.proA = PRO_GELU_DROP; g.dropA = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_H, l), tr);
+      g.bias = lp + lo.b2; g.add = y.x1; g.ldadd = D;
+      g.dropE = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_OUT, l), tr);
+      g.gamma = lp + lo.g2; g.beta = lp + lo.be2; g.ln_eps = c->ln_eps; g.Z = y.z2; g.stats = y.st2;
+      DR4SR_TRY(gemm_ln(g, D, st));
+    }
+    x = x2;
+  }
+  if (q_last) {
+    gather_last_kernel<<<ceil_div(c->B, 8), 256, 0, st>>>(x, tok_off, c->B, D, q_last);
+    DR4SR_LAUNCH_CHECK("gather_last_kernel");
+  }
+  if (q_dense) {
+    const int blocks = ceil_div(T, 8) < 8 * kNumSMs ? ceil_div(T, 8) : 8 * kNumSMs;
+    unpack_dense_kernel<<<blocks, 256, 0, st>>>(x, tok_off, c->B, c->L, D, q_dense);
+    DR4SR_LAUNCH_CHECK("unpack_dense_kernel");
+  }
+  return DR4SR_OK;
+}
+
+extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, const float* params,
+                                const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                                const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed, float* grads,
+                                float* dx0_packed, dr4sr_stream_t stream) {
+  (void)table; (void)row_seq;
+  DR4SR_TRY(check_cfg(c));
+  if (!params || !in_item_id || !tok_off || !counts || !ws || !dq_packed || !grads || !dx0_packed) return DR4SR_EINVAL;
+  Workspace w = carve(*c, ws);
+  if (ws_bytes < w.bytes) return DR4SR_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int T = c->B * c->L, D = c->D, F = c->F;
+  const float p = c->dropout_p;
+  const bool tr = p > 0.f;   // the backward mirrors whatever masks the forward drew (p == 0 -> none)
+  const LayerOffsets lo = layer_offsets(D, F);
+  const size_t pw_in = 0, pw_out = (size_t)kSplit * 3 * D * D, pw_w1 = pw_out + (size_t)kSplit * D * D,
+               pw_w2 = pw_w1 + (size_t)kSplit * F * D;
+
+  float* gin = dq_packed;   // gradient w.r.t. the current layer's output
+  for (int l = c->n_layer - 1; l >= 0; --l) {
+    const float* lp = params + (size_t)c->L * D + (size_t)l * lo.total;
+    float* lg = grads + (size_t)c->L * D + (size_t)l * lo.total;
+    auto& y = w.layer[l];
+    const float* xin = l == 0 ? w.x0 : w.layer[l - 1].x2;
+    const Dropout d_ffn_out = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_OUT, l), tr);
+    const Dropout d_ffn_h = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_H, l), tr);
+    const Dropout d_attn_out = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_OUT, l), tr);
+    const Dropout d_attn_p = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr);
+
+    // LN2 backward: g1 = dz2 ; partials -> dgamma2, dbeta2, db2
+    DR4SR_TRY(launch_ln_bwd(gin, y.z2, y.st2, lp + lo.g2, w.g1, w.part_ln2, D, T, counts, d_ffn_out, st));
+    {  // dpre = ((dz2 * mask_out) W2) * mask_h * gelu'(pre)
+      GemmArgs g = gemm_args(w.g1, D, lp + lo.w2, F, w.dpre, F, T, F, D, counts);
+      g.proA = PRO_DROPMASK; g.dropA = d_ffn_out;
+      g.epi = EPI_GELU_BWD; g.pre = y.pre; g.dropE = d_ffn_h;
+      DR4SR_TRY(gemm_nn(g, st));
+    }
+    {  // dW2[d,f] = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]
+      GemmArgs g = gemm_args(w.g1, D, y.pre, F, nullptr, F, D, F, T, counts);
+      g.proA = PRO_DROPMASK; g.dropA = d_ffn_out; g.proB = PRO_GELU_DROP; g.dropB = d_ffn_h;
+      DR4SR_TRY(gemm_tn(g, w.part_w + pw_w2, st));
+    }
+    {  // dW1[f,d] = sum_m dpre[m,f] * x1[m,d]
+      GemmArgs g = gemm_args(w.dpre, F, y.x1, D, nullptr, D, F, D, T, counts);
+      DR4SR_TRY(gemm_tn(g, w.part_w + pw_w1, st));
+    }
+    DR4SR_TRY(launch_colsum(w.dpre, F, T, counts, w.part_cs_b1, st));
+    {  // dx1 = dz2 + dpre W1   -> g0
+      GemmArgs g = gemm_args(w.dpre, F, lp + lo.w1, D, w.g0, D, T, D, F, counts);
+      g.add = w.g1; g.ldadd = D;
+      DR4SR_TRY(gemm_nn(g, st));
+    }
+    // LN1 backward: g1 = dz1 ; partials -> dgamma1, dbeta1, db_out
+    DR4SR_TRY(launch_ln_bwd(w.g0, y.z1, y.st1, lp + lo.g1, w.g1, w.part_ln1, D, T, counts, d_attn_out, st));
+    {  // d(attn) = (dz1 * mask) Wo -> g2
+      GemmArgs g = gemm_args(w.g1, D, lp + lo.out_w, D, w.g2, D, T, D, D, counts);
+      g.proA = PRO_DROPMASK; g.dropA = d_attn_out;
+      DR4SR_TRY(gemm_nn(g, st));
+    }
+    {  // dWo[n,k] = sum_m (dz1*mask)[m,n] * attn[m,k]
+      GemmArgs g = gemm_args(w.g1, D, y.attn, D, nullptr, D, D, D, T, counts);
+      g.proA = PRO_DROPMASK; g.dropA = d_attn_out;
+      DR4SR_TRY(gemm_tn(g, w.part_w + pw_out, st));
+    }
+    DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, w.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
+    {  // dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
+      GemmArgs g = gemm_args(w.dqkv, 3 * D, xin, D, nullptr, D, 3 * D, D, T, counts);
+      DR4SR_TRY(gemm_tn(g, w.part_w + pw_in, st));
+    }
+    DR4SR_TRY(launch_colsum(w.dqkv, 3 * D, T, counts, w.part_cs_in, st));
+    {  // dx = dz1 + dqkv Win  (layer 0: times the embedding-dropout mask) -> g0 / dx0
+      float* dst = l == 0 ? dx0_packed : w.g0;
+      GemmArgs g = gemm_args(w.dqkv, 3 * D, lp + lo.in_w, D, dst, D, T, D, 3 * D, counts);
+      g.add = w.g1; g.ldadd = D;
+      if (l == 0) g.dropE = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
+      DR4SR_TRY(gemm_nn(g, st));
+    }
+    {  // fixed-order reduction of every partial of this layer into the flat gradient buffer
+      ReduceTable tab{};
+      int k = 0;
+      auto seg = [&](const float* src, float* dst, int ns, int64_t stride, int n) { tab.seg[k++] = ReduceSeg{src, dst, ns, stride, n}; };
+      seg(w.part_w + pw_in, lg + lo.in_w, kSplit, (int64_t)3 * D * D, 3 * D * D);
+      seg(w.part_w + pw_out, lg + lo.out_w, kSplit, (int64_t)D * D, D * D);
+      seg(w.part_w + pw_w1, lg + lo.w1, kSplit, (int64_t)F * D, F * D);
+      seg(w.part_w + pw_w2, lg + lo.w2, kSplit, (int64_t)D * F, D * F);
+      seg(w.part_cs_in, lg + lo.in_b, kColsumBlocks, 3 * D, 3 * D);
+      seg(w.part_cs_b1, lg + lo.b1, kColsumBlocks, F, F);
+      seg(w.part_ln1, lg + lo.g1, kLnBwdBlocks, 3 * D, D);
+      seg(w.part_ln1 + D, lg + lo.be1, kLnBwdBlocks, 3 * D, D);
+      seg(w.part_ln1 + 2 * D, lg + lo.out_b, kLnBwdBlocks, 3 * D, D);
+      seg(w.part_ln2, lg + lo.g2, kLnBwdBlocks, 3 * D, D);
+      seg(w.part_ln2 + D, lg + lo.be2, kLnBwdBlocks, 3 * D, D);
+      seg(w.part_ln2 + 2 * D, lg + lo.b2, kLnBwdBlocks, 3 * D, D);
+      tab.count = k;
+      DR4SR_TRY(launch_reduce_segments(tab, st));
+    }
+    gin = w.g0;
+  }
+  return DR4SR_OK;
+}
+
+extern "C" int dr4sr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int32_t M, int32_t N, int32_t K,
+                                const int32_t* m_dev, dr4sr_stream_t stream) {
+  if (!x || !w || !y || M <= 0 || N % 4 || K % 4) return DR4SR_EINVAL;
+  GemmArgs g = gemm_args(x, K, w, K, y, N, M, N, K, m_dev);
+  g.bias = bias;
+  return gemm_nt(g, as_stream(stream));
+}

@@ -1,0 +1,175 @@
+// topk.cu -- full-catalog scoring + top-k, replaces BaseModel.topk (reference model/basemodel.py:354-365).
+//
+//   scores = q @ E[:N].T ; -inf at ids outside the eval domain and at the user's history ; top-k.
+// Round-1 structure: exact-fp32 FFMA GEMM with the domain mask folded in as a column bias (0 / -inf),
+// a scatter of -inf at the history ids, then one CTA per row doing an 8-bit MSD radix select for the
+// k-th key followed by an index-ordered gather and a bitonic sort of the k survivors.
+// Ties are broken by the lower item id (deterministic; torch.topk leaves tie order unspecified).
+#include "gemm_simt.cuh"
+#include "internal.cuh"
+
+namespace dr4sr {
+namespace {
+
+// column bias of the scoring GEMM: 0 for live items, -inf for dead ones and for the row padding
+__global__ void __launch_bounds__(256) dead_bias_kernel(const uint8_t* __restrict__ dead, int64_t N, int64_t n_al,
+                                                        float* __restrict__ bias) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_al; i += (int64_t)gridDim.x * blockDim.x)
+    bias[i] = (i >= N || (dead && dead[i])) ? -INFINITY : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) mask_hist_kernel(const int64_t* __restrict__ hist, int B, int H, int64_t N, int64_t ld,
+                                                        float* __restrict__ scores) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int64_t id = hist[i];
+  if (id >= 0 && id < N) scores[(size_t)(i / H) * ld + id] = -INFINITY;
+}
+
+// monotone map float -> uint32 (larger float => larger key); -inf -> smallest finite-class key
+__device__ __forceinline__ uint32_t order_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+constexpr int kSelThreads = 512;
+
+__global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const float* __restrict__ scores, int64_t N, int64_t ld, int k,
+                                                                  int kpad, float* __restrict__ out_scores,
+                                                                  int64_t* __restrict__ out_ids) {
+  extern __shared__ uint32_t sm_u[];
+  uint32_t* hist = sm_u;                       // [256]
+  uint32_t* ck = hist + 256;                   // [kpad] candidate keys
+  int32_t* ci = reinterpret_cast<int32_t*>(ck + kpad);   // [kpad] candidate ids
+  __shared__ uint32_t s_prefix, s_mask;
+  __shared__ int s_need, s_base, s_tiebase, s_warp[kSelThreads / 32][2];
+  const float* row = scores + (size_t)blockIdx.x * ld;
+  const int tid = threadIdx.x;
+
+  // ---- radix select: find key K such that count(key > K) < k <= count(key >= K) ----
+  if (tid == 0) { s_prefix = 0u; s_mask = 0u; s_need = k; }
+  __syncthreads();
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0u;
+    __syncthreads();
+    const uint32_t prefix = s_prefix, mask = s_mask;
+    for (int64_t start = 0; start < N; start += kSelThreads) {   // uniform trip count: match_any needs full warps
+      const int64_t i = start + tid;
+      bool live = false;
+      uint32_t digit = 0x100u | (uint32_t)(tid & 31);              // unique per lane => never aggregated
+      if (i < N) {
+        const uint32_t key = order_key(row[i]);
+        if ((key & mask) == prefix) { live = true; digit = (key >> shift) & 255u; }
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, digit);  // warp-aggregated histogram update
+      if (live && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = s_need;
+      int d = 255;
+      for (; d > 0; --d) {
+        const int c = (int)hist[d];
+        if (c >= need) break;
+        need -= c;
+      }
+      s_need = need;   // how many of the selected digit's bucket still belong to the top-k
+      s_prefix = prefix | ((uint32_t)d << shift);
+      s_mask = mask | (255u << shift);
+    }
+    __syncthreads();
+  }
+  const uint32_t kth = s_prefix;
+  const int n_tie = s_need;              // elements equal to kth that are kept (lowest ids first)
+  const int n_gt = k - n_tie;
+
+  // ---- ordered gather: keys > kth to slots [0, n_gt), first n_tie keys == kth to [n_gt, k) ----
+  if (tid == 0) { s_base = 0; s_tiebase = 0; }
+  for (int i = tid; i < kpad; i += kSelThreads) { ck[i] = 0u; ci[i] = 0x7fffffff; }
+  __syncthreads();
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int64_t start = 0; start < N; start += kSelThreads) {
+    const int64_t i = start + tid;
+    uint32_t key = 0u;
+    bool gt = false, eq = false;
+    if (i < N) { key = order_key(row[i]); gt = key > kth; eq = key == kth; }
+    const uint32_t bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) { s_warp[warp][0] = __popc(bg); s_warp[warp][1] = __popc(be); }
+    __syncthreads();
+    int og = s_base, oe = s_tiebase;
+    for (int wv = 0; wv < warp; ++wv) { og += s_warp[wv][0]; oe += s_warp[wv][1]; }
+    og += __popc(bg & ((1u << lane) - 1u));
+    oe += __popc(be & ((1u << lane) - 1u));
+    if (gt) { ck[og] = key; ci[og] = (int32_t)i; }
+    if (eq && oe < n_tie) { ck[n_gt + oe] = key; ci[n_gt + oe] = (int32_t)i; }
+    __syncthreads();
+    if (tid == 0) {
+      int tg = 0, te = 0;
+      for (int wv = 0; wv < kSelThreads / 32; ++wv) { tg += s_warp[wv][0]; te += s_warp[wv][1]; }
+      s_base += tg; s_tiebase += te;
+    }
+    __syncthreads();
+  }
+
+  // ---- bitonic sort of kpad (key desc, id asc); padding entries (key 0, id max) sink to the end ----
+  for (int size = 2; size <= kpad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < kpad; i += kSelThreads) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;   // 'up' blocks hold the better elements first
+          const uint32_t ki = ck[i], kj = ck[j];
+          const int32_t ii = ci[i], ij = ci[j];
+          const bool i_better = ki > kj || (ki == kj && ii < ij);
+          if (up ? !i_better : i_better) { ck[i] = kj; ck[j] = ki; ci[i] = ij; ci[j] = ii; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += kSelThreads) {
+    const int32_t id = ci[i];
+    out_ids[(size_t)blockIdx.x * k + i] = id;
+    out_scores[(size_t)blockIdx.x * k + i] = row[id];
+  }
+}
+
+}  // namespace
+}  // namespace dr4sr
+
+using namespace dr4sr;
+
+extern "C" size_t dr4sr_topk_workspace_bytes(int32_t B, int64_t N, int32_t k) {
+  (void)k;
+  const size_t n_al = ((size_t)N + 127) & ~(size_t)127;
+  return sizeof(float) * ((size_t)B * n_al + n_al) + 256;
+}
+
+extern "C" int dr4sr_topk(const float* q, const float* table, const uint8_t* item_dead, const int64_t* user_hist, int32_t B,
+                          int32_t D, int64_t N, int32_t H, int32_t k, float* out_scores, int64_t* out_ids, void* ws,
+                          size_t ws_bytes, dr4sr_stream_t stream) {
+  if (!q || !table || !out_scores || !out_ids || !ws || B <= 0 || D % 4 || N <= 0 || N > 0x7fffff00) return DR4SR_EINVAL;
+  if (k <= 0 || k > 1024 || k > N) return DR4SR_EINVAL;
+  if (ws_bytes < dr4sr_topk_workspace_bytes(B, N, k)) return DR4SR_EWORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const size_t n_al = ((size_t)N + 127) & ~(size_t)127;   // padded row stride: 16-byte stores, whole tiles
+  float* bias = reinterpret_cast<float*>(ws);
+  float* scores = bias + n_al;
+  dead_bias_kernel<<<ceil_div(n_al, 256) < 4 * kNumSMs ? ceil_div(n_al, 256) : 4 * kNumSMs, 256, 0, st>>>(item_dead, N, (int64_t)n_al, bias);
+  DR4SR_LAUNCH_CHECK("dead_bias_kernel");
+  {
+    GemmArgs g = gemm_args(q, D, table, D, scores, (int)n_al, B, (int)n_al, D, nullptr);
+    g.bias = bias; g.b_rows = (int)N;
+    DR4SR_TRY((launch_gemm<128, 128, true, true, false>(g, st)));
+  }
+  if (user_hist && H > 0) {
+    mask_hist_kernel<<<ceil_div((int64_t)B * H, 256), 256, 0, st>>>(user_hist, B, H, N, (int64_t)n_al, scores);
+    DR4SR_LAUNCH_CHECK("mask_hist_kernel");
+  }
+  int kpad = 32;
+  while (kpad < k) kpad <<= 1;
+  const size_t smem = sizeof(uint32_t) * (256 + 2 * (size_t)kpad);
+  topk_select_kernel<<<B, kSelThreads, smem, st>>>(scores, N, (int64_t)n_al, k, kpad, out_scores, out_ids);
+  DR4SR_LAUNCH_CHECK("topk_select_kernel");
+  return DR4SR_OK;
+}

@@ -1,0 +1,194 @@
+"""Device-side engine: owns the workspaces and drives libdr4sr through its C ABI.
+
+PyTorch is used for device memory and streams only; every arithmetic step of the hot path is a
+kernel of libdr4sr launched on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import SasrecCfg, check
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.Dr4srError(f'{name} must be a CUDA tensor (no CPU fallback); got device {t.device}')
+    if t.dtype != dtype:
+        raise _lib.Dr4srError(f'{name} must be {dtype}, got {t.dtype}')
+    return t if t.is_contiguous() else t.contiguous()
+
+
+@dataclass
+class _Buffers:
+    """Everything sized by the batch size B (cached per B)."""
+    tok_off: torch.Tensor
+    row_seq: torch.Tensor
+    counts: torch.Tensor
+    ws: torch.Tensor
+    q_packed: torch.Tensor
+    dq: torch.Tensor
+    dx0: torch.Tensor
+    dscore: torch.Tensor
+    loss_pos: torch.Tensor
+    loss: torch.Tensor
+    q_last: torch.Tensor
+
+
+class SASRecEngine:
+    """Kernels + workspaces of one SASRec encoder (reference model/sasrec.py:10-75)."""
+
+    def __init__(self, num_items: int, embed_dim: int, max_seq_len: int, hidden_size: int, head_num: int,
+                 layer_num: int, dropout_rate: float, layer_norm_eps: float, seed: int, device: torch.device) -> None:
+        self.lib = _lib.lib()
+        self.N, self.D, self.L, self.F = int(num_items), int(embed_dim), int(max_seq_len), int(hidden_size)
+        self.H, self.n_layer = int(head_num), int(layer_num)
+        self.p, self.eps, self.seed = float(dropout_rate), float(layer_norm_eps), int(seed) & (2 ** 64 - 1)
+        self.device = torch.device(device)
+        self.step = 0                       # dropout stream counter (bumped per training forward)
+        self.fwd_token = 0                  # identifies whose activations the workspace holds
+        self._bufs: Dict[int, _Buffers] = {}
+        n = self.lib.dr4sr_sasrec_param_count(C.byref(self.cfg(1)))
+        if n == 0:
+            raise _lib.Dr4srError(f'unsupported SASRec shape D={self.D} F={self.F} L={self.L} heads={self.H} '
+                                  f'layers={self.n_layer} (D in {{64,128}}, F % 64 == 0, L <= 64)')
+        self.param_count = int(n)
+
+    # ---- configuration ------------------------------------------------------------------------
+    def cfg(self, B: int, step: Optional[int] = None) -> SasrecCfg:
+        return SasrecCfg(B=B, L=self.L, D=self.D, F=self.F, n_head=self.H, n_layer=self.n_layer, N=self.N,
+                         dropout_p=self.p, ln_eps=self.eps, seed=self.seed, step=self.step if step is None else step)
+
+    def buffers(self, B: int) -> _Buffers:
+        b = self._bufs.get(B)
+        if b is None:
+            dev, T, D = self.device, B * self.L, self.D
+            ws_bytes = self.lib.dr4sr_sasrec_workspace_bytes(C.byref(self.cfg(B)))
+            f32 = dict(dtype=torch.float32, device=dev)
+            b = _Buffers(
+                tok_off=torch.zeros(B + 1, dtype=torch.int32, device=dev),
+                row_seq=torch.zeros(T, dtype=torch.int32, device=dev),
+                counts=torch.zeros(4, dtype=torch.int32, device=dev),
+                ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev),
+                q_packed=torch.zeros(T, D, **f32), dq=torch.zeros(T, D, **f32), dx0=torch.zeros(T, D, **f32),
+                dscore=torch.zeros(T, 2, **f32), loss_pos=torch.zeros(B, self.L, **f32), loss=torch.zeros((), **f32),
+                q_last=torch.zeros(B, D, **f32))
+            self._bufs[B] = b
+        return b
+
+    # ---- kernels ------------------------------------------------------------------------------
+    def prep(self, seqlen: torch.Tensor, item_id: Optional[torch.Tensor]) -> _Buffers:
+        seqlen = _req(seqlen, torch.int64, 'seqlen')
+        B = seqlen.numel()
+        b = self.buffers(B)
+        one_d = 0
+        if item_id is not None:
+            item_id = _req(item_id, torch.int64, 'item_id')
+            one_d = 1 if item_id.dim() == 1 else 0
+        check(self.lib.dr4sr_prep_batch(_p(seqlen), _p(item_id), B, self.L, one_d, _p(b.tok_off), _p(b.row_seq),
+                                        _p(b.counts), _stream()), 'dr4sr_prep_batch')
+        return b
+
+    def encode(self, b: _Buffers, table: torch.Tensor, flat: torch.Tensor, in_ids: torch.Tensor, train: bool,
+               want_last: bool = False, q_dense: Optional[torch.Tensor] = None) -> torch.Tensor:
+        in_ids = _req(in_ids, torch.int64, 'in_item_id')
+        B = in_ids.size(0)
+        cfg = self.cfg(B)
+        check(self.lib.dr4sr_sasrec_fwd(C.byref(cfg), _p(_req(table, torch.float32, 'table')),
+                                        _p(_req(flat, torch.float32, 'params')), _p(in_ids), _p(b.tok_off), _p(b.row_seq),
+                                        _p(b.counts), _p(b.ws), b.ws.numel(), 1 if train else 0, _p(b.q_packed),
+                                        _p(b.q_last) if want_last else None, _p(q_dense), _stream()), 'dr4sr_sasrec_fwd')
+        return b.q_packed
+
+    def score_bce(self, b: _Buffers, table: torch.Tensor, item_id: torch.Tensor, neg_item: torch.Tensor,
+                  want_grad: bool, loss_weight: Optional[torch.Tensor] = None, upstream: Optional[torch.Tensor] = None,
+                  q_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+        item_id = _req(item_id, torch.int64, 'item_id')
+        neg_item = _req(neg_item, torch.int64, 'neg_item')
+        B = item_id.size(0)
+        q = b.q_packed if q_packed is None else q_packed
+        check(self.lib.dr4sr_score_bce(_p(q), _p(table), _p(item_id), _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
+                                       B, self.L, self.D, _p(loss_weight), _p(upstream), _p(b.loss_pos), _p(b.dscore),
+                                       _p(b.dq) if want_grad else None, _stream()), 'dr4sr_score_bce')
+        return b.loss_pos
+
+    def reduce_loss(self, b: _Buffers) -> torch.Tensor:
+        check(self.lib.dr4sr_sum(_p(b.loss_pos), b.loss_pos.numel(), _p(b.loss), _stream()), 'dr4sr_sum')
+        return b.loss
+
+    def encode_bwd(self, b: _Buffers, table: torch.Tensor, flat: torch.Tensor, in_ids: torch.Tensor, grads_flat: torch.Tensor,
+                   dq: Optional[torch.Tensor] = None) -> torch.Tensor:
+        in_ids = _req(in_ids, torch.int64, 'in_item_id')
+        B = in_ids.size(0)
+        cfg = self.cfg(B)
+        dq = b.dq if dq is None else dq
+        check(self.lib.dr4sr_sasrec_bwd(C.byref(cfg), _p(table), _p(flat), _p(in_ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
+                                        _p(b.ws), b.ws.numel(), _p(dq), _p(grads_flat), _p(b.dx0), _stream()), 'dr4sr_sasrec_bwd')
+        return b.dx0
+
+    def table_grad(self, b: _Buffers, in_ids: torch.Tensor, item_id: Optional[torch.Tensor], neg_item: Optional[torch.Tensor],
+                   table_grad: torch.Tensor, pos_grad: Optional[torch.Tensor], with_dx0: bool = True) -> None:
+        B = in_ids.size(0)
+        check(self.lib.dr4sr_table_grad(_p(b.dx0) if with_dx0 else None, _p(b.q_packed), _p(b.dscore), _p(in_ids), _p(item_id),
+                                        _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L, self.D, self.N,
+                                        _p(table_grad), _p(pos_grad), _stream()), 'dr4sr_table_grad')
+
+
+# ---- stateless wrappers ---------------------------------------------------------------------------
+def neg_sample(shape, num_items: int, seed: int, step: int, device) -> torch.Tensor:
+    """BaseModel._neg_sampling replacement: uniform ids in {1..N-1} (reference model/basemodel.py:50-61)."""
+    out = torch.empty(shape, dtype=torch.int64, device=device)
+    check(_lib.lib().dr4sr_neg_sample(_p(out), out.numel(), num_items, seed & (2 ** 64 - 1), step & (2 ** 64 - 1), _stream()),
+          'dr4sr_neg_sample')
+    return out
+
+
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float, beta1: float = 0.9,
+              beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0, zero_grad: bool = False) -> None:
+    for t, n in ((p, 'p'), (g, 'g'), (m, 'm'), (v, 'v')):
+        _req(t, torch.float32, n)
+        if not t.is_contiguous():
+            raise _lib.Dr4srError(f'adam: {n} must be contiguous')
+    check(_lib.lib().dr4sr_adam(_p(p), _p(g), _p(m), _p(v), p.numel(), int(step), lr, beta1, beta2, eps, weight_decay,
+                                1 if zero_grad else 0, _stream()), 'dr4sr_adam')
+
+
+_topk_ws: Dict[tuple, torch.Tensor] = {}
+
+
+def topk(q: torch.Tensor, table: torch.Tensor, item_dead: Optional[torch.Tensor], user_hist: Optional[torch.Tensor], k: int):
+    """BaseModel.topk replacement (reference model/basemodel.py:354-365)."""
+    L = _lib.lib()
+    q = _req(q, torch.float32, 'query')
+    table = _req(table, torch.float32, 'table')
+    B, D = q.shape
+    N = table.size(0)
+    H = 0
+    if user_hist is not None:
+        user_hist = _req(user_hist, torch.int64, 'user_hist')
+        H = user_hist.size(1)
+    if item_dead is not None:
+        item_dead = _req(item_dead, torch.uint8, 'item_dead')
+    nbytes = L.dr4sr_topk_workspace_bytes(B, N, k)
+    key = (q.device, nbytes)
+    ws = _topk_ws.get(key)
+    if ws is None:
+        _topk_ws.clear()
+        ws = _topk_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    scores = torch.empty(B, k, dtype=torch.float32, device=q.device)
+    ids = torch.empty(B, k, dtype=torch.int64, device=q.device)
+    check(L.dr4sr_topk(_p(q), _p(table), _p(item_dead), _p(user_hist), B, D, N, H, k, _p(scores), _p(ids), _p(ws), nbytes,
+                       _stream()), 'dr4sr_topk')
+    return scores, ids

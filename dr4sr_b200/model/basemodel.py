@@ -1,0 +1,292 @@
+"""BaseModel: the trainer-is-the-model surface of the reference (reference model/basemodel.py:19-407),
+re-hosted on libdr4sr.  Same constructor, hooks and batch contract:
+
+    Model(config, dataset_list); fit(); evaluate(); _init_model(); _neg_sampling(batch);
+    training_step(batch, reduce=True, return_query=False); forward(batch); topk(batch, k, user_h);
+    set_eval_domain(domain); load_checkpoint(path)
+
+What differs is underneath: negatives come from a counter-based kernel instead of a B x N multinomial
+(basemodel.py:50-61), scoring + BCE + their backward are one kernel (basemodel.py:205-210,
+loss_func.py:9-35), the table gradient is one scatter-add instead of three dense [N, D] buffers, Adam
+is a single fused pass, and top-k never copies the domain item list to the device per batch
+(basemodel.py:358-359).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import time
+from collections import defaultdict
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from .. import engine as _engine
+from ..optim import FlatGroup, FusedAdam
+from .loss_func import BinaryCrossEntropyLoss, BPRLoss
+
+
+def normal_initialization(module: nn.Module, initial_range: float = 0.02) -> None:
+    """Reference utils/utils.py:70-81."""
+    if isinstance(module, nn.Embedding):
+        module.weight.data.normal_(mean=0.0, std=initial_range)
+        if module.padding_idx is not None:
+            module.weight.data[module.padding_idx].zero_()
+    elif isinstance(module, nn.Linear):
+        module.weight.data.normal_(mean=0.0, std=initial_range)
+        if module.bias is not None:
+            module.bias.data.zero_()
+    elif isinstance(module, nn.LayerNorm):
+        module.bias.data.zero_()
+        module.weight.data.fill_(1.0)
+
+
+class BaseModel(nn.Module):
+    def __init__(self, config: Dict, dataset_list: List) -> None:
+        super().__init__()
+        self.config = config
+        self.ckpt_path = None
+        self.logger = logging.getLogger('CDR')
+        self.dataset_list = dataset_list
+        self.device = config['train']['device']
+        self.fuid, self.fiid = 'user_id', 'item_id'
+        head = dataset_list[0]
+        self.domain_name_list = head.domain_name_list
+        self.domain_user_mapping = head.domain_user_mapping
+        self.domain_item_mapping = head.domain_item_mapping
+        self.training_time = 0.0
+        self.inference_time = 0.0
+        self.embed_dim = config['model']['embed_dim']
+        self.max_seq_len = config['data']['max_seq_len']
+        self.num_users = head.num_users
+        self.num_items = head.num_items
+        self.item_embedding = nn.Embedding(self.num_items, self.embed_dim, padding_idx=0)
+        self.eval_domain = self.domain_name_list[0]
+        self.engine = None
+        self._dead_cache: Dict[str, torch.Tensor] = {}
+        self._neg_step = 0
+
+    # ---- hooks a subclass provides ----------------------------------------------------------
+    def _build_engine(self) -> None:
+        raise NotImplementedError
+
+    def _flat_parameters(self) -> List[nn.Parameter]:
+        """Non-table parameters in the order of the engine's flat layout."""
+        raise NotImplementedError
+
+    def forward(self, batch):
+        raise NotImplementedError
+
+    # ---- setup ------------------------------------------------------------------------------
+    def _init_model(self, train_data=None):
+        self.apply(normal_initialization)
+        self.to(self.device)
+        if torch.device(self.device).type != 'cuda':
+            raise _engine._lib.Dr4srError("dr4sr_b200 runs on CUDA only (config['train']['device'] must be a GPU)")
+        self._build_engine()
+        self._flatten()
+        self.optimizer = self._get_optimizers()
+        self.loss_fn = self._get_loss_func()
+
+    def _flatten(self) -> None:
+        """Re-home the encoder parameters as views of one flat fp32 buffer (the C ABI's layout) and
+        allocate the gradient buffers.  state_dict keys and shapes are unchanged."""
+        params = self._flat_parameters()
+        n = sum(p.numel() for p in params)
+        if n != self.engine.param_count:
+            raise _engine._lib.Dr4srError(f'flat layout mismatch: python {n} vs C {self.engine.param_count}')
+        dev = self.item_embedding.weight.device
+        self._flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self._flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._grad_views = []
+        off = 0
+        for p in params:
+            k = p.numel()
+            self._flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self._flat[off:off + k].view(p.shape)
+            self._grad_views.append(self._flat_grad[off:off + k].view(p.shape))
+            off += k
+        self._flat_params = params
+        self._table_grad = torch.zeros_like(self.item_embedding.weight.data)
+        self._table_group: Optional[FlatGroup] = None
+
+    def _check_flat(self) -> None:
+        p0 = self._flat_params[0]
+        if p0.data_ptr() != self._flat.data_ptr() or self._table_grad.device != self.item_embedding.weight.device:
+            self._flatten()          # parameters were moved / re-created after _init_model
+
+    def _get_optimizers(self):
+        t = self.config['train']
+        name, lr, wd = t['optimizer'].lower(), t['learning_rate'], t['weight_decay']
+        if name == 'adam':
+            self._table_group = FlatGroup(self.item_embedding.weight.data, self._table_grad, 'table', zero_grad_in_step=True)
+            groups = [FlatGroup(self._flat, self._flat_grad, 'encoder'), self._table_group]
+            return FusedAdam(self.parameters(), groups, lr=lr, weight_decay=wd)
+        if name == 'sgd':
+            return torch.optim.SGD(self.parameters(), lr=lr, weight_decay=wd)
+        if name == 'adagrad':
+            return torch.optim.Adagrad(self.parameters(), lr=lr, weight_decay=wd)
+        if name == 'rmsprop':
+            return torch.optim.RMSprop(self.parameters(), lr=lr, weight_decay=wd)
+        raise NotImplementedError(f'optimizer {name!r}')
+
+    def _get_loss_func(self):
+        kind = self.config['model']['loss_fn']
+        if kind == 'bce':
+            return BinaryCrossEntropyLoss()
+        if kind == 'bpr':
+            return BPRLoss()
+        raise NotImplementedError(kind)
+
+    # ---- hot path ---------------------------------------------------------------------------
+    def _neg_sampling(self, batch):
+        """One uniform negative per target slot, shape target.shape + (1,) (basemodel.py:50-61)."""
+        tgt = batch[self.fiid]
+        self._neg_step += 1
+        return _engine.neg_sample(tuple(tgt.shape) + (1,), self.num_items, self.config['train'].get('seed', 0),
+                                  self._neg_step, tgt.device)
+
+    def _publish_grads(self) -> None:
+        """Expose the kernel-written gradient buffers as .grad (what loss.backward() leaves behind)."""
+        for p, g in zip(self._flat_params, self._grad_views):
+            p.grad = g
+        self.item_embedding.weight.grad = self._table_grad
+
+    def _table_grad_buffer(self) -> torch.Tensor:
+        """Zeroed accumulator for the embedding gradient (the fused Adam clears it while reading)."""
+        grp = self._table_group
+        if grp is None or grp.dirty:
+            self._table_grad.zero_()
+        if grp is not None:
+            grp.dirty = True
+        return self._table_grad
+
+    def training_step(self, batch, reduce=True, return_query=False):
+        raise NotImplementedError
+
+    def _item_dead(self, domain: str) -> torch.Tensor:
+        """u8 mask of ids outside the eval domain (always id 0), built once per domain and kept on
+        the device (the reference re-uploads the python list every batch, basemodel.py:358-359)."""
+        m = self._dead_cache.get(domain)
+        if m is None or m.device != self.item_embedding.weight.device:
+            m = torch.ones(self.num_items, dtype=torch.uint8)
+            m[torch.as_tensor(list(self.domain_item_mapping[domain]), dtype=torch.int64)] = 0
+            m = self._dead_cache[domain] = m.to(self.item_embedding.weight.device)
+        return m
+
+    @torch.no_grad()
+    def topk(self, batch, k, user_h=None):
+        query = self.forward(batch)
+        return _engine.topk(query, self.item_embedding.weight.data, self._item_dead(self.eval_domain), user_h, k)
+
+    def set_eval_domain(self, domain):
+        self.eval_domain = domain
+
+    # ---- epoch loops (host glue; mirrors basemodel.py:171-262) ------------------------------------
+    def current_epoch_trainloaders(self, nepoch):
+        return self.dataset_list[0].get_loader()
+
+    def training_epoch(self, nepoch):
+        outputs = []
+        for batch in self.current_epoch_trainloaders(nepoch):
+            batch = {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
+            batch['neg_item'] = self._neg_sampling(batch)
+            self.optimizer.zero_grad()
+            loss = self.training_step(batch=batch)
+            loss.backward()
+            self.optimizer.step()
+            outputs.append({'loss_0': loss.detach()})
+        return [outputs]
+
+    @staticmethod
+    def _rank_metrics(hit: torch.Tensor, cutoffs) -> Dict[str, torch.Tensor]:
+        """ndcg@k / recall@k for one relevant item per user (reference evaluation/__init__.py:9-36,107-134)."""
+        out = {}
+        for k in cutoffs:
+            h = hit[:, :k].float()
+            disc = torch.log2(torch.arange(k, device=hit.device, dtype=torch.float32) + 2.0)
+            out[f'ndcg@{k}'] = (h / disc).sum(-1)
+            out[f'recall@{k}'] = h.sum(-1)
+        return out
+
+    @torch.no_grad()
+    def _eval_epoch(self, loader, cutoffs) -> Dict[str, float]:
+        sums, n = defaultdict(float), 0
+        for batch in loader:
+            batch = {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
+            _, ids = self.topk(batch, self.config['eval']['topk'], batch['user_hist'])
+            hit = batch[self.fiid].view(-1, 1) == ids
+            for name, v in self._rank_metrics(hit, cutoffs).items():
+                sums[name] += float(v.sum())
+            n += hit.size(0)
+        return {k: v / max(n, 1) for k, v in sums.items()}
+
+    def fit(self):
+        self._init_model(self.dataset_list[0])
+        self.fit_loop()
+
+    def fit_loop(self):
+        t, e = self.config['train'], self.config['eval']
+        best, bad, self._best_state = -1.0, 0, None
+        for epoch in range(t['epochs']):
+            tic = time.time()
+            self.train()
+            outs = self.training_epoch(epoch)
+            self.training_time += time.time() - tic
+            tic = time.time()
+            self.eval()
+            self.logged_metrics = {'epoch': epoch}
+            for domain in self.domain_name_list:
+                val = self.dataset_list[1]
+                val.set_eval_domain(domain)
+                self.set_eval_domain(domain)
+                m = self._eval_epoch(val.get_loader(), [e['cutoff'][0]])
+                self.logged_metrics.update({f'{domain}_{k}': v for k, v in m.items()})
+                for k, v in m.items():
+                    self.logged_metrics[k] = self.logged_metrics.get(k, 0.0) + v
+            self.inference_time += time.time() - tic
+            self.logged_metrics['train_loss_0'] = float(torch.stack([o['loss_0'] for o in outs[0]]).mean())
+            self.logger.info(self.logged_metrics)
+            score = self.logged_metrics.get('ndcg@20', self.logged_metrics.get(f"ndcg@{e['cutoff'][0]}", 0.0))
+            if score > best:
+                best, bad = score, 0
+                self._best_state = {k: v.detach().clone() for k, v in self.state_dict().items()}
+                self._best_epoch = epoch
+            else:
+                bad += 1
+                if bad >= t['early_stop_patience']:
+                    break
+        self.save_checkpoint()
+
+    def save_checkpoint(self, path: Optional[str] = None) -> str:
+        """Same dict layout as the reference's EarlyStopping.save_checkpoint (utils/callbacks.py:130-136)."""
+        root = os.path.join(self.config['eval']['save_path'], type(self).__name__, self.config['data']['dataset'])
+        os.makedirs(root, exist_ok=True)
+        path = path or os.path.join(root, time.strftime('%Y-%m-%d-%H-%M-%S') + '.ckpt')
+        state = self._best_state if getattr(self, '_best_state', None) is not None else self.state_dict()
+        torch.save({'config': self.config, 'model': type(self).__name__, 'epoch': getattr(self, '_best_epoch', 0),
+                    'parameters': state, 'metric': dict(getattr(self, 'logged_metrics', {}))}, path)
+        self.ckpt_path = path
+        return path
+
+    def evaluate(self) -> Dict:
+        if self.ckpt_path:
+            self.load_checkpoint(self.ckpt_path)
+        self.eval()
+        out: Dict[str, float] = {}
+        test = self.dataset_list[-1]
+        for domain in self.domain_name_list:
+            test.set_eval_domain(domain)
+            self.set_eval_domain(domain)
+            m = self._eval_epoch(test.get_loader(), self.config['eval']['cutoff'])
+            out.update({f'{domain}_{k}': v for k, v in m.items()})
+            for k, v in m.items():
+                out[k] = out.get(k, 0.0) + v
+        self.logger.info(out)
+        return out
+
+    def load_checkpoint(self, path: str) -> None:
+        ckpt = torch.load(path, map_location=self.device, weights_only=False)
+        self.config = ckpt['config']
+        self.load_state_dict(ckpt['parameters'])

@@ -1,0 +1,146 @@
+"""SASRec on libdr4sr (reference model/sasrec.py:10-120).
+
+`SASRecQueryEncoder` keeps the reference's parameter containers (``item_encoder``, ``position_emb``,
+``transformer_layer`` = torch.nn.TransformerEncoder) so ``state_dict()`` round-trips with the shipped
+checkpoints, but none of their ``forward``s run: the arithmetic is `dr4sr_sasrec_fwd/bwd`,
+`dr4sr_score_bce` and `dr4sr_table_grad` (include/dr4sr.h).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import engine as _engine
+from .basemodel import BaseModel
+
+
+class SASRecQueryEncoder(nn.Module):
+    """Parameter container with the reference's attribute names (model/sasrec.py:11-37)."""
+
+    def __init__(self, fiid, embed_dim, max_seq_len, n_head, hidden_size, dropout, activation, layer_norm_eps, n_layer,
+                 item_encoder, bidirectional=False, training_pooling_type='origin', eval_pooling_type='last') -> None:
+        super().__init__()
+        if activation != 'gelu' or bidirectional or training_pooling_type != 'origin' or eval_pooling_type != 'last':
+            raise NotImplementedError('libdr4sr implements the configuration the reference ships: causal, GELU, '
+                                      "'origin'/'last' pooling (configs/sasrec.yaml)")
+        self.fiid = fiid
+        self.item_encoder = item_encoder
+        self.position_emb = nn.Embedding(max_seq_len, embed_dim)
+        block = nn.TransformerEncoderLayer(d_model=embed_dim, nhead=n_head, dim_feedforward=hidden_size, dropout=dropout,
+                                           activation=activation, layer_norm_eps=layer_norm_eps, batch_first=True,
+                                           norm_first=False)
+        self.transformer_layer = nn.TransformerEncoder(encoder_layer=block, num_layers=n_layer)
+        self.dropout = nn.Dropout(p=dropout)
+
+    def flat_parameters(self):
+        """Order of the C ABI's flat layout (include/dr4sr.h): positions, then per layer in state_dict order."""
+        out = [self.position_emb.weight]
+        for blk in self.transformer_layer.layers:
+            out += [blk.self_attn.in_proj_weight, blk.self_attn.in_proj_bias, blk.self_attn.out_proj.weight,
+                    blk.self_attn.out_proj.bias, blk.linear1.weight, blk.linear1.bias, blk.linear2.weight, blk.linear2.bias,
+                    blk.norm1.weight, blk.norm1.bias, blk.norm2.weight, blk.norm2.bias]
+        return out
+
+    def forward(self, batch, need_pooling=True):
+        raise RuntimeError('SASRecQueryEncoder is a parameter container here; call SASRec.forward(batch)')
+
+
+class _EncodeScoreBCE(torch.autograd.Function):
+    """training_step as one autograd node: forward = encoder + sampled BCE kernels, backward = BCE
+    backward + encoder backward + table scatter-add.  Gradients are written by the kernels into the
+    model's flat buffers and published as ``.grad``; nothing flows back through autograd edges."""
+
+    @staticmethod
+    def forward(ctx, table, model, batch, reduce, return_query):
+        eng = model.engine
+        model._check_flat()
+        in_ids, item_id, neg = batch['in_' + model.fiid], batch[model.fiid], batch['neg_item']
+        b = eng.prep(batch['seqlen'], item_id)
+        if model.training:
+            eng.step += 1
+        q_dense = None
+        if return_query:
+            q_dense = torch.empty(in_ids.size(0), eng.L, eng.D, dtype=torch.float32, device=in_ids.device)
+        eng.encode(b, table, model._flat, in_ids, train=model.training, q_dense=q_dense)
+        eng.score_bce(b, table, item_id, neg.view(item_id.shape), want_grad=False)
+        loss = eng.reduce_loss(b).clone() if reduce else b.loss_pos.clone()
+        ctx.model, ctx.bufs, ctx.reduce = model, b, reduce
+        ctx.ids = (in_ids, item_id, neg.view(item_id.shape))
+        eng.fwd_token += 1
+        ctx.token = eng.fwd_token
+        ctx.set_materialize_grads(False)
+        if return_query:
+            return loss, q_dense
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dloss, dquery=None):
+        model, b = ctx.model, ctx.bufs
+        eng = model.engine
+        if ctx.token != eng.fwd_token:
+            raise RuntimeError('dr4sr_b200: backward() of a stale training_step (the engine keeps the activations of '
+                               'the most recent forward per batch size only)')
+        in_ids, item_id, neg = ctx.ids
+        table = model.item_embedding.weight.data
+        if dloss is None:
+            raise RuntimeError('dr4sr_b200: training_step loss received no gradient')
+        dloss = dloss.contiguous()
+        if ctx.reduce:
+            eng.score_bce(b, table, item_id, neg, want_grad=True, upstream=dloss)
+        else:
+            eng.score_bce(b, table, item_id, neg, want_grad=True, loss_weight=dloss)
+        if dquery is not None:
+            valid = torch.arange(eng.L, device=dquery.device).view(1, -1) < batch_len(b)
+            n = int(b.counts[0])
+            b.dq[:n] += dquery[valid]
+        eng.encode_bwd(b, table, model._flat, in_ids, model._flat_grad)
+        tg = model._table_grad_buffer()
+        eng.table_grad(b, in_ids, item_id, neg, tg, model._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
+        model._publish_grads()
+        return None, None, None, None, None
+
+
+def batch_len(b) -> torch.Tensor:
+    return (b.tok_off[1:] - b.tok_off[:-1]).view(-1, 1)
+
+
+class SASRec(BaseModel):
+    def __init__(self, config, dataset_list) -> None:
+        super().__init__(config, dataset_list)
+        m = config['model']
+        self.query_encoder = SASRecQueryEncoder(self.fiid, self.embed_dim, self.max_seq_len, m['head_num'], m['hidden_size'],
+                                                m['dropout_rate'], m['activation'], m['layer_norm_eps'], m['layer_num'],
+                                                self.item_embedding)
+
+    def _build_engine(self) -> None:
+        m = self.config['model']
+        self.engine = _engine.SASRecEngine(self.num_items, self.embed_dim, self.max_seq_len, m['hidden_size'], m['head_num'],
+                                           m['layer_num'], m['dropout_rate'], m['layer_norm_eps'],
+                                           self.config['train'].get('seed', 0), self.item_embedding.weight.device)
+
+    def _flat_parameters(self):
+        return self.query_encoder.flat_parameters()
+
+    def current_epoch_trainloaders(self, nepoch):
+        return super().current_epoch_trainloaders(nepoch)
+
+    @torch.no_grad()
+    def forward(self, batch, need_pooling=True):
+        """Eval: row seqlen-1 ('last' pooling) [B, D]; train: zero-padded rows ('origin') [B, L, D]."""
+        self._check_flat()
+        eng = self.engine
+        in_ids = batch['in_' + self.fiid]
+        b = eng.prep(batch['seqlen'], None)
+        table = self.item_embedding.weight.data
+        if self.training or not need_pooling:
+            q_dense = torch.empty(in_ids.size(0), eng.L, eng.D, dtype=torch.float32, device=in_ids.device)
+            eng.encode(b, table, self._flat, in_ids, train=self.training, q_dense=q_dense)
+            return q_dense
+        eng.encode(b, table, self._flat, in_ids, train=False, want_last=True)
+        return b.q_last.clone()
+
+    def training_step(self, batch, reduce=True, return_query=False, align=False):
+        if align:
+            raise NotImplementedError('the align branch (model/sasrec.py:111-119) has no caller in the reference')
+        return _EncodeScoreBCE.apply(self.item_embedding.weight, self, batch, reduce, return_query)

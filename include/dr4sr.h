@@ -1,0 +1,173 @@
+/* dr4sr.h -- C ABI of libdr4sr (B200 / sm_100a kernels for DR4SR's sequential-recommender hot path).
+ *
+ * The reference (USTC-StarTeam/DR4SR) has no FFI: its operator surface is Python duck typing
+ * (`run.py -m <Model>` -> utils/utils.py:32-36 -> `model.<name>.<Name>`), and every kernel it runs is
+ * an ATen/cuBLAS/cuDNN/cuFFT call dispatched from the functions cited below.  Each entry point here
+ * replaces the set of library calls made by ONE of those reference functions; the Python classes in
+ * dr4sr_b200/model/*.py (same names, constructor and hook signatures as the reference) bind them
+ * through ctypes.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, POD structs; no torch types; caller owns every buffer.
+ *   - every function enqueues work on `stream` and returns immediately (no host sync, no allocation,
+ *     no global mutable state); return 0 on success, a negative DR4SR_E* code otherwise.
+ *   - ids are int64 (the reference batch contract, data/dataset.py:149-164); floats are fp32.
+ *   - "packed" activations: only slots t < seqlen[b] of a post-padded batch are materialised; row
+ *     tok_off[b] + t of a [T_cap, D] buffer holds (b, t), T_cap = B*L.  Pad slots are exact dead work
+ *     in SASRec/GRU4Rec, so nothing is lost.
+ */
+#ifndef DR4SR_H_
+#define DR4SR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* dr4sr_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define DR4SR_API __attribute__((visibility("default")))
+#else
+#define DR4SR_API
+#endif
+
+enum {
+  DR4SR_OK = 0,
+  DR4SR_EINVAL = -1,    /* unsupported shape / null pointer */
+  DR4SR_EWORKSPACE = -2, /* workspace too small */
+  DR4SR_ECUDA = -3       /* a CUDA launch failed; see dr4sr_last_cuda_error() */
+};
+
+#define DR4SR_ABI_VERSION 1
+DR4SR_API int dr4sr_abi_version(void);
+/* last CUDA error string seen by this thread's most recent failing call ("" if none) */
+DR4SR_API const char* dr4sr_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batch preparation: packed-token index from `seqlen`, loss normaliser from `item_id`.
+ * Replaces the mask construction at model/sasrec.py:48,58 and `(~padding_mask).sum()` at
+ * model/loss_func.py:18,28.
+ *   seqlen [B] i64, item_id [B,L] (or [B] when target_is_1d) i64
+ *   tok_off [B+1] i32 (exclusive prefix sums of clamp(seqlen,0,L)); row_seq [B*L] i32 (row -> b)
+ *   counts [4] i32: {T_valid, n_valid_targets, 0, 0}
+ */
+DR4SR_API int dr4sr_prep_batch(const int64_t* seqlen, const int64_t* item_id, int32_t B, int32_t L, int32_t target_is_1d,
+                     int32_t* tok_off, int32_t* row_seq, int32_t* counts, dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Negative sampling, replaces BaseModel._neg_sampling (model/basemodel.py:50-61): one id per target
+ * slot, i.i.d. uniform on {1..N-1}, with replacement (no B x N weight matrix).  Counter-based RNG:
+ * out[i] = 1 + mulhi(hash(seed, step, i), N-1).
+ */
+DR4SR_API int dr4sr_neg_sample(int64_t* out, int64_t n, int64_t num_items, uint64_t seed, uint64_t step, dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SASRec encoder, replaces SASRecQueryEncoder.forward (model/sasrec.py:39-75) with the
+ * torch.nn.TransformerEncoder configured at model/sasrec.py:21-34 (post-norm, GELU-erf, causal +
+ * key-padding mask) and SeqPoolingLayer 'origin' / 'last' (module/layers.py:41-50,69-73).
+ *
+ * Flat parameter layout (fp32, contiguous, same order as the reference state_dict):
+ *   position_emb [L,D];  then per layer:
+ *   in_proj_weight [3D,D], in_proj_bias [3D], out_proj.weight [D,D], out_proj.bias [D],
+ *   linear1.weight [F,D], linear1.bias [F], linear2.weight [D,F], linear2.bias [D],
+ *   norm1.weight [D], norm1.bias [D], norm2.weight [D], norm2.bias [D]
+ * The gradient buffer has the same layout.
+ */
+typedef struct {
+  int32_t B, L, D, F, n_head, n_layer;
+  int64_t N;          /* table rows (incl. pad row 0) */
+  float dropout_p;    /* applied only when train != 0 */
+  float ln_eps;
+  uint64_t seed;      /* dropout stream = (seed, step) */
+  uint64_t step;
+} dr4sr_sasrec_cfg;
+
+DR4SR_API size_t dr4sr_sasrec_param_count(const dr4sr_sasrec_cfg* cfg);
+DR4SR_API size_t dr4sr_sasrec_workspace_bytes(const dr4sr_sasrec_cfg* cfg);
+
+/* Forward.  table [N,D]; params flat; in_item_id [B,L]; tok_off/row_seq/counts from dr4sr_prep_batch;
+ * ws: workspace (activations stay there for the backward); train: 1 = dropout on.
+ * q_packed (optional out) [B*L, D]: encoder output rows in packed order (== 'origin' pooling on
+ * valid rows); q_last (optional out) [B, D]: row seqlen-1 of each sequence ('last' pooling);
+ * q_dense (optional out) [B, L, D]: 'origin' pooling in the reference's dense layout. */
+DR4SR_API int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* cfg, const float* table, const float* params,
+                     const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                     const int32_t* counts, void* ws, size_t ws_bytes, int32_t train,
+                     float* q_packed, float* q_last, float* q_dense, dr4sr_stream_t stream);
+
+/* Backward of the forward whose activations are in `ws`.  dq_packed [B*L, D] (in: dLoss/dq rows,
+ * clobbered).  Writes grads (flat layout, overwritten not accumulated) and dx0_packed [B*L, D]
+ * (gradient w.r.t. the gathered input rows; consumed by dr4sr_table_grad). */
+DR4SR_API int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* cfg, const float* table, const float* params,
+                     const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                     const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed,
+                     float* grads, float* dx0_packed, dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampled scoring + BCE, replaces BaseModel.training_step (model/basemodel.py:205-210) and
+ * BinaryCrossEntropyLoss.forward (model/loss_func.py:9-35) with one negative per slot, forward and
+ * backward in one pass:
+ *   s+ = <q, E[item_id]>, s- = <q, E[neg]>, loss_pos[b,t] = (-logsig(s+) + softplus(s-)) / n
+ *   dq = ds+ E+ + ds- E-;  ds+ = -sigmoid(-s+) w/n, ds- = sigmoid(s-) w/n      (w = loss_weight or 1)
+ * q_packed [B*L,D] packed rows; item_id/neg_item [B,L] i64; loss_pos [B,L] (out, 0 at pads);
+ * dscore [B*L,2] packed (out: ds+, ds-); dq_packed (out).  upstream: optional device scalar that
+ * multiplies every gradient (autograd's grad_output), NULL = 1.  loss_weight: optional [B,L].
+ */
+DR4SR_API int dr4sr_score_bce(const float* q_packed, const float* table, const int64_t* item_id, const int64_t* neg_item,
+                    const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                    int32_t D, const float* loss_weight, const float* upstream, float* loss_pos, float* dscore,
+                    float* dq_packed, dr4sr_stream_t stream);
+
+/* Deterministic sum of loss_pos [n] into loss[0] (reduce=True path). */
+DR4SR_API int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embedding-gradient scatter-add, replaces the autograd backward of the three table gathers
+ * (nn.Embedding input lookup model/sasrec.py:46, weight[item_id] / weight[neg_item]
+ * model/basemodel.py:206-207): table_grad[in_id] += dx0; [item_id] += ds+ q; [neg] += ds- q.
+ * table_grad [N,D] is accumulated into (caller zeroes it; dr4sr_adam can zero it while reading).
+ * pos_grad [L,D] (optional): dP[t] = sum_b dx0[b,t], overwritten.
+ */
+DR4SR_API int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, const float* dscore,
+                     const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
+                     const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                     int32_t D, int64_t N, float* table_grad, float* pos_grad, dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense Adam, replaces torch.optim.Adam.step as configured at model/basemodel.py:85-86
+ * (betas .9/.999, eps 1e-8, L2 weight decay added to the gradient, no amsgrad).  One pass over
+ * (p, g, m, v); step is 1-based; zero_grad != 0 clears g after reading it.
+ */
+DR4SR_API int dr4sr_adam(float* p, float* g, float* m, float* v, int64_t n, int64_t step, float lr, float beta1, float beta2,
+               float eps, float weight_decay, int32_t zero_grad, dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Full-catalog scoring + top-k, replaces BaseModel.topk (model/basemodel.py:354-365):
+ * scores = q @ table[:N].T; -inf where item_dead[n] != 0 (ids outside the eval domain, always id 0)
+ * and at every id in user_hist[b,:]; top-k values (descending) and ids.
+ * q [B,D]; item_dead [N] u8; user_hist [B,H] i64 (may be NULL, H=0); out_scores [B,k] f32, out_ids [B,k] i64.
+ * ws: at least dr4sr_topk_workspace_bytes(B,N,k).
+ */
+DR4SR_API size_t dr4sr_topk_workspace_bytes(int32_t B, int64_t N, int32_t k);
+DR4SR_API int dr4sr_topk(const float* q, const float* table, const uint8_t* item_dead, const int64_t* user_hist, int32_t B,
+               int32_t D, int64_t N, int32_t H, int32_t k, float* out_scores, int64_t* out_ids, void* ws,
+               size_t ws_bytes, dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Building blocks exported for unit parity tests (each is also used inside the composites).
+ */
+/* x0_packed[row] = dropout(table[in_id] + pos[t]) (model/sasrec.py:42-46,64-66) */
+DR4SR_API int dr4sr_embed_fwd(const float* table, const float* pos, const int64_t* in_item_id, const int32_t* tok_off,
+                    const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L, int32_t D, float dropout_p,
+                    uint64_t seed, uint64_t step, float* x0_packed, dr4sr_stream_t stream);
+/* y[M,N] = x[M,K] @ w[N,K]^T + bias (torch.nn.functional.linear); M read from m_dev[0] if non-NULL */
+DR4SR_API int dr4sr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int32_t M, int32_t N, int32_t K,
+                     const int32_t* m_dev, dr4sr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DR4SR_H_ */

@@ -1,0 +1,342 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libdr4sr.so (ctypes) and is checked against the CPU oracle and the golden vectors dumped from the
+unmodified reference.  Tolerances: bit-exact for ids / integer work; fp32 within 1e-4 relative for
+losses and logits (BASELINE.json north_star), gradients within 1e-4 of the tensor's max magnitude.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dr4sr_oracle as orc
+from tests.helpers import load_fixture, oracle_from_fixture, rel_err, load_params
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+
+
+def make_model(N, D, F=128, layers=2, heads=2, p=0.0, wd=0.0, seed=2023):
+    from dr4sr_b200.model.sasrec import SASRec
+    from dr4sr_b200.utils.config import default_config, SyntheticCatalog
+    cfg = default_config('SASRec', model__embed_dim=D, model__hidden_size=F, model__layer_num=layers, model__head_num=heads,
+                         model__dropout_rate=p, train__device=DEV, train__weight_decay=wd, train__seed=seed)
+    torch.manual_seed(seed)
+    m = SASRec(cfg, [SyntheticCatalog(N)] * 3)
+    m._init_model()
+    return m
+
+
+def model_from_fixture(fx, p=0.0):
+    prm = fx['param']
+    N, D = prm['item_embedding.weight'].shape
+    F = prm['query_encoder.transformer_layer.layers.0.linear1.weight'].shape[0]
+    m = make_model(N, D, F, p=p)
+    load_params(m, {k: v.to(DEV) for k, v in prm.items()})
+    return m
+
+
+def to_dev(batch):
+    return {k: v.to(DEV) for k, v in batch.items()}
+
+
+def valid_mask(batch):
+    return torch.arange(batch['in_item_id'].size(1)).view(1, -1) < batch['seqlen'].view(-1, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_prep_batch_and_embed_bit_exact():
+    _need_gpu()
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    m = make_model(500, 64)
+    batch = synthetic_batch(37, 50, 500, seed=3)
+    eng = m.engine
+    b = eng.prep(batch['seqlen'].to(DEV), batch['item_id'].to(DEV))
+    lens = batch['seqlen'].clamp(0, 50)
+    want_off = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)]).int()
+    assert torch.equal(b.tok_off.cpu(), want_off)
+    assert int(b.counts[0]) == int(lens.sum())
+    assert int(b.counts[1]) == int((batch['item_id'] != 0).sum())
+    want_seq = torch.repeat_interleave(torch.arange(37), lens).int()
+    assert torch.equal(b.row_seq.cpu()[: want_seq.numel()], want_seq)
+    # K1: gather + positions, dropout off => bit exact (one fp32 add per element)
+    from dr4sr_b200 import _lib
+    from dr4sr_b200.engine import _p, _stream
+    x0 = torch.zeros(37 * 50, 64, device=DEV)
+    table = m.item_embedding.weight.data
+    pos = m.query_encoder.position_emb.weight.data
+    ids = batch['in_item_id'].to(DEV)
+    _lib.check(_lib.lib().dr4sr_embed_fwd(_p(table), _p(pos), _p(ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts), 37, 50, 64,
+                                          0.0, 0, 0, _p(x0), _stream()), 'embed')
+    want = (table.cpu()[batch['in_item_id']] + pos.cpu()[:50].unsqueeze(0))[valid_mask(batch)]
+    assert torch.equal(x0.cpu()[: want.size(0)], want)
+
+
+def test_linear_fwd_matches_torch():
+    _need_gpu()
+    from dr4sr_b200 import _lib
+    from dr4sr_b200.engine import _p, _stream
+    torch.manual_seed(0)
+    for (M, N, K) in [(257, 384, 128), (64, 64, 64), (1000, 128, 256), (130, 192, 64)]:
+        x, w, bias = torch.randn(M, K), torch.randn(N, K) * 0.1, torch.randn(N)
+        y = torch.zeros(M, N, device=DEV)
+        _lib.check(_lib.lib().dr4sr_linear_fwd(_p(x.to(DEV)), _p(w.to(DEV)), _p(bias.to(DEV)), _p(y), M, N, K, None, _stream()),
+                   'linear')
+        want = torch.nn.functional.linear(x.double(), w.double(), bias.double())
+        assert rel_err(y.cpu(), want) < 2e-6, (M, N, K)
+
+
+@pytest.mark.parametrize('name', ['sasrec_d64.npz', 'sasrec_d128.npz'])
+def test_forward_matches_reference_golden(name):
+    _need_gpu()
+    fx = load_fixture(name)
+    m = model_from_fixture(fx).train()
+    batch = to_dev(fx['batch'])
+    q = m.forward(batch).cpu()                       # train mode: 'origin' pooling, [B, L, D]
+    want = fx['train']['query']
+    assert q.shape == want.shape
+    assert rel_err(q, want) < 1e-5
+    assert torch.equal(q[~valid_mask(fx['batch'])], torch.zeros_like(q[~valid_mask(fx['batch'])]))
+
+
+@pytest.mark.parametrize('name', ['sasrec_d64.npz', 'sasrec_d128.npz'])
+def test_loss_and_gradients_match_reference_golden(name):
+    _need_gpu()
+    fx = load_fixture(name)
+    m = model_from_fixture(fx).train()
+    batch = to_dev(fx['batch'])
+    loss = m.training_step(batch)
+    assert abs(float(loss) - float(fx['train']['loss'])) / abs(float(fx['train']['loss'])) < 1e-5
+    per = m.training_step(batch, reduce=False).detach().cpu()
+    assert rel_err(per, fx['train']['loss_per_pos']) < 1e-5
+    m.optimizer.zero_grad()
+    loss = m.training_step(batch)
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        assert rel_err(p.grad.cpu(), fx['grad'][k]) < 1e-4, k
+    assert float(m.item_embedding.weight.grad[0].abs().max()) == 0.0      # pad row never receives gradient
+
+
+@pytest.mark.parametrize('name', ['sasrec_d64.npz', 'sasrec_d128.npz'])
+def test_adam_steps_match_reference_golden(name):
+    _need_gpu()
+    fx = load_fixture(name)
+    m = model_from_fixture(fx).train()
+    batch = to_dev(fx['batch'])
+    for want in fx['adam']['losses'].tolist():
+        m.optimizer.zero_grad()
+        loss = m.training_step(batch)
+        loss.backward()
+        m.optimizer.step()
+        assert abs(float(loss) - want) / want < 2e-5
+    for k, p in m.named_parameters():
+        # Adam's first steps move every touched weight by ~lr regardless of gradient size, so
+        # compare the update against lr
+        assert float((p.detach().cpu() - fx['param_after'][k]).abs().max()) < 2e-5, k
+
+
+@pytest.mark.parametrize('name', ['sasrec_d64.npz', 'sasrec_d128.npz'])
+def test_eval_query_and_topk_match_reference_golden(name):
+    _need_gpu()
+    fx = load_fixture(name)
+    m = model_from_fixture(fx)
+    load_params(m, {k: v.to(DEV) for k, v in fx['param_after'].items()})
+    m.eval()
+    ev = to_dev(fx['evalbatch'])
+    q = m.forward(ev).cpu()
+    assert rel_err(q, fx['eval']['query']) < 1e-5
+    k = fx['eval']['topk_ids'].shape[1]
+    s, i = m.topk(ev, k, ev['user_hist'])
+    s, i = s.cpu(), i.cpu()
+    assert rel_err(s, fx['eval']['topk_scores']) < 1e-5
+    # ids: identical wherever neighbouring reference scores are separated by more than fp32 noise
+    ws = fx['eval']['topk_scores']
+    gap = torch.minimum(torch.cat([ws[:, :1] * 0 + 1, (ws[:, :-1] - ws[:, 1:])], 1),
+                        torch.cat([(ws[:, :-1] - ws[:, 1:]), ws[:, :1] * 0 + 1], 1))
+    firm = gap > 1e-5
+    assert torch.equal(i[firm], fx['eval']['topk_ids'][firm])
+    assert float(firm.float().mean()) > 0.95
+
+
+def test_topk_random_against_fp64_oracle():
+    _need_gpu()
+    from dr4sr_b200 import engine
+    torch.manual_seed(5)
+    B, D, N, H, k = 33, 64, 4999, 50, 100
+    q, table = torch.randn(B, D), torch.randn(N, D)
+    dead = torch.zeros(N, dtype=torch.uint8)
+    dead[0] = 1
+    dead[torch.randint(1, N, (300,))] = 1
+    hist = torch.randint(0, N, (B, H))
+    s, i = engine.topk(q.to(DEV), table.to(DEV), dead.to(DEV), hist.to(DEV), k)
+    full = (q.double() @ table.double().T).masked_fill(dead.bool().view(1, -1), -math.inf)
+    full = torch.scatter(full, 1, hist, -math.inf)
+    ws, wi = torch.topk(full, k)
+    assert rel_err(s.cpu(), ws) < 1e-5
+    assert torch.equal(i.cpu(), wi)      # gaussian scores: no ties at fp32 resolution for this seed
+    assert bool((s[:, :-1] >= s[:, 1:]).all())
+
+
+def test_topk_with_ties_and_few_live_items():
+    _need_gpu()
+    from dr4sr_b200 import engine
+    B, D, N, k = 5, 64, 1030, 100
+    q = torch.ones(B, D)
+    table = torch.zeros(N, D)
+    table[:, 0] = torch.arange(N).float() % 7          # many exact ties
+    dead = torch.zeros(N, dtype=torch.uint8)
+    dead[0] = 1
+    s, i = engine.topk(q.to(DEV), table.to(DEV), dead.to(DEV), None, k)
+    full = (q @ table.T).masked_fill(dead.bool().view(1, -1), -math.inf)
+    ws, _ = torch.topk(full, k)
+    assert torch.equal(s.cpu(), ws)                     # values exact
+    got = full.gather(1, i.cpu())
+    assert torch.equal(got, ws)                         # returned ids carry those values
+    for r in range(B):                                  # ties broken by lower id, no duplicates
+        ids = i[r].cpu().tolist()
+        assert len(set(ids)) == k
+        six = [j for j in ids if full[r, j] == 6]
+        assert six == sorted(six) and six[0] == 6
+
+
+@pytest.mark.parametrize('B,D,N,minlen', [(64, 128, 5000, 1), (9, 64, 777, 50), (5, 64, 300, 1), (1, 128, 1000, 7)])
+def test_training_step_matches_oracle_on_synthetic(B, D, N, minlen):
+    _need_gpu()
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    m = make_model(N, D).train()
+    o = orc.OracleSASRec(N, embed_dim=D, dropout_rate=0.0).train()
+    o.load_state_dict({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    batch = synthetic_batch(B, 50, N, seed=B + D, min_len=minlen)
+    if B == 5:                                            # hot ids: every target / negative collides on 3 rows
+        batch['item_id'] = torch.where(batch['item_id'] != 0, batch['item_id'] % 3 + 1, batch['item_id'])
+        batch['neg_item'] = batch['neg_item'] % 3 + 1
+        batch['seqlen'][:] = 1
+        batch['seqlen'][0] = 50
+        v = valid_mask(batch)
+        batch['in_item_id'] = torch.where(v, batch['in_item_id'], torch.zeros_like(batch['in_item_id']))
+        batch['item_id'] = torch.where(v, batch['item_id'], torch.zeros_like(batch['item_id']))
+    lo, qo = o.training_step(batch, return_query=True)
+    lo.backward()
+    loss, q = m.training_step(to_dev(batch), return_query=True)
+    loss.backward()
+    assert abs(float(loss) - float(lo)) / abs(float(lo)) < 1e-5
+    assert rel_err(q.detach().cpu(), qo.detach()) < 1e-5
+    for (k, p), (_, po) in zip(m.named_parameters(), o.named_parameters()):
+        want = po.grad if po.grad is not None else torch.zeros_like(po)
+        assert rel_err(p.grad.cpu(), want) < 1e-4, k
+
+
+def test_explicit_spec_layer_vs_kernels_three_layers_f256():
+    """Non-default encoder shape (3 layers, FFN 256, 4 heads) against the elementary-algebra spec."""
+    _need_gpu()
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    N, D = 400, 64
+    m = make_model(N, D, F=256, layers=3, heads=4).train()
+    o = orc.OracleSASRec(N, embed_dim=D, hidden_size=256, layer_num=3, head_num=4, dropout_rate=0.0).train()
+    o.load_state_dict({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    batch = synthetic_batch(12, 50, N, seed=1)
+    with torch.no_grad():
+        want = orc.sasrec_encode_explicit(o, batch)
+    q = m.forward(to_dev(batch)).cpu()
+    v = valid_mask(batch)
+    assert rel_err(q[v], want[v]) < 1e-5
+
+
+def test_dropout_is_deterministic_unbiased_and_consistent_with_backward():
+    _need_gpu()
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    N, D = 2000, 64
+    m = make_model(N, D, p=0.5).train()
+    batch = to_dev(synthetic_batch(64, 50, N, seed=9))
+    eng = m.engine
+    # same (seed, step) => identical forward; different step => different masks
+    eng.step = 7
+    a = m.forward(batch).clone()
+    eng.step = 7
+    b_ = m.forward(batch).clone()
+    eng.step = 8
+    c = m.forward(batch).clone()
+    assert torch.equal(a, b_) and not torch.equal(a, c)
+    # K1 keep-rate: embedding stage alone, p = 0.5
+    from dr4sr_b200 import _lib
+    from dr4sr_b200.engine import _p, _stream
+    bufs = eng.prep(batch['seqlen'], batch['item_id'])
+    x0 = torch.zeros(64 * 50, D, device=DEV)
+    table = torch.ones(N, D, device=DEV)
+    _lib.check(_lib.lib().dr4sr_embed_fwd(_p(table), None, _p(batch['in_item_id']), _p(bufs.tok_off), _p(bufs.row_seq),
+                                          _p(bufs.counts), 64, 50, D, 0.5, 1, 2, _p(x0), _stream()), 'embed')
+    n = int(bufs.counts[0])
+    live = x0[:n]
+    keep = float((live != 0).float().mean())
+    assert abs(keep - 0.5) < 0.01
+    assert set(torch.unique(live).tolist()) <= {0.0, 2.0}          # inverted scaling 1/(1-p)
+    # backward regenerates the forward's masks: directional derivative along a random direction
+    torch.manual_seed(0)
+    params = [p for p in m.query_encoder.flat_parameters()]
+    direction = [torch.randn_like(p) for p in params]
+
+    def loss_at(eps):
+        for p, d in zip(params, direction):
+            p.data.add_(d, alpha=eps)
+        eng.step = 20                       # training_step bumps to 21: same masks every call
+        l = float(m.training_step(batch))
+        for p, d in zip(params, direction):
+            p.data.add_(d, alpha=-eps)
+        return l
+
+    eng.step = 20
+    m.optimizer.zero_grad()
+    loss = m.training_step(batch)
+    loss.backward()
+    analytic = sum(float((p.grad * d).sum()) for p, d in zip(params, direction))
+    h = 2e-3
+    numeric = (loss_at(h) - loss_at(-h)) / (2 * h)
+    assert abs(analytic - numeric) <= 0.03 * max(abs(numeric), 1e-3), (analytic, numeric)
+
+
+def test_neg_sampling_range_uniformity_determinism():
+    _need_gpu()
+    from dr4sr_b200 import engine
+    N = 1000
+    a = engine.neg_sample((512, 50, 1), N, seed=2023, step=1, device=DEV)
+    b_ = engine.neg_sample((512, 50, 1), N, seed=2023, step=1, device=DEV)
+    c = engine.neg_sample((512, 50, 1), N, seed=2023, step=2, device=DEV)
+    assert a.shape == (512, 50, 1) and a.dtype == torch.int64
+    assert torch.equal(a, b_) and not torch.equal(a, c)
+    assert int(a.min()) >= 1 and int(a.max()) <= N - 1
+    counts = torch.bincount(a.flatten().cpu(), minlength=N)[1:].double()
+    expected = a.numel() / (N - 1)
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    assert chi2 < (N - 2) + 6 * math.sqrt(2 * (N - 2))            # within 6 sigma of the chi-square mean
+
+
+def test_full_size_step_matches_oracle_config2():
+    """BASELINE config 2 shape: B=1024, L=50, D=128, N=100K (one step, dropout off)."""
+    _need_gpu()
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    B, D, N = 1024, 128, 100_000
+    m = make_model(N, D).train()
+    o = orc.OracleSASRec(N, embed_dim=D, dropout_rate=0.0).train()
+    o.load_state_dict({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    batch = synthetic_batch(B, 50, N, seed=42)
+    lo = o.training_step(batch)
+    lo.backward()
+    loss = m.training_step(to_dev(batch))
+    loss.backward()
+    assert abs(float(loss) - float(lo)) / abs(float(lo)) < 1e-5
+    for (k, p), (_, po) in zip(m.named_parameters(), o.named_parameters()):
+        assert rel_err(p.grad.cpu(), po.grad) < 1e-4, k
+    # size-independent properties
+    g = m.item_embedding.weight.grad
+    assert float(g[0].abs().max()) == 0.0
+    touched = torch.zeros(N, dtype=torch.bool)
+    for key in ('in_item_id', 'item_id', 'neg_item'):
+        touched[batch[key].flatten()] = True
+    assert float(g.cpu()[~touched].abs().max()) == 0.0             # untouched rows get exactly zero gradient
