@@ -86,8 +86,8 @@ def test_linear_fwd_matches_torch():
     for (M, N, K) in [(257, 384, 128), (64, 64, 64), (1000, 128, 256), (130, 192, 64)]:
         x, w, bias = torch.randn(M, K), torch.randn(N, K) * 0.1, torch.randn(N)
         y = torch.zeros(M, N, device=DEV)
-        _lib.check(_lib.lib().dr4sr_linear_fwd(_p(x.to(DEV)), _p(w.to(DEV)), _p(bias.to(DEV)), _p(y), M, N, K, None, _stream()),
-                   'linear')
+        xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)     # keep the device buffers alive across the async launch
+        _lib.check(_lib.lib().dr4sr_linear_fwd(_p(xd), _p(wd), _p(bd), _p(y), M, N, K, None, _stream()), 'linear')
         want = torch.nn.functional.linear(x.double(), w.double(), bias.double())
         assert rel_err(y.cpu(), want) < 2e-6, (M, N, K)
 
