@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- train-step sequences/second of the DR4SR hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model SASRec]
+
+One "step" = negative sampling -> encoder forward -> sampled BCE -> backward -> embedding-gradient
+scatter-add -> dense Adam on every parameter, over one synthetic batch of B sequences per GPU
+(BASELINE.json configs[1]: SASRec, |items| = 100K, d = 128, L = 50, B = 1024, dropout 0.5 as configured).
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
+  value     : whole-job seqs/s, batches already resident in HBM, CUDA-event timed, max over ranks
+  e2e       : same metric through the public API with HOST (pinned) batches: per step H2D of the
+              batch tensors and a D2H read of the loss inside the timed region
+  roofline  : dominant kernel of the step (per-kernel CUDA-event timing inside this process)
+  cpu_baseline : the oracle port (= the reference's own torch CPU path restated) on the host cores
+`--impl reference` times that CPU path as its own arm (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+METRIC = 'train-step seqs/sec (SASRec, B=1024 L=50)'
+UNIT = 'seqs/s'
+CFG2 = dict(model='SASRec', num_items=100_000, embed_dim=128, max_seq_len=50, batch_per_gpu=1024, hidden_size=128,
+            layer_num=2, head_num=2, dropout_rate=0.5)
+
+
+def peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tensor=p.get('bf16_tflops_sustained', p['bf16_tflops']), source='measured')
+    return dict(hbm=6650.0, tensor=1400.0, source='fallback')
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks (nvidia-smi sampled during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int) -> None:
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (reference's torch CPU path restated; oracle/dr4sr_oracle.py)
+# --------------------------------------------------------------------------------------------------
+def cpu_step_rate(steps: int, warmup: int, budget_s: float = 25.0):
+    """Times `_neg_sampling -> training_step -> backward -> Adam.step` (reference basemodel.py:194-199)
+    of the oracle port on the host cores.  Bounded: stops after `steps` or `budget_s` seconds."""
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    from oracle import dr4sr_oracle as orc
+    c = CFG2
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(2023)
+    m = orc.OracleSASRec(c['num_items'], embed_dim=c['embed_dim'], max_seq_len=c['max_seq_len'], head_num=c['head_num'],
+                         hidden_size=c['hidden_size'], dropout_rate=c['dropout_rate'], layer_num=c['layer_num'])
+    m.init_reference_style().train()
+    opt = m.make_adam(lr=1e-3)
+    B, L, N = c['batch_per_gpu'], c['max_seq_len'], c['num_items']
+    batches = [synthetic_batch(B, L, N, seed=100 + i, with_neg=False) for i in range(2)]
+
+    def one(i):
+        b = dict(batches[i % len(batches)])
+        b['neg_item'] = orc.neg_sampling_as_reference(b, N, L)      # the reference's B x N multinomial
+        opt.zero_grad()
+        loss = m.training_step(b)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for i in range(warmup):
+        one(i)
+    t0, done = time.perf_counter(), 0
+    while done < steps and (done == 0 or time.perf_counter() - t0 < budget_s):
+        one(done)
+        done += 1
+    dt = time.perf_counter() - t0
+    return dict(value=B * done / dt, unit=UNIT, cores=cores, kind='port', ms_per_step=1e3 * dt / done,
+                sample=f'{done} steps of B={B} L={L} |items|={N} d={c["embed_dim"]} (dropout {c["dropout_rate"]}, '
+                       f'reference B x N multinomial negatives), torch {torch.__version__} CPU, {cores} threads')
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = cpu_step_rate(steps=args.steps, warmup=min(args.warmup, 2), budget_s=120.0)
+    line = {'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'SASRec synthetic |items|=100K d=128 L=50 batch=1024 (BASELINE configs[1]), CPU'},
+            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# algorithmic work per kernel launch (DESIGN.md "Kernels"): T = live (non-pad) tokens of the batch
+# --------------------------------------------------------------------------------------------------
+def kernel_work(name: str, T: int, B: int, c: dict):
+    D, F, N, L = c['embed_dim'], c['hidden_size'], c['num_items'], c['max_seq_len']
+    U = T * D * 4
+    gemm = {'gemm_qkv': 2 * T * 3 * D * D, 'gemm_outproj_ln': 2 * T * D * D, 'gemm_ffn1': 2 * T * F * D,
+            'gemm_ffn2_ln': 2 * T * D * F, 'gemm_bwd_dpre': 2 * T * D * F, 'gemm_bwd_dx1': 2 * T * D * F,
+            'gemm_bwd_dattn': 2 * T * D * D, 'gemm_bwd_dx': 2 * T * 3 * D * D, 'gemm_wgrad_w2': 2 * T * D * F,
+            'gemm_wgrad_w1': 2 * T * D * F, 'gemm_wgrad_out': 2 * T * D * D, 'gemm_wgrad_in': 2 * T * 3 * D * D}
+    if name in gemm:
+        return dict(bound='tensor', work=gemm[name], unit='TFLOP/s')
+    byts = {'adam_table': 24 * N * D, 'embed_fwd': 2 * U, 'score_bce': 4 * U, 'table_grad_scatter': 5 * U, 'ln_bwd': 3 * U,
+            'attn_fwd': 4 * U, 'attn_bwd': 7 * U, 'colsum': 2 * U, 'pos_grad': U}
+    if name in byts:
+        return dict(bound='hbm', work=byts[name], unit='GB/s')
+    return None
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    from dr4sr_b200 import _lib
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    from dr4sr_b200.model.sasrec import SASRec
+    from dr4sr_b200.utils.config import SyntheticCatalog, default_config
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torchrun --nproc-per-node N for --gpus N')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    c = CFG2
+    B, L, N = c['batch_per_gpu'], c['max_seq_len'], c['num_items']
+    cfg = default_config('SASRec', model__embed_dim=c['embed_dim'], model__hidden_size=c['hidden_size'],
+                         model__layer_num=c['layer_num'], model__head_num=c['head_num'], model__dropout_rate=c['dropout_rate'],
+                         train__device=str(dev), train__batch_size=B)
+    torch.manual_seed(2023)
+    model = SASRec(cfg, [SyntheticCatalog(N)] * 3)
+    model._init_model()
+    if world > 1:
+        model.enable_data_parallel(dist.group.WORLD)
+    model.train()
+    lib = _lib.lib()
+
+    P = 8   # distinct batches cycled, per rank
+    host = [synthetic_batch(B, L, N, seed=1000 * rank + i, with_neg=False) for i in range(P)]
+    keys = ('user_id', 'in_item_id', 'item_id', 'seqlen')
+    pinned = [{k: b[k].pin_memory() for k in keys} for b in host]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in pinned]
+    live_tokens = sum(int(b['seqlen'].clamp(max=L).sum()) for b in host) / P
+
+    def step(batch):
+        batch = dict(batch)
+        batch['neg_item'] = model._neg_sampling(batch)
+        model.optimizer.zero_grad()
+        loss = model.training_step(batch=batch)
+        loss.backward()
+        model.optimizer.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        beg, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        beg.record()
+        for i in range(steps):
+            fn(i)
+        end.record()
+        barrier()
+        ms = torch.tensor([beg.elapsed_time(end)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for i in range(max(args.warmup, 3)):
+        step(resident[i % P])
+    launches0 = lib.dr4sr_launch_count()
+    with ClockSampler(local) as clk:
+        ms_dev = timed(lambda i: step(resident[i % P]), args.steps)
+    launches = lib.dr4sr_launch_count() - launches0
+    clocks = clk.summary()
+
+    # ---- e2e: host (pinned) batches -> H2D -> step -> D2H of the loss, every step ----
+    h2d = sum(pinned[0][k].numel() * pinned[0][k].element_size() for k in keys)
+    sink = []
+
+    def e2e_step(i):
+        src = pinned[i % P]
+        batch = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
+        sink.append(float(step(batch)))           # .item(): device -> host read of the loss
+
+    for i in range(3):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- per-kernel timing pass (CUDA events around every launcher, same workload) ----
+    lib.dr4sr_prof_enable(1)
+    prof_steps = min(args.steps, 20)
+    for i in range(prof_steps):
+        step(resident[i % P])
+    torch.cuda.synchronize()
+    lib.dr4sr_prof_enable(0)
+    import ctypes
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.dr4sr_prof_collect(buf, len(buf))
+    rows = []
+    for line in buf.value.decode().strip().splitlines():
+        name, cnt, tot = line.split(',')
+        rows.append((name, int(cnt), float(tot)))
+    total_kernel_ms = sum(r[2] for r in rows) or 1.0
+    pk = peaks()
+    roof, breakdown = None, []
+    for name, cnt, tot in rows:
+        per_launch_ms = tot / cnt
+        breakdown.append({'kernel': name, 'launches_per_step': cnt / prof_steps, 'ms_per_step': tot / prof_steps,
+                          'share': tot / total_kernel_ms})
+        w = kernel_work(name, int(live_tokens), B, c)
+        if roof is None and w is not None:
+            ach = w['work'] / (per_launch_ms * 1e-3) / (1e12 if w['bound'] == 'tensor' else 1e9)
+            peak = pk['tensor'] if w['bound'] == 'tensor' else pk['hbm']
+            roof = {'kernel': name, 'bound': w['bound'], 'achieved': ach, 'peak': peak, 'unit': w['unit'], 'frac': ach / peak,
+                    'traffic': None, 'peak_source': pk['source'], 'us_per_launch': per_launch_ms * 1e3,
+                    'share_of_step': tot / total_kernel_ms,
+                    'note': 'algorithmic work uses live (non-pad) tokens; fp32-exact FFMA GEMM measured against the bf16 '
+                            'tensor peak' if w['bound'] == 'tensor' else 'algorithmic bytes on live (non-pad) tokens'}
+
+    total_seqs = B * world * args.steps
+    line = {
+        'metric': METRIC, 'value': total_seqs / (ms_dev * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'SASRec synthetic |items|=100K d=128 L=50 batch=1024 per GPU, sampled BCE, dropout 0.5, dense '
+                               'Adam (BASELINE configs[1])',
+                   'global_batch': B * world, 'seq_len': L, 'parallelism': f'dp{world}' if world > 1 else 'single',
+                   'l2': 'no explicit flush: the step streams the 51 MB table + m + v + grad (205 MB) plus activations, '
+                         'larger than the 126 MB L2; 8 distinct batches are cycled',
+                   'live_tokens_per_batch': live_tokens},
+        'clocks': clocks, 'gpu_launches': int(launches),
+        'e2e': {'value': total_seqs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                'ms_per_step': ms_e2e / args.steps},
+        'roofline': roof, 'kernels': breakdown[:12],
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_step_rate(steps=6, warmup=1, budget_s=25.0)
+        line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

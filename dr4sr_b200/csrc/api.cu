@@ -1,6 +1,12 @@
-// api.cu -- ABI version and error plumbing of libdr4sr.
+// api.cu -- ABI version, error plumbing, launch counter and the optional per-kernel event timer.
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 #include "common.cuh"
 
 namespace dr4sr {
@@ -8,7 +14,69 @@ static thread_local char g_err[256] = "";
 void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec { const char* name; cudaEvent_t beg, end; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(const char* n, cudaStream_t s) : name(n), st(s), slot(-1) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r{n, nullptr, nullptr};
+  if (cudaEventCreate(&r.beg) != cudaSuccess || cudaEventCreate(&r.end) != cudaSuccess) return;
+  cudaEventRecord(r.beg, s);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].end, st);
+}
 }  // namespace dr4sr
 
+using namespace dr4sr;
+
 extern "C" int dr4sr_abi_version(void) { return DR4SR_ABI_VERSION; }
-extern "C" const char* dr4sr_last_cuda_error(void) { return dr4sr::g_err; }
+extern "C" const char* dr4sr_last_cuda_error(void) { return g_err; }
+extern "C" long long dr4sr_launch_count(void) { return g_launches.load(); }
+
+extern "C" int dr4sr_prof_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return DR4SR_OK;
+}
+
+// Waits for the recorded events, writes "name,launches,total_ms\n" lines (sorted by total time) into buf and
+// clears the records.  Returns the number of bytes written (0 if nothing was recorded).
+extern "C" size_t dr4sr_prof_collect(char* buf, size_t cap) {
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    recs.swap(g_prof);
+  }
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.end) == cudaSuccess && cudaEventElapsedTime(&ms, r.beg, r.end) == cudaSuccess) {
+      auto& a = agg[r.name];
+      a.first += 1; a.second += ms;
+    }
+    cudaEventDestroy(r.beg); cudaEventDestroy(r.end);
+  }
+  std::vector<std::pair<std::string, std::pair<long long, double>>> rows(agg.begin(), agg.end());
+  std::sort(rows.begin(), rows.end(), [](auto& a, auto& b) { return a.second.second > b.second.second; });
+  size_t off = 0;
+  for (auto& r : rows) {
+    char line[160];
+    int n = snprintf(line, sizeof(line), "%s,%lld,%.6f\n", r.first.c_str(), r.second.first, r.second.second);
+    if (n < 0 || off + (size_t)n >= cap) break;
+    memcpy(buf + off, line, (size_t)n);
+    off += (size_t)n;
+  }
+  if (cap) buf[off < cap ? off : cap - 1] = 0;
+  return off;
+}

@@ -186,6 +186,7 @@ int launch_attn_fwd(const float* qkv, const int64_t* in_ids, const int32_t* tok_
   if (L > 64 || D % n_head || (D / n_head) % 4) return DR4SR_EINVAL;
   const int dh = D / n_head;
   const size_t smem = fwd_smem_bytes(L, dh);
+  ProfScope prof("attn_fwd", st);
   static thread_local size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -204,6 +205,7 @@ int launch_attn_bwd(const float* qkv, const float* d_out, const int64_t* in_ids,
   if (L > 64 || D % n_head || (D / n_head) % 4) return DR4SR_EINVAL;
   const int dh = D / n_head;
   const size_t smem = bwd_smem_bytes(L, dh);
+  ProfScope prof("attn_bwd", st);
   static thread_local size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {

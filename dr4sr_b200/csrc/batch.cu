@@ -107,6 +107,7 @@ extern "C" int dr4sr_prep_batch(const int64_t* seqlen, const int64_t* item_id, i
                                 int32_t* tok_off, int32_t* row_seq, int32_t* counts, dr4sr_stream_t stream) {
   if (!seqlen || !tok_off || !row_seq || !counts || B <= 0 || L <= 0) return DR4SR_EINVAL;
   cudaStream_t st = as_stream(stream);
+  ProfScope prof("prep_batch", st);
   prep_scan_kernel<<<1, 1024, 0, st>>>(seqlen, B, L, tok_off, row_seq, counts);
   DR4SR_LAUNCH_CHECK("prep_scan_kernel");
   if (item_id) {
@@ -123,6 +124,7 @@ extern "C" int dr4sr_neg_sample(int64_t* out, int64_t n, int64_t num_items, uint
   if (!out || n < 0 || num_items < 2 || num_items > 0xFFFFFFFFll) return DR4SR_EINVAL;
   if (n == 0) return DR4SR_OK;
   const int blocks = ceil_div(n, 256 * 4) < 4 * kNumSMs ? ceil_div(n, 256 * 4) : 4 * kNumSMs;
+  ProfScope prof("neg_sample", as_stream(stream));
   neg_sample_kernel<<<blocks, 256, 0, as_stream(stream)>>>(out, n, (uint32_t)(num_items - 1), stream_key(seed, step, 0xA11CEu));
   DR4SR_LAUNCH_CHECK("neg_sample_kernel");
   return DR4SR_OK;
@@ -135,6 +137,7 @@ extern "C" int dr4sr_embed_fwd(const float* table, const float* pos, const int64
   const Dropout drop = make_dropout(dropout_p, seed, step, SITE_EMBED, dropout_p > 0.f);
   const int T_cap = B * L;
   const int blocks = ceil_div(T_cap, 8) < 4 * kNumSMs ? ceil_div(T_cap, 8) : 4 * kNumSMs;
+  ProfScope prof("embed_fwd", as_stream(stream));
   embed_fwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(table, pos, in_item_id, tok_off, row_seq, counts, L, D, drop, x0_packed);
   DR4SR_LAUNCH_CHECK("embed_fwd_kernel");
   return DR4SR_OK;

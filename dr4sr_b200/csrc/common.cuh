@@ -12,8 +12,17 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multi
 
 // ---- error plumbing (no exceptions cross the C ABI) -------------------------------------------
 void set_cuda_error(cudaError_t e, const char* where);
+void count_launch();
+// Optional per-kernel timing (bench / profiling only): CUDA events on the launching stream around one
+// launcher scope.  Disabled => two predictable branches, no events.
+struct ProfScope {
+  const char* name; cudaStream_t st; int slot;
+  ProfScope(const char* name, cudaStream_t st);
+  ~ProfScope();
+};
 #define DR4SR_LAUNCH_CHECK(where)                         \
   do {                                                    \
+    ::dr4sr::count_launch();                              \
     cudaError_t e__ = cudaGetLastError();                 \
     if (e__ != cudaSuccess) {                             \
       ::dr4sr::set_cuda_error(e__, where);                \

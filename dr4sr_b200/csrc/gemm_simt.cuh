@@ -39,6 +39,7 @@ struct GemmArgs {
   // LN epilogue (GemmLN kernel only): z = drop(acc + bias) + add ; y = LN(z)
   const float* gamma; const float* beta; float ln_eps;
   float* Z; float* stats;  // Z [M,N] pre-norm sum, stats [M,2] = {mean, rstd}
+  const char* tag;         // name under which the optional event timer files this launch
 };
 
 __device__ __forceinline__ float4 apply_prologue(float4 v, int pro, const Dropout& d, uint32_t idx) {
@@ -284,6 +285,7 @@ template <int BM, int BN, bool A_KC, bool B_KC, bool LN_EPI>
 inline int launch_gemm(const GemmArgs& g, cudaStream_t st) {
   dim3 grid(ceil_div(g.N, BN), A_KC ? ceil_div(g.M, BM) : ceil_div(g.M, BM), A_KC ? 1 : g.n_split);
   if (LN_EPI && g.N != BN) return DR4SR_EINVAL;
+  ProfScope prof(g.tag ? g.tag : "gemm", st);
   gemm_simt_kernel<BM, BN, A_KC, B_KC, LN_EPI><<<grid, 256, 0, st>>>(g);
   DR4SR_LAUNCH_CHECK("gemm_simt_kernel");
   return DR4SR_OK;

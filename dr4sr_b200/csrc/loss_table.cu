@@ -193,6 +193,7 @@ extern "C" int dr4sr_score_bce(const float* q_packed, const float* table, const 
   if (D % 4 || D > 256) return DR4SR_EINVAL;
   const int total = B * L;
   const int blocks = ceil_div(total, 8) < 8 * kNumSMs ? ceil_div(total, 8) : 8 * kNumSMs;
+  ProfScope prof("score_bce", as_stream(stream));
   score_bce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(q_packed, table, item_id, neg_item, tok_off, counts, B, L, D,
                                                            loss_weight, upstream, loss_pos, dscore, dq_packed);
   DR4SR_LAUNCH_CHECK("score_bce_kernel");
@@ -201,6 +202,7 @@ extern "C" int dr4sr_score_bce(const float* q_packed, const float* table, const 
 
 extern "C" int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t stream) {
   if (!x || !out || n < 0) return DR4SR_EINVAL;
+  ProfScope prof("loss_sum", as_stream(stream));
   sum_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n, out);
   DR4SR_LAUNCH_CHECK("sum_kernel");
   return DR4SR_OK;
@@ -216,10 +218,14 @@ extern "C" int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, 
   cudaStream_t st = as_stream(stream);
   const int T_cap = B * L;
   const int blocks = ceil_div(T_cap, 8) < 8 * kNumSMs ? ceil_div(T_cap, 8) : 8 * kNumSMs;
+  {
+  ProfScope prof("table_grad_scatter", st);
   table_grad_kernel<<<blocks, 256, 0, st>>>(dx0_packed, q_packed, dscore, in_item_id, item_id, neg_item, tok_off, row_seq,
                                             counts, L, D, table_grad);
   DR4SR_LAUNCH_CHECK("table_grad_kernel");
+  }
   if (pos_grad && dx0_packed) {
+    ProfScope prof("pos_grad", st);
     pos_grad_kernel<<<dim3(L, ceil_div(D, 128)), 128, 0, st>>>(dx0_packed, tok_off, B, D, pos_grad);
     DR4SR_LAUNCH_CHECK("pos_grad_kernel");
   }
@@ -238,6 +244,7 @@ extern "C" int dr4sr_adam(float* p, float* g, float* m, float* v, int64_t n, int
   const int64_t n4 = n / 4;
   int64_t want = (n4 + 255) / 256;
   const int blocks = (int)(want < 1 ? 1 : (want > 16 * kNumSMs ? 16 * kNumSMs : want));
+  ProfScope prof(n >= (1 << 22) ? "adam_table" : "adam_small", as_stream(stream));
   adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n4, n, step_size, inv_bc2_sqrt, beta1, beta2, eps,
                                                      weight_decay, zero_grad);
   DR4SR_LAUNCH_CHECK("adam_kernel");

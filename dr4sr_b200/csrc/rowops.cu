@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(256) reduce_segments_kernel(ReduceTable tab) {
 int launch_ln_bwd(const float* dy, const float* z, const float* stats, const float* gamma, float* dz, float* partials,
                   int D, int T_cap, const int32_t* tok_dev, Dropout bias_drop, cudaStream_t st) {
   if (D % 4 || D > 256) return DR4SR_EINVAL;
+  ProfScope prof("ln_bwd", st);
   if (D <= 128)
     ln_bwd_kernel<1><<<kLnBwdBlocks, 256, 0, st>>>(dy, z, stats, gamma, dz, partials, D, T_cap, tok_dev, bias_drop);
   else
@@ -127,6 +128,7 @@ int launch_ln_bwd(const float* dy, const float* z, const float* stats, const flo
 
 int launch_colsum(const float* x, int N, int T_cap, const int32_t* tok_dev, float* partials, cudaStream_t st) {
   if (N % 4 || N > 1024) return DR4SR_EINVAL;
+  ProfScope prof("colsum", st);
   colsum_kernel<<<kColsumBlocks, 256, 0, st>>>(x, N, T_cap, tok_dev, partials);
   DR4SR_LAUNCH_CHECK("colsum_kernel");
   return DR4SR_OK;
@@ -135,6 +137,7 @@ int launch_colsum(const float* x, int N, int T_cap, const int32_t* tok_dev, floa
 int launch_reduce_segments(const ReduceTable& tab, cudaStream_t st) {
   if (tab.count <= 0) return DR4SR_OK;
   if (tab.count > kMaxSeg) return DR4SR_EINVAL;
+  ProfScope prof("reduce_partials", st);
   int nmax = 0;
   for (int i = 0; i < tab.count; ++i) nmax = nmax > tab.seg[i].n ? nmax : tab.seg[i].n;
   dim3 grid(ceil_div(nmax, 256) < 64 ? ceil_div(nmax, 256) : 64, tab.count);

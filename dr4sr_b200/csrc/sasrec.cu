@@ -169,7 +169,7 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
     float* x2 = (l == c->n_layer - 1 && q_packed) ? q_packed : y.x2;
     {  // QKV projection
       GemmArgs g = gemm_args(x, D, lp + lo.in_w, D, y.qkv, 3 * D, T, 3 * D, D, counts);
-      g.bias = lp + lo.in_b;
+      g.bias = lp + lo.in_b; g.tag = "gemm_qkv";
       DR4SR_TRY(gemm_nt(g, st));
     }
     DR4SR_TRY(launch_attn_fwd(y.qkv, in_item_id, tok_off, y.attn, c->B, c->L, D, c->n_head,
@@ -178,12 +178,12 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
       GemmArgs g = gemm_args(y.attn, D, lp + lo.out_w, D, y.x1, D, T, D, D, counts);
       g.bias = lp + lo.out_b; g.add = x; g.ldadd = D;
       g.dropE = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_OUT, l), tr);
-      g.gamma = lp + lo.g1; g.beta = lp + lo.be1; g.ln_eps = c->ln_eps; g.Z = y.z1; g.stats = y.st1;
+      g.gamma = lp + lo.g1; g.beta = lp + lo.be1; g.ln_eps = c->ln_eps; g.Z = y.z1; g.stats = y.st1; g.tag = "gemm_outproj_ln";
       DR4SR_TRY(gemm_ln(g, D, st));
     }
     {  // FFN up-projection (pre-activation kept for the backward)
       GemmArgs g = gemm_args(y.x1, D, lp + lo.w1, D, y.pre, F, T, F, D, counts);
-      g.bias = lp + lo.b1;
+      g.bias = lp + lo.b1; g.tag = "gemm_ffn1";
       DR4SR_TRY(gemm_nt(g, st));
     }
     {  // gelu + dropout (prologue) -> down-projection + dropout + residual + LN2
@@ -191,17 +191,19 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
       g.proA = PRO_GELU_DROP; g.dropA = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_H, l), tr);
       g.bias = lp + lo.b2; g.add = y.x1; g.ldadd = D;
       g.dropE = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_OUT, l), tr);
-      g.gamma = lp + lo.g2; g.beta = lp + lo.be2; g.ln_eps = c->ln_eps; g.Z = y.z2; g.stats = y.st2;
+      g.gamma = lp + lo.g2; g.beta = lp + lo.be2; g.ln_eps = c->ln_eps; g.Z = y.z2; g.stats = y.st2; g.tag = "gemm_ffn2_ln";
       DR4SR_TRY(gemm_ln(g, D, st));
     }
     x = x2;
   }
   if (q_last) {
+    ProfScope prof("gather_last", st);
     gather_last_kernel<<<ceil_div(c->B, 8), 256, 0, st>>>(x, tok_off, c->B, D, q_last);
     DR4SR_LAUNCH_CHECK("gather_last_kernel");
   }
   if (q_dense) {
     const int blocks = ceil_div(T, 8) < 8 * kNumSMs ? ceil_div(T, 8) : 8 * kNumSMs;
+    ProfScope prof("unpack_dense", st);
     unpack_dense_kernel<<<blocks, 256, 0, st>>>(x, tok_off, c->B, c->L, D, q_dense);
     DR4SR_LAUNCH_CHECK("unpack_dense_kernel");
   }
@@ -241,39 +243,41 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
     {  // dpre = ((dz2 * mask_out) W2) * mask_h * gelu'(pre)
       GemmArgs g = gemm_args(w.g1, D, lp + lo.w2, F, w.dpre, F, T, F, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_ffn_out;
-      g.epi = EPI_GELU_BWD; g.pre = y.pre; g.dropE = d_ffn_h;
+      g.epi = EPI_GELU_BWD; g.pre = y.pre; g.dropE = d_ffn_h; g.tag = "gemm_bwd_dpre";
       DR4SR_TRY(gemm_nn(g, st));
     }
     {  // dW2[d,f] = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]
       GemmArgs g = gemm_args(w.g1, D, y.pre, F, nullptr, F, D, F, T, counts);
-      g.proA = PRO_DROPMASK; g.dropA = d_ffn_out; g.proB = PRO_GELU_DROP; g.dropB = d_ffn_h;
+      g.proA = PRO_DROPMASK; g.dropA = d_ffn_out; g.proB = PRO_GELU_DROP; g.dropB = d_ffn_h; g.tag = "gemm_wgrad_w2";
       DR4SR_TRY(gemm_tn(g, w.part_w + pw_w2, st));
     }
     {  // dW1[f,d] = sum_m dpre[m,f] * x1[m,d]
       GemmArgs g = gemm_args(w.dpre, F, y.x1, D, nullptr, D, F, D, T, counts);
+      g.tag = "gemm_wgrad_w1";
       DR4SR_TRY(gemm_tn(g, w.part_w + pw_w1, st));
     }
     DR4SR_TRY(launch_colsum(w.dpre, F, T, counts, w.part_cs_b1, st));
     {  // dx1 = dz2 + dpre W1   -> g0
       GemmArgs g = gemm_args(w.dpre, F, lp + lo.w1, D, w.g0, D, T, D, F, counts);
-      g.add = w.g1; g.ldadd = D;
+      g.add = w.g1; g.ldadd = D; g.tag = "gemm_bwd_dx1";
       DR4SR_TRY(gemm_nn(g, st));
     }
     // LN1 backward: g1 = dz1 ; partials -> dgamma1, dbeta1, db_out
     DR4SR_TRY(launch_ln_bwd(w.g0, y.z1, y.st1, lp + lo.g1, w.g1, w.part_ln1, D, T, counts, d_attn_out, st));
     {  // d(attn) = (dz1 * mask) Wo -> g2
       GemmArgs g = gemm_args(w.g1, D, lp + lo.out_w, D, w.g2, D, T, D, D, counts);
-      g.proA = PRO_DROPMASK; g.dropA = d_attn_out;
+      g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_bwd_dattn";
       DR4SR_TRY(gemm_nn(g, st));
     }
     {  // dWo[n,k] = sum_m (dz1*mask)[m,n] * attn[m,k]
       GemmArgs g = gemm_args(w.g1, D, y.attn, D, nullptr, D, D, D, T, counts);
-      g.proA = PRO_DROPMASK; g.dropA = d_attn_out;
+      g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_wgrad_out";
       DR4SR_TRY(gemm_tn(g, w.part_w + pw_out, st));
     }
     DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, w.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
     {  // dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
       GemmArgs g = gemm_args(w.dqkv, 3 * D, xin, D, nullptr, D, 3 * D, D, T, counts);
+      g.tag = "gemm_wgrad_in";
       DR4SR_TRY(gemm_tn(g, w.part_w + pw_in, st));
     }
     DR4SR_TRY(launch_colsum(w.dqkv, 3 * D, T, counts, w.part_cs_in, st));
@@ -282,6 +286,7 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
       GemmArgs g = gemm_args(w.dqkv, 3 * D, lp + lo.in_w, D, dst, D, T, D, 3 * D, counts);
       g.add = w.g1; g.ldadd = D;
       if (l == 0) g.dropE = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
+      g.tag = "gemm_bwd_dx";
       DR4SR_TRY(gemm_nn(g, st));
     }
     {  // fixed-order reduction of every partial of this layer into the flat gradient buffer

@@ -155,20 +155,25 @@ extern "C" int dr4sr_topk(const float* q, const float* table, const uint8_t* ite
   const size_t n_al = ((size_t)N + 127) & ~(size_t)127;   // padded row stride: 16-byte stores, whole tiles
   float* bias = reinterpret_cast<float*>(ws);
   float* scores = bias + n_al;
+  {
+  ProfScope prof("topk_dead_bias", st);
   dead_bias_kernel<<<ceil_div(n_al, 256) < 4 * kNumSMs ? ceil_div(n_al, 256) : 4 * kNumSMs, 256, 0, st>>>(item_dead, N, (int64_t)n_al, bias);
   DR4SR_LAUNCH_CHECK("dead_bias_kernel");
+  }
   {
     GemmArgs g = gemm_args(q, D, table, D, scores, (int)n_al, B, (int)n_al, D, nullptr);
-    g.bias = bias; g.b_rows = (int)N;
+    g.bias = bias; g.b_rows = (int)N; g.tag = "topk_logits_gemm";
     DR4SR_TRY((launch_gemm<128, 128, true, true, false>(g, st)));
   }
   if (user_hist && H > 0) {
+    ProfScope prof("topk_mask_hist", st);
     mask_hist_kernel<<<ceil_div((int64_t)B * H, 256), 256, 0, st>>>(user_hist, B, H, N, (int64_t)n_al, scores);
     DR4SR_LAUNCH_CHECK("mask_hist_kernel");
   }
   int kpad = 32;
   while (kpad < k) kpad <<= 1;
   const size_t smem = sizeof(uint32_t) * (256 + 2 * (size_t)kpad);
+  ProfScope prof("topk_select", st);
   topk_select_kernel<<<B, kSelThreads, smem, st>>>(scores, N, (int64_t)n_al, k, kpad, out_scores, out_ids);
   DR4SR_LAUNCH_CHECK("topk_select_kernel");
   return DR4SR_OK;

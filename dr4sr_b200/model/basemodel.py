@@ -139,12 +139,30 @@ class BaseModel(nn.Module):
             return BPRLoss()
         raise NotImplementedError(kind)
 
+    # ---- data parallel (no reference counterpart: the reference is single-device) -----------------
+    def enable_data_parallel(self, group) -> None:
+        """Replicated parameters, batch sharded over the ranks of `group`.  The loss normaliser n and the
+        gradients are summed over ranks, so N ranks x B sequences compute exactly the single-process step
+        on the N*B global batch (up to fp32 summation order)."""
+        self._dp_group = group
+
+    def _dp_sum(self, *tensors) -> None:
+        grp = getattr(self, '_dp_group', None)
+        if grp is not None:
+            import torch.distributed as dist
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=grp)
+
     # ---- hot path ---------------------------------------------------------------------------
     def _neg_sampling(self, batch):
         """One uniform negative per target slot, shape target.shape + (1,) (basemodel.py:50-61)."""
         tgt = batch[self.fiid]
         self._neg_step += 1
-        return _engine.neg_sample(tuple(tgt.shape) + (1,), self.num_items, self.config['train'].get('seed', 0),
+        rank = 0
+        if getattr(self, '_dp_group', None) is not None:
+            import torch.distributed as dist
+            rank = dist.get_rank(self._dp_group)
+        return _engine.neg_sample(tuple(tgt.shape) + (1,), self.num_items, self.config['train'].get('seed', 0) + 7919 * rank,
                                   self._neg_step, tgt.device)
 
     def _publish_grads(self) -> None:

@@ -56,6 +56,7 @@ class _EncodeScoreBCE(torch.autograd.Function):
         model._check_flat()
         in_ids, item_id, neg = batch['in_' + model.fiid], batch[model.fiid], batch['neg_item']
         b = eng.prep(batch['seqlen'], item_id)
+        model._dp_sum(b.counts[1:2])          # data parallel: normalise by the global number of valid targets
         if model.training:
             eng.step += 1
         q_dense = None
@@ -64,6 +65,8 @@ class _EncodeScoreBCE(torch.autograd.Function):
         eng.encode(b, table, model._flat, in_ids, train=model.training, q_dense=q_dense)
         eng.score_bce(b, table, item_id, neg.view(item_id.shape), want_grad=False)
         loss = eng.reduce_loss(b).clone() if reduce else b.loss_pos.clone()
+        if reduce:
+            model._dp_sum(loss)
         ctx.model, ctx.bufs, ctx.reduce = model, b, reduce
         ctx.ids = (in_ids, item_id, neg.view(item_id.shape))
         eng.fwd_token += 1
@@ -97,6 +100,7 @@ class _EncodeScoreBCE(torch.autograd.Function):
         eng.encode_bwd(b, table, model._flat, in_ids, model._flat_grad)
         tg = model._table_grad_buffer()
         eng.table_grad(b, in_ids, item_id, neg, tg, model._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
+        model._dp_sum(model._flat_grad, tg)
         model._publish_grads()
         return None, None, None, None, None
 

@@ -46,6 +46,14 @@ DR4SR_API int dr4sr_abi_version(void);
 /* last CUDA error string seen by this thread's most recent failing call ("" if none) */
 DR4SR_API const char* dr4sr_last_cuda_error(void);
 
+/* Measurement hooks (bench / profiling only; not on the product path).
+ * dr4sr_launch_count: kernels launched by this library since load.
+ * dr4sr_prof_enable(1): bracket every launcher with CUDA events on its stream; dr4sr_prof_collect waits
+ * for them and writes "name,launches,total_ms\n" lines sorted by total time into buf (returns bytes). */
+DR4SR_API long long dr4sr_launch_count(void);
+DR4SR_API int dr4sr_prof_enable(int on);
+DR4SR_API size_t dr4sr_prof_collect(char* buf, size_t cap);
+
 /* ------------------------------------------------------------------------------------------------
  * Batch preparation: packed-token index from `seqlen`, loss normaliser from `item_id`.
  * Replaces the mask construction at model/sasrec.py:48,58 and `(~padding_mask).sum()` at
