@@ -4,78 +4,156 @@
 // torch.nn.TransformerEncoderLayer at reference model/sasrec.py:65-68:
 //   S = Q_h K_h^T / sqrt(d_h) + M,  M[i,j] = -inf if j > i or in_id[b,j] == 0
 //   A = dropout(softmax_j S);  O_h = A V_h
-// A whole (sequence, head) problem is 50 x 50 x 64 -- it lives in one CTA's shared memory, so the
-// score matrix never touches HBM and the backward recomputes the probabilities instead of storing
-// them.  One CTA per (sequence, head); only the t < seqlen rows exist (packed layout).
+// A whole (sequence, head) problem is at most 64 x 64 x 64: it lives in one CTA's shared memory, the
+// score matrix never touches HBM, and the backward recomputes the probabilities instead of storing
+// them.  One CTA (256 threads) per (sequence, head); only the t < seqlen rows exist (packed layout).
+//
+// Register tiling: the two matmul shapes of the problem are
+//   abt : C[i][j] = sum_d A[i][d] B[j][d]      -- 4x4 outputs per thread, rows strided by 16 so that the
+//         float4 reads of 8 neighbouring lanes fall in 8 different 16-byte bank groups (ld % 32 == 4)
+//   pv  : C[r][d] = sum_x S(r,x) M[x][d]       -- 4 rows x one float4 of d per thread
+// i.e. 64 (resp. 16) FMAs per 8 (resp. 5) shared loads instead of 1 FMA per 2 loads.
 #include "internal.cuh"
 
 namespace dr4sr {
 namespace {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;
 
-struct AttnSmem {
-  float *Q, *K, *V, *S;
-  int* pad;
-  int ldk, lds;
+__host__ __device__ inline int round4(int x) { return (x + 3) & ~3; }
+
+struct Tile {            // shared-memory geometry of one (sequence, head) problem
+  int rows, ld, lds;     // rows = L rounded up to 16; ld = dh + 4; lds = rows rounded up to 32, + 4 (lds % 32 == 4)
 };
-
-__device__ __forceinline__ AttnSmem carve_fwd(float* sm, int L, int dh) {
-  AttnSmem a;
-  a.ldk = dh + 1; a.lds = L + 1;
-  a.Q = sm; a.K = a.Q + L * dh; a.V = a.K + L * a.ldk; a.S = a.V + L * dh;
-  a.pad = reinterpret_cast<int*>(a.S + L * a.lds);
-  return a;
+__host__ __device__ inline Tile make_tile(int L, int dh) {
+  Tile t;
+  t.rows = (L + 15) & ~15;
+  t.ld = dh + 4;
+  t.lds = ((t.rows + 31) / 32) * 32 + 4;
+  return t;
 }
-inline size_t fwd_smem_bytes(int L, int dh) { return sizeof(float) * (size_t)(L * dh + L * (dh + 1) + L * dh + L * (L + 1) + L); }
 
-// loads the head slices of Q, K, V (and optionally dO) for one sequence; K is row-padded (+1) so the
-// j-strided reads of the score loop are bank-conflict free
-__device__ __forceinline__ void load_head(const float* __restrict__ qkv, int off, int len, int D, int h, int dh, float* Q,
-                                          float* K, int ldk, float* V, int ldv) {
-  const int f4_per_row = dh / 4;
-  for (int e = threadIdx.x; e < len * f4_per_row; e += blockDim.x) {
-    const int r = e / f4_per_row, c = (e % f4_per_row) * 4;
-    const float* src = qkv + (size_t)(off + r) * 3 * D + h * dh + c;
-    const float4 q = *reinterpret_cast<const float4*>(src);
-    const float4 k = *reinterpret_cast<const float4*>(src + D);
-    const float4 v = *reinterpret_cast<const float4*>(src + 2 * D);
-    *reinterpret_cast<float4*>(Q + r * dh + c) = q;
-    float* kd = K + r * ldk + c;
-    kd[0] = k.x; kd[1] = k.y; kd[2] = k.z; kd[3] = k.w;
-    float* vd = V + r * ldv + c;
-    vd[0] = v.x; vd[1] = v.y; vd[2] = v.z; vd[3] = v.w;
+// rows [0,len) of one head slice of a packed [T, stride] matrix -> smem [rows][ld]
+__device__ __forceinline__ void load_rows(const float* __restrict__ src, int stride, int len, int dh, float* dst, int ld) {
+  const int f4 = dh / 4;
+  for (int e = threadIdx.x; e < len * f4; e += blockDim.x) {
+    const int r = e / f4, c = (e % f4) * 4;
+    *reinterpret_cast<float4*>(dst + r * ld + c) = *reinterpret_cast<const float4*>(src + (size_t)r * stride + c);
   }
 }
 
-// S[i][j] = softmax_j(scale * <Q_i, K_j> + mask); rows owned by warps, two keys per lane (L <= 64)
-__device__ __forceinline__ void scores_softmax(const AttnSmem& a, int len, int dh, float scale) {
-  for (int e = threadIdx.x; e < len * len; e += blockDim.x) {
-    const int i = e / len, j = e % len;
-    float s = -INFINITY;
-    if (j <= i && !a.pad[j]) {
-      float acc = 0.f;
-      const float* q = a.Q + i * dh;
-      const float* k = a.K + j * a.ldk;
-#pragma unroll 8
-      for (int d = 0; d < dh; ++d) acc = fmaf(q[d], k[d], acc);
-      s = acc * scale;
+// Q, K, V head slices in one pass: three independent 16-byte loads in flight per iteration
+__device__ __forceinline__ void load_qkv(const float* __restrict__ src, int D, int len, int dh, float* Q, float* K, float* V, int ld) {
+  const int f4 = dh / 4;
+  for (int e = threadIdx.x; e < len * f4; e += blockDim.x) {
+    const int r = e / f4, c = (e % f4) * 4;
+    const float* p = src + (size_t)r * 3 * D + c;
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    const float4 k = *reinterpret_cast<const float4*>(p + D);
+    const float4 v = *reinterpret_cast<const float4*>(p + 2 * D);
+    *reinterpret_cast<float4*>(Q + r * ld + c) = q;
+    *reinterpret_cast<float4*>(K + r * ld + c) = k;
+    *reinterpret_cast<float4*>(V + r * ld + c) = v;
+  }
+}
+
+// C[i][j] = sum_d A[i][d] * B[j][d] for j <= i < len; thread (ti, tj) owns i = ti + 16a, j = tj + 16b.
+// Whole 16x16 blocks are skipped uniformly across the CTA: blocks beyond ceil(len/16) and the blocks
+// b > a that lie strictly above the causal diagonal (their outputs are reported as `above`).
+// Rows >= len of A / B hold stale shared memory; each output depends only on its own two rows, and
+// outputs with i or j >= len are never reported.
+template <class Out>
+__device__ __forceinline__ void mm_abt(const float* __restrict__ A, const float* __restrict__ B, int ld, int len, int dh, Out out) {
+  const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+  const int nblk = (len + 15) >> 4;                       // CTA-uniform
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  for (int d = 0; d < dh; d += 4) {
+    float4 av[4], bv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (a < nblk) {
+        av[a] = *reinterpret_cast<const float4*>(A + (ti + 16 * a) * ld + d);
+        bv[a] = *reinterpret_cast<const float4*>(B + (tj + 16 * a) * ld + d);
+      }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (a < nblk) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]);
+          acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
+          acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]);
+          acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
+        }
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ti + 16 * a, j = tj + 16 * b;
+      if (i < len && j < len) out(i, j, acc[a][b], b > a);
     }
-    a.S[i * a.lds + j] = s;
+}
+
+// C[r][4c..4c+3] = sum_x S(r,x) * M[x][4c..], S(r,x) = TRANS ? S[x][r] : S[r][x].
+// Causal structure: !TRANS sums x <= r (keys up to the query), TRANS sums x >= r (queries from the key
+// on); S holds exact zeros outside the band, so the loop bounds only have to cover it.
+template <bool TRANS, class Out>
+__device__ __forceinline__ void mm_pv(const float* __restrict__ S, int lds, const float* __restrict__ M, int ld, int len, int dh, Out out) {
+  const int ncol = dh / 4;                       // float4 columns (16 for dh = 64)
+  const int tc = threadIdx.x % ncol, tr = threadIdx.x / ncol;
+  const int rstep = kAttnThreads / ncol;         // row stride between a thread's rows (16 for dh = 64)
+  for (int r0 = tr; r0 < len; r0 += 4 * rstep) {
+    const int na = min(4, (len - r0 + rstep - 1) / rstep);          // live rows of this thread
+    const int na_u = min(4, (len - (r0 - tr) + rstep - 1) / rstep); // CTA-uniform bound for the unrolled body
+    float4 acc[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int x_lo = TRANS ? r0 : 0, x_hi = TRANS ? len : min(len, r0 + (na - 1) * rstep + 1);
+    for (int x = x_lo; x < x_hi; ++x) {
+      const float4 m = *reinterpret_cast<const float4*>(M + x * ld + tc * 4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a < na_u) {
+          const int r = r0 + a * rstep;
+          float s = 0.f;
+          if (r < len) s = TRANS ? S[x * lds + r] : S[r * lds + x];
+          acc[a].x = fmaf(s, m.x, acc[a].x); acc[a].y = fmaf(s, m.y, acc[a].y);
+          acc[a].z = fmaf(s, m.z, acc[a].z); acc[a].w = fmaf(s, m.w, acc[a].w);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (r0 + a * rstep < len) out(r0 + a * rstep, tc * 4, acc[a]);
   }
-  __syncthreads();
+}
+
+// P[i][j] = softmax_j(S[i][j]) over j < len (masked entries hold -inf -> exactly 0).  Forward: S is
+// overwritten with dropout(P).  Backward (Pd != null): S <- P and Pd <- dropout(P).
+// One warp per row, two keys per lane (L <= 64).
+__device__ __forceinline__ void softmax_rows(float* S, float* Pd, int lds, int len, const Dropout& drop, uint32_t base, int L) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   for (int i = warp; i < len; i += nwarp) {
-    float* row = a.S + i * a.lds;
+    float* row = S + i * lds;
     const float s0 = lane < len ? row[lane] : -INFINITY;
     const float s1 = lane + 32 < len ? row[lane + 32] : -INFINITY;
     const float mx = warp_max(fmaxf(s0, s1));
-    const float e0 = expf(s0 - mx), e1 = expf(s1 - mx);   // exp(-inf - mx) = 0 at masked keys
+    const float e0 = expf(s0 - mx), e1 = expf(s1 - mx);
     const float inv = 1.0f / warp_sum(e0 + e1);
-    if (lane < len) row[lane] = e0 * inv;
-    if (lane + 32 < len) row[lane + 32] = e1 * inv;
+    const float p0 = e0 * inv, p1 = e1 * inv;
+    if (Pd) {
+      if (lane < len) { row[lane] = p0; Pd[i * lds + lane] = drop.apply(p0, base + i * L + lane); }
+      if (lane + 32 < len) { row[lane + 32] = p1; Pd[i * lds + lane + 32] = drop.apply(p1, base + i * L + lane + 32); }
+    } else {
+      if (lane < len) row[lane] = drop.apply(p0, base + i * L + lane);
+      if (lane + 32 < len) row[lane + 32] = drop.apply(p1, base + i * L + lane + 32);
+    }
   }
-  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ in_ids,
@@ -86,24 +164,21 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __r
   const int off = tok_off[b], len = min(tok_off[b + 1] - off, L);
   if (len <= 0) return;
   const int dh = D / n_head;
-  AttnSmem a = carve_fwd(sm, L, dh);
-  load_head(qkv, off, len, D, h, dh, a.Q, a.K, a.ldk, a.V, dh);
-  for (int j = threadIdx.x; j < len; j += blockDim.x) a.pad[j] = in_ids[(size_t)b * L + j] == 0;
+  const Tile t = make_tile(L, dh);
+  float* Q = sm; float* K = Q + t.rows * t.ld; float* V = K + t.rows * t.ld; float* S = V + t.rows * t.ld;
+  int* pad = reinterpret_cast<int*>(S + t.rows * t.lds);
+  const float* base_q = qkv + (size_t)off * 3 * D + h * dh;
+  load_qkv(base_q, D, len, dh, Q, K, V, t.ld);
+  for (int j = threadIdx.x; j < len; j += blockDim.x) pad[j] = in_ids[(size_t)b * L + j] == 0;
   __syncthreads();
-  scores_softmax(a, len, dh, scale);
-  const uint32_t base = (uint32_t)(b * n_head + h) * (uint32_t)(L * L);
-  for (int e = threadIdx.x; e < len * dh; e += blockDim.x) {
-    const int i = e / dh, d = e % dh;
-    const float* p = a.S + i * a.lds;
-    float acc = 0.f;
-    for (int j = 0; j <= i; ++j) acc = fmaf(drop.apply(p[j], base + i * L + j), a.V[j * dh + d], acc);
-    out[(size_t)(off + i) * D + h * dh + d] = acc;
-  }
-}
-
-__host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
-inline size_t bwd_smem_bytes(int L, int dh) {
-  return sizeof(float) * (size_t)(L * dh + 2 * align4(L * (dh + 1)) + L * dh + 2 * align4(L * (L + 1)) + L);
+  mm_abt(Q, K, t.ld, len, dh, [&](int i, int j, float v, bool above) {
+    S[i * t.lds + j] = (!above && j <= i && !pad[j]) ? v * scale : -INFINITY;
+  });
+  __syncthreads();
+  softmax_rows(S, nullptr, t.lds, len, drop, (uint32_t)(b * n_head + h) * (uint32_t)(L * L), L);
+  __syncthreads();
+  float* dst = out + (size_t)off * D + h * dh;
+  mm_pv<false>(S, t.lds, V, t.ld, len, dh, [&](int i, int c, float4 v) { *reinterpret_cast<float4*>(dst + (size_t)i * D + c) = v; });
 }
 
 // dQKV from dO, recomputing the probabilities (no [B,H,L,L] tensor is ever stored)
@@ -116,84 +191,77 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __r
   const int off = tok_off[b], len = min(tok_off[b + 1] - off, L);
   if (len <= 0) return;
   const int dh = D / n_head;
-  AttnSmem a;
-  a.ldk = dh + 1; a.lds = L + 1;
-  a.Q = sm; a.K = a.Q + L * dh; a.V = a.K + align4(L * a.ldk);   // V row-padded too (j-strided reads below)
-  float* dO = a.V + align4(L * a.ldk);                           // [L][dh], 16-byte aligned
-  a.S = dO + L * dh;                                             // P  [L][L+1]
-  float* dS = a.S + align4(L * a.lds);                           // dS [L][L+1]
-  a.pad = reinterpret_cast<int*>(dS + align4(L * a.lds));
-  load_head(qkv, off, len, D, h, dh, a.Q, a.K, a.ldk, a.V, a.ldk);
-  for (int e = threadIdx.x; e < len * (dh / 4); e += blockDim.x) {
-    const int r = e / (dh / 4), c = (e % (dh / 4)) * 4;
-    *reinterpret_cast<float4*>(dO + r * dh + c) =
-        *reinterpret_cast<const float4*>(d_out + (size_t)(off + r) * D + h * dh + c);
-  }
-  for (int j = threadIdx.x; j < len; j += blockDim.x) a.pad[j] = in_ids[(size_t)b * L + j] == 0;
+  const Tile t = make_tile(L, dh);
+  const int msz = t.rows * t.ld, ssz = t.rows * t.lds;
+  float* Q = sm; float* K = Q + msz; float* V = K + msz; float* dO = V + msz;
+  float* P = dO + msz; float* W = P + ssz;                  // W: Pd, then dP, then dS
+  int* pad = reinterpret_cast<int*>(W + ssz);
+  const float* base_q = qkv + (size_t)off * 3 * D + h * dh;
+  load_qkv(base_q, D, len, dh, Q, K, V, t.ld);
+  load_rows(d_out + (size_t)off * D + h * dh, D, len, dh, dO, t.ld);
+  for (int j = threadIdx.x; j < len; j += blockDim.x) pad[j] = in_ids[(size_t)b * L + j] == 0;
   __syncthreads();
-  scores_softmax(a, len, dh, scale);
   const uint32_t base = (uint32_t)(b * n_head + h) * (uint32_t)(L * L);
-
-  // dP[i][j] = factor * <dO_i, V_j>  (gradient w.r.t. the pre-dropout probability)
-  for (int e = threadIdx.x; e < len * len; e += blockDim.x) {
-    const int i = e / len, j = e % len;
-    float v = 0.f;
-    if (j <= i && !a.pad[j]) {
-      float acc = 0.f;
-      const float* g = dO + i * dh;
-      const float* vv = a.V + j * a.ldk;
-#pragma unroll 8
-      for (int d = 0; d < dh; ++d) acc = fmaf(g[d], vv[d], acc);
-      v = acc * drop.factor(base + i * L + j);
-    }
-    dS[i * a.lds + j] = v;
-  }
+  mm_abt(Q, K, t.ld, len, dh, [&](int i, int j, float v, bool above) {
+    P[i * t.lds + j] = (!above && j <= i && !pad[j]) ? v * scale : -INFINITY;
+  });
   __syncthreads();
-  // dS = P * (dP - sum_j dP P)
-  {
+  softmax_rows(P, W, t.lds, len, drop, base, L);            // P = softmax, W = dropout(P)
+  __syncthreads();
+  float* dst = d_qkv + (size_t)off * 3 * D + h * dh;
+  // dV_j = sum_{i>=j} Pd_ij dO_i
+  mm_pv<true>(W, t.lds, dO, t.ld, len, dh, [&](int j, int c, float4 v) { *reinterpret_cast<float4*>(dst + (size_t)j * 3 * D + 2 * D + c) = v; });
+  __syncthreads();
+  // dP_ij = factor_ij <dO_i, V_j> on the causal, non-pad band (0 elsewhere)
+  mm_abt(dO, V, t.ld, len, dh, [&](int i, int j, float v, bool above) {
+    W[i * t.lds + j] = (!above && j <= i && !pad[j]) ? v * drop.factor(base + i * L + j) : 0.f;
+  });
+  __syncthreads();
+  {  // dS = P * (dP - sum_j dP P), pre-multiplied by the 1/sqrt(d_h) of the score
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     for (int i = warp; i < len; i += nwarp) {
-      float* g = dS + i * a.lds;
-      const float* p = a.S + i * a.lds;
+      float* g = W + i * t.lds;
+      const float* p = P + i * t.lds;
       const float g0 = lane < len ? g[lane] : 0.f, p0 = lane < len ? p[lane] : 0.f;
       const float g1 = lane + 32 < len ? g[lane + 32] : 0.f, p1 = lane + 32 < len ? p[lane + 32] : 0.f;
       const float dot = warp_sum(fmaf(g0, p0, g1 * p1));
-      if (lane < len) g[lane] = p0 * (g0 - dot);
-      if (lane + 32 < len) g[lane + 32] = p1 * (g1 - dot);
+      if (lane < len) g[lane] = p0 * (g0 - dot) * scale;
+      if (lane + 32 < len) g[lane + 32] = p1 * (g1 - dot) * scale;
     }
   }
   __syncthreads();
-  // dQ_i = scale sum_{j<=i} dS_ij K_j ; dK_j = scale sum_{i>=j} dS_ij Q_i ; dV_j = sum_{i>=j} Pdrop_ij dO_i
-  for (int e = threadIdx.x; e < len * dh; e += blockDim.x) {
-    const int r = e / dh, d = e % dh;
-    float dq = 0.f, dk = 0.f, dv = 0.f;
-    for (int j = 0; j <= r; ++j) dq = fmaf(dS[r * a.lds + j], a.K[j * a.ldk + d], dq);
-    for (int i = r; i < len; ++i) {
-      dk = fmaf(dS[i * a.lds + r], a.Q[i * dh + d], dk);
-      dv = fmaf(drop.apply(a.S[i * a.lds + r], base + i * L + r), dO[i * dh + d], dv);
-    }
-    float* dst = d_qkv + (size_t)(off + r) * 3 * D + h * dh + d;
-    dst[0] = dq * scale;
-    dst[D] = dk * scale;
-    dst[2 * D] = dv;
-  }
+  // dQ_i = sum_{j<=i} dS_ij K_j ; dK_j = sum_{i>=j} dS_ij Q_i
+  mm_pv<false>(W, t.lds, K, t.ld, len, dh, [&](int i, int c, float4 v) { *reinterpret_cast<float4*>(dst + (size_t)i * 3 * D + c) = v; });
+  mm_pv<true>(W, t.lds, Q, t.ld, len, dh, [&](int j, int c, float4 v) { *reinterpret_cast<float4*>(dst + (size_t)j * 3 * D + D + c) = v; });
+}
+
+inline size_t fwd_smem_bytes(int L, int dh) {
+  const Tile t = make_tile(L, dh);
+  return sizeof(float) * (size_t)(3 * t.rows * t.ld + t.rows * t.lds + t.rows);
+}
+inline size_t bwd_smem_bytes(int L, int dh) {
+  const Tile t = make_tile(L, dh);
+  return sizeof(float) * (size_t)(4 * t.rows * t.ld + 2 * t.rows * t.lds + t.rows);
+}
+
+int check_shape(int L, int D, int n_head) {
+  if (L > 64 || L <= 0 || D % n_head) return DR4SR_EINVAL;
+  const int dh = D / n_head;
+  if (dh % 4 || dh > 64 || kAttnThreads % (dh / 4)) return DR4SR_EINVAL;
+  return DR4SR_OK;
 }
 
 }  // namespace
 
 int launch_attn_fwd(const float* qkv, const int64_t* in_ids, const int32_t* tok_off, float* out, int B, int L, int D,
                     int n_head, Dropout drop, cudaStream_t st) {
-  if (L > 64 || D % n_head || (D / n_head) % 4) return DR4SR_EINVAL;
+  DR4SR_TRY(check_shape(L, D, n_head));
   const int dh = D / n_head;
   const size_t smem = fwd_smem_bytes(L, dh);
   ProfScope prof("attn_fwd", st);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      set_cuda_error(cudaGetLastError(), "attn_fwd smem attribute");
-      return DR4SR_ECUDA;
-    }
-    configured = smem;
+  if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "attn_fwd smem attribute");
+    return DR4SR_ECUDA;
   }
   attn_fwd_kernel<<<B * n_head, kAttnThreads, smem, st>>>(qkv, in_ids, tok_off, out, L, D, n_head, 1.0f / sqrtf((float)dh), drop);
   DR4SR_LAUNCH_CHECK("attn_fwd_kernel");
@@ -202,17 +270,13 @@ int launch_attn_fwd(const float* qkv, const int64_t* in_ids, const int32_t* tok_
 
 int launch_attn_bwd(const float* qkv, const float* d_out, const int64_t* in_ids, const int32_t* tok_off, float* d_qkv,
                     int B, int L, int D, int n_head, Dropout drop, cudaStream_t st) {
-  if (L > 64 || D % n_head || (D / n_head) % 4) return DR4SR_EINVAL;
+  DR4SR_TRY(check_shape(L, D, n_head));
   const int dh = D / n_head;
   const size_t smem = bwd_smem_bytes(L, dh);
   ProfScope prof("attn_bwd", st);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-      set_cuda_error(cudaGetLastError(), "attn_bwd smem attribute");
-      return DR4SR_ECUDA;
-    }
-    configured = smem;
+  if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "attn_bwd smem attribute");
+    return DR4SR_ECUDA;
   }
   attn_bwd_kernel<<<B * n_head, kAttnThreads, smem, st>>>(qkv, d_out, in_ids, tok_off, d_qkv, L, D, n_head,
                                                           1.0f / sqrtf((float)dh), drop);

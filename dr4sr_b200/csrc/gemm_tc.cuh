@@ -1,0 +1,392 @@
+// gemm_tc.cuh -- tcgen05 / TMEM GEMM for the encoder's dense layers with fp32-grade products.
+//
+//   C[m,n] (+epilogue) = sum_k proA(A)[m,k] * W[n,k]       A: fp32 activations in HBM (k contiguous)
+//
+// The reference runs these layers as true-fp32 cuBLAS SGEMMs (allow_tf32 is off); parity is 1e-4
+// relative, so a plain bf16 tensor-core product is not admissible.  Each operand is split on the fly
+// into bf16 hi + bf16 lo (16 mantissa bits) and the product is issued as three kind::f16 UMMAs
+//   hi*hi + hi*lo + lo*hi          (the dropped lo*lo term is below 2^-16 relative)
+// accumulating in one fp32 TMEM tile.  These GEMMs are skinny (K = 128..384, N = 128..384): they are
+// bound by streaming A in and C out of HBM, and the tensor pipe (3 x 8 UMMAs of 128x128x16 per tile
+// and 64-deep k-stage) hides under that traffic.
+//
+// Structure of one CTA (128 threads = 4 warps, one output tile 128 x 128, ~64 KB smem => 3 CTAs/SM):
+//   * weights are pre-split once per step by `weight_image_kernel` into bf16 hi/lo images already in
+//     the UMMA K-major SWIZZLE_128B layout, so a 128 x 64 weight stage is one contiguous 16 KB block
+//     that a single thread fetches with cp.async.bulk (TMA bulk copy, mbarrier complete_tx);
+//   * all threads load the fp32 A stage (coalesced 16-byte loads), apply the prologue (GELU + dropout
+//     or a dropout mask), split to bf16 hi/lo and write the swizzled smem operand;
+//   * one thread issues the 12 UMMAs of the stage and commits to an mbarrier;
+//   * epilogue: tcgen05.ld 32x32b -- thread t owns row t of the tile, so LayerNorm statistics are
+//     purely in-thread (three passes over TMEM: z (stored back with tcgen05.st), variance, normalise).
+#pragma once
+#include <cuda_bf16.h>
+#include "gemm_simt.cuh"
+
+namespace dr4sr {
+namespace tc {
+
+constexpr int kBM = 128, kBN = 128, kBK = 64;       // CTA tile; k-stage
+constexpr int kThreads = 128;
+constexpr uint32_t kStageBytes = kBM * kBK * 2;     // one bf16 operand stage = 16 KB
+constexpr uint32_t kSmemBytes = 4 * kStageBytes + 1024;   // A_hi, A_lo, B_hi, B_lo (+ alignment slack)
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 64 bf16 (128 B), 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);      // start address, 16-byte units, bits [0,14)
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset = 1024 B, bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+// byte offset of element (row, k) inside a [rows x 64] bf16 SW128 K-major block whose base is 1024-byte aligned
+__host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t k) {
+  return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ (row & 7u)) & 7u) << 4) + (k & 7u) * 2u;
+}
+
+__device__ __forceinline__ void split_bf16x8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- weight images --------------------------------------------------------------------------------
+// Image of a logical [N, K] operand (N % 128 == 0, K % 64 == 0): K/64 blocks, each N rows x 128 bytes in
+// SW128 K-major order; the rows n0..n0+127 of block kb are the contiguous 16 KB at (kb * N + n0) * 128.
+// transpose != 0: logical W'[n][k] = src[k * ld + n] (the backward-data operand W^T).
+struct ImageJob { const float* src; int ld; int N, K; int transpose; uint16_t* hi; uint16_t* lo; };
+constexpr int kMaxImageJobs = 16;
+struct ImageTable { ImageJob job[kMaxImageJobs]; int count; };
+
+__global__ void __launch_bounds__(256) weight_image_kernel(ImageTable tab) {
+  const ImageJob j = tab.job[blockIdx.y];
+  const int chunks = j.N * (j.K / 8);                 // 16-byte chunks (8 consecutive k of one row)
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += gridDim.x * blockDim.x) {
+    const int n = c / (j.K / 8), k0 = (c % (j.K / 8)) * 8;
+    float x[8];
+    if (!j.transpose) {
+      const float4 a = *reinterpret_cast<const float4*>(j.src + (size_t)n * j.ld + k0);
+      const float4 b = *reinterpret_cast<const float4*>(j.src + (size_t)n * j.ld + k0 + 4);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = j.src[(size_t)(k0 + i) * j.ld + n];
+    }
+    uint4 hi, lo;
+    split_bf16x8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), hi, lo);
+    const size_t off = (size_t)(k0 / 64) * j.N * 128 + sw128_offset((uint32_t)n, (uint32_t)(k0 % 64));
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(j.hi) + off) = hi;
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(j.lo) + off) = lo;
+  }
+}
+
+inline int launch_weight_images(const ImageTable& tab, cudaStream_t st) {
+  if (tab.count <= 0) return DR4SR_OK;
+  if (tab.count > kMaxImageJobs) return DR4SR_EINVAL;
+  for (int i = 0; i < tab.count; ++i)
+    if (tab.job[i].N % 128 || tab.job[i].K % 64) return DR4SR_EINVAL;
+  ProfScope prof("weight_images", st);
+  weight_image_kernel<<<dim3(24, tab.count), 256, 0, st>>>(tab);
+  DR4SR_LAUNCH_CHECK("weight_image_kernel");
+  return DR4SR_OK;
+}
+inline size_t image_elems(int N, int K) { return (size_t)N * K; }   // per image (hi or lo), in bf16 elements
+
+// ---- the GEMM ---------------------------------------------------------------------------------------
+struct TcArgs {
+  GemmArgs g;                 // A, C, lda, ldc, M, N, K, tok_dev, prologue A, epilogue fields
+  const uint16_t* b_hi;       // weight images of the logical [N, K] operand
+  const uint16_t* b_lo;
+};
+
+enum TcEpi : int { TC_LINEAR = 0, TC_GELU_BWD = 1, TC_LN = 2 };
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
+  const GemmArgs& g = t.g;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
+  const int Mlim = min(g.M, g.tok_dev ? *g.tok_dev : g.M);
+  if (m0 >= Mlim) return;                                   // uniform: the whole CTA leaves before any allocation
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 atoms need 1 KB alignment
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = smem + kStageBytes;
+  uint8_t* b_hi = smem + 2 * kStageBytes;
+  uint8_t* b_lo = smem + 3 * kStageBytes;
+
+  if (tid == 0) {
+    mbar_init(&bar_b, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, kBN);               // 128 fp32 accumulator columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  const int nstage = g.K / kBK;
+  const int chunk = tid & 7, rsub = tid >> 3;               // 8 threads per row (8 x 32 B = one 64-wide k block)
+  for (int s = 0; s < nstage; ++s) {
+    if (s > 0) {                                            // the previous stage's UMMAs have consumed the smem operands
+      mbar_wait(&bar_mma, (uint32_t)((s - 1) & 1));
+      tc_fence_after();
+    }
+    if (tid == 0) {
+      mbar_expect_tx(&bar_b, 2 * kStageBytes);
+      const size_t off = ((size_t)s * g.N + n0) * 128;      // rows n0..n0+127 of k-block s: contiguous 16 KB
+      bulk_g2s(b_hi, reinterpret_cast<const uint8_t*>(t.b_hi) + off, kStageBytes, &bar_b);
+      bulk_g2s(b_lo, reinterpret_cast<const uint8_t*>(t.b_lo) + off, kStageBytes, &bar_b);
+    }
+    // A stage: 128 rows x 64 k fp32 -> bf16 hi/lo, swizzled.  8 row-iterations of 16 rows; loads first.
+    float4 va[8][2];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 16 + rsub, gm = m0 + row, gk = s * kBK + chunk * 8;
+      if (gm < Mlim) {
+        const float* p = g.A + (size_t)gm * g.lda + gk;
+        va[it][0] = *reinterpret_cast<const float4*>(p);
+        va[it][1] = *reinterpret_cast<const float4*>(p + 4);
+      } else {
+        va[it][0] = va[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 16 + rsub, gm = m0 + row, gk = s * kBK + chunk * 8;
+      if (g.proA != PRO_NONE && gm < Mlim) {
+        const uint32_t idx = (uint32_t)gm * (uint32_t)g.lda + gk;
+        va[it][0] = apply_prologue(va[it][0], g.proA, g.dropA, idx);
+        va[it][1] = apply_prologue(va[it][1], g.proA, g.dropA, idx + 4);
+      }
+      uint4 hi, lo;
+      split_bf16x8(va[it][0], va[it][1], hi, lo);
+      const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)(chunk * 8));
+      *reinterpret_cast<uint4*>(a_hi + off) = hi;
+      *reinterpret_cast<uint4*>(a_lo + off) = lo;
+    }
+    fence_async_smem();                                     // generic-proxy writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(&bar_b, (uint32_t)(s & 1));                 // weight stage landed
+      tc_fence_after();
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+      for (int k = 0; k < kBK / 16; ++k) {                  // UMMA K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
+        const uint32_t ko = (uint32_t)k * 32u;
+        umma_bf16(tmem, sw128_desc(ah + ko), sw128_desc(bh + ko), kIdesc, (s > 0 || k > 0) ? 1u : 0u);
+        umma_bf16(tmem, sw128_desc(ah + ko), sw128_desc(bl + ko), kIdesc, 1u);
+        umma_bf16(tmem, sw128_desc(al + ko), sw128_desc(bh + ko), kIdesc, 1u);
+      }
+      umma_commit(&bar_mma);                                // arrives when every UMMA above has finished
+    }
+  }
+  mbar_wait(&bar_mma, (uint32_t)((nstage - 1) & 1));
+  tc_fence_after();
+
+  // ---------------- epilogue: thread `tid` owns tile row `tid` (TMEM lane tid) ----------------
+  const int m = m0 + tid;
+  const bool live = m < Mlim;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  if (EPI != TC_LN) {
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      float v[32];
+      tmem_ld32(trow + (uint32_t)(c * 32), v);
+      if (!live) continue;
+      const int nb = n0 + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int n = nb + j;
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (EPI == TC_GELU_BWD) {
+          const float4 p = *reinterpret_cast<const float4*>(g.pre + (size_t)m * g.ldc + n);
+          const uint32_t idx = (uint32_t)m * (uint32_t)g.ldc + n;
+          o.x *= g.dropE.factor(idx) * gelu_grad_f(p.x); o.y *= g.dropE.factor(idx + 1) * gelu_grad_f(p.y);
+          o.z *= g.dropE.factor(idx + 2) * gelu_grad_f(p.z); o.w *= g.dropE.factor(idx + 3) * gelu_grad_f(p.w);
+        } else {
+          if (g.bias) {
+            const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+          }
+          if (g.add) {
+            const float4 aa = *reinterpret_cast<const float4*>(g.add + (size_t)m * g.ldadd + n);
+            o.x += aa.x; o.y += aa.y; o.z += aa.z; o.w += aa.w;
+          }
+          if (g.dropE.thresh) {
+            const uint32_t idx = (uint32_t)m * (uint32_t)g.ldc + n;
+            o.x *= g.dropE.factor(idx); o.y *= g.dropE.factor(idx + 1); o.z *= g.dropE.factor(idx + 2); o.w *= g.dropE.factor(idx + 3);
+          }
+        }
+        *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = o;
+      }
+    }
+  } else {
+    // z = drop(acc + bias) + residual (written back to TMEM and to Z), then two-pass LayerNorm
+    const float invN = 1.0f / (float)kBN;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      float v[32];
+      tmem_ld32(trow + (uint32_t)(c * 32), v);
+      const int nb = c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int n = nb + j;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), rr = bb;
+        if (g.bias) bb = *reinterpret_cast<const float4*>(g.bias + n);
+        if (live) rr = *reinterpret_cast<const float4*>(g.add + (size_t)m * g.ldadd + n);
+        const uint32_t idx = (uint32_t)m * (uint32_t)kBN + n;
+        v[j] = g.dropE.apply(v[j] + bb.x, idx) + rr.x;
+        v[j + 1] = g.dropE.apply(v[j + 1] + bb.y, idx + 1) + rr.y;
+        v[j + 2] = g.dropE.apply(v[j + 2] + bb.z, idx + 2) + rr.z;
+        v[j + 3] = g.dropE.apply(v[j + 3] + bb.w, idx + 3) + rr.w;
+        sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+        if (live && g.Z) *reinterpret_cast<float4*>(g.Z + (size_t)m * kBN + n) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      tmem_st32(trow + (uint32_t)(c * 32), v);
+    }
+    const float mu = sum * invN;
+    float var = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      float v[32];
+      tmem_ld32(trow + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; var = fmaf(d, d, var); }
+    }
+    const float rstd = rsqrtf(var * invN + g.ln_eps);
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      float v[32];
+      tmem_ld32(trow + (uint32_t)(c * 32), v);
+      if (!live) continue;
+      const int nb = c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int n = nb + j;
+        const float4 gg = *reinterpret_cast<const float4*>(g.gamma + n);
+        const float4 be = *reinterpret_cast<const float4*>(g.beta + n);
+        float4 y;
+        y.x = (v[j] - mu) * rstd * gg.x + be.x; y.y = (v[j + 1] - mu) * rstd * gg.y + be.y;
+        y.z = (v[j + 2] - mu) * rstd * gg.z + be.z; y.w = (v[j + 3] - mu) * rstd * gg.w + be.w;
+        *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = y;
+      }
+    }
+    if (live && g.stats) { g.stats[2 * m] = mu; g.stats[2 * m + 1] = rstd; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kBN);
+}
+
+// true when the tensor-core path supports the shape (otherwise the caller uses the FFMA kernel)
+inline bool tc_supported(int N, int K, bool ln) { return N % kBN == 0 && K % kBK == 0 && (!ln || N == kBN); }
+
+template <int EPI>
+inline int launch_gemm_tc(const GemmArgs& g, const uint16_t* b_hi, const uint16_t* b_lo, cudaStream_t st) {
+  if (!tc_supported(g.N, g.K, EPI == TC_LN) || !b_hi || !b_lo) return DR4SR_EINVAL;
+  if (g.lda % 4 || g.ldc % 4) return DR4SR_EINVAL;
+  TcArgs t{g, b_hi, b_lo};
+  ProfScope prof(g.tag ? g.tag : "gemm_tc", st);
+  if (cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "gemm_tc smem attribute");
+    return DR4SR_ECUDA;
+  }
+  dim3 grid(g.N / kBN, ceil_div(g.M, kBM));
+  gemm_tc_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(t);
+  DR4SR_LAUNCH_CHECK("gemm_tc_kernel");
+  return DR4SR_OK;
+}
+
+}  // namespace tc
+}  // namespace dr4sr

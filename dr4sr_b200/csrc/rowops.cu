@@ -103,12 +103,38 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
+// out[e] = sum_k src[k][e] in a fixed order.  A CTA owns 32 consecutive outputs; its 8 warps each sum
+// an interleaved eighth of the splits (coalesced 128-byte rows, 8 independent loads in flight per lane),
+// then the eight partial sums are added in warp order -> deterministic and latency-tolerant even for
+// the 296-way LayerNorm / bias partials.
 __global__ void __launch_bounds__(256) reduce_segments_kernel(ReduceTable tab) {
   const ReduceSeg s = tab.seg[blockIdx.y];
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < s.n; e += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ float part[8][32];
+  for (int e0 = blockIdx.x * 32; e0 < s.n; e0 += gridDim.x * 32) {
+    const int e = e0 + lane;
     float acc = 0.f;
-    for (int k = 0; k < s.n_split; ++k) acc += s.src[(size_t)k * s.stride + e];
-    s.dst[e] = acc;
+    if (e < s.n) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = warp;
+      for (; k + 24 < s.n_split; k += 32) {
+        a0 += s.src[(size_t)k * s.stride + e];
+        a1 += s.src[(size_t)(k + 8) * s.stride + e];
+        a2 += s.src[(size_t)(k + 16) * s.stride + e];
+        a3 += s.src[(size_t)(k + 24) * s.stride + e];
+      }
+      for (; k < s.n_split; k += 8) a0 += s.src[(size_t)k * s.stride + e];
+      acc = (a0 + a1) + (a2 + a3);
+    }
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && e < s.n) {
+      float t = part[0][lane];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t += part[w][lane];
+      s.dst[e] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -140,7 +166,7 @@ int launch_reduce_segments(const ReduceTable& tab, cudaStream_t st) {
   ProfScope prof("reduce_partials", st);
   int nmax = 0;
   for (int i = 0; i < tab.count; ++i) nmax = nmax > tab.seg[i].n ? nmax : tab.seg[i].n;
-  dim3 grid(ceil_div(nmax, 256) < 64 ? ceil_div(nmax, 256) : 64, tab.count);
+  dim3 grid(ceil_div(nmax, 32) < 2 * kNumSMs ? ceil_div(nmax, 32) : 2 * kNumSMs, tab.count);
   reduce_segments_kernel<<<grid, 256, 0, st>>>(tab);
   DR4SR_LAUNCH_CHECK("reduce_segments_kernel");
   return DR4SR_OK;

@@ -3,11 +3,15 @@
 // Replaces SASRecQueryEncoder.forward (reference model/sasrec.py:39-75) = embedding + learned
 // positions + dropout -> 2 x post-norm TransformerEncoderLayer (model/sasrec.py:21-34) -> pooling,
 // and its autograd backward.  Spec: SURVEY.md Appendix C.1, C.2, C.5.
+#include <atomic>
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "internal.cuh"
 
 namespace dr4sr {
 namespace {
+
+std::atomic<int> g_gemm_backend{0};   // 0 = tcgen05 where the shape allows, 1 = FFMA everywhere (dr4sr_set_gemm_backend)
 
 constexpr int kSplit = 32;   // token splits of the weight-gradient GEMMs (partials reduced in fixed order)
 
@@ -42,6 +46,10 @@ struct Workspace {
   float *part_w;     // [kSplit][3DD + DD + FD + DF] weight-gradient partials of the current layer
   float *part_ln2, *part_ln1;   // [kLnBwdBlocks][3D]
   float *part_cs_in, *part_cs_b1;   // [kColsumBlocks][3D], [kColsumBlocks][F]
+  // bf16 hi/lo weight images (UMMA SW128 K-major) of every layer: forward operands W[n,k] and the
+  // transposed backward-data operands W^T, rebuilt at the start of every forward
+  struct Img { uint16_t *hi, *lo; };
+  struct LayerImg { Img in_f, out_f, w1_f, w2_f, in_b, out_b, w1_b, w2_b; } img[8];
   size_t bytes;
 };
 
@@ -65,6 +73,17 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
   w.part_ln1 = take((size_t)kLnBwdBlocks * 3 * D);
   w.part_cs_in = take((size_t)kColsumBlocks * 3 * D);
   w.part_cs_b1 = take((size_t)kColsumBlocks * F);
+  auto take_img = [&](size_t elems) {   // hi + lo images, bf16; 1 KB aligned (align_up keeps 256 B, images are multiples of 16 KB)
+    Workspace::Img im;
+    im.hi = reinterpret_cast<uint16_t*>(take((elems + 1) / 2));
+    im.lo = reinterpret_cast<uint16_t*>(take((elems + 1) / 2));
+    return im;
+  };
+  for (int l = 0; l < c.n_layer; ++l) {
+    auto& m = w.img[l];
+    m.in_f = take_img(3 * D * D); m.out_f = take_img(D * D); m.w1_f = take_img(F * D); m.w2_f = take_img(D * F);
+    m.in_b = take_img(3 * D * D); m.out_b = take_img(D * D); m.w1_b = take_img(F * D); m.w2_b = take_img(D * F);
+  }
   w.bytes = off * sizeof(float);
   return w;
 }
@@ -79,20 +98,57 @@ int check_cfg(const dr4sr_sasrec_cfg* c) {
   return DR4SR_OK;
 }
 
+using Img = Workspace::Img;
+bool use_tc(const GemmArgs& g, const Img& im, bool ln) {
+  return g_gemm_backend.load(std::memory_order_relaxed) == 0 && im.hi && tc::tc_supported(g.N, g.K, ln);
+}
 // y = LN(drop(A W^T + b) + res), rows complete inside a CTA (BN == D)
-int gemm_ln(GemmArgs& g, int D, cudaStream_t st) {
+int gemm_ln(GemmArgs& g, int D, const Img& im, cudaStream_t st) {
+  if (use_tc(g, im, true)) return tc::launch_gemm_tc<tc::TC_LN>(g, im.hi, im.lo, st);
   if (D == 128) return launch_gemm<64, 128, true, true, true>(g, st);
   return launch_gemm<64, 64, true, true, true>(g, st);
 }
-int gemm_nt(GemmArgs& g, cudaStream_t st) {
+int gemm_nt(GemmArgs& g, const Img& im, cudaStream_t st) {
+  if (use_tc(g, im, false)) return tc::launch_gemm_tc<tc::TC_LINEAR>(g, im.hi, im.lo, st);
   if (g.N >= 256) return launch_gemm<128, 128, true, true, false>(g, st);
   if (g.N > 64) return launch_gemm<64, 128, true, true, false>(g, st);
   return launch_gemm<64, 64, true, true, false>(g, st);
 }
-int gemm_nn(GemmArgs& g, cudaStream_t st) {
+// backward-data: C = A W, the tensor-core path consumes the transposed image of W
+int gemm_nn(GemmArgs& g, const Img& im, cudaStream_t st) {
+  if (use_tc(g, im, false)) {
+    return g.epi == EPI_GELU_BWD ? tc::launch_gemm_tc<tc::TC_GELU_BWD>(g, im.hi, im.lo, st)
+                                 : tc::launch_gemm_tc<tc::TC_LINEAR>(g, im.hi, im.lo, st);
+  }
   if (g.N >= 256) return launch_gemm<128, 128, true, false, false>(g, st);
   if (g.N > 64) return launch_gemm<64, 128, true, false, false>(g, st);
   return launch_gemm<64, 64, true, false, false>(g, st);
+}
+// bf16 hi/lo images of all layers' weights (one launch per <= 2 layers)
+int build_weight_images(const dr4sr_sasrec_cfg& c, const float* params, const Workspace& w, const LayerOffsets& lo, cudaStream_t st) {
+  const int D = c.D, F = c.F;
+  if (g_gemm_backend.load(std::memory_order_relaxed) != 0) return DR4SR_OK;   // FFMA path needs none
+  tc::ImageTable tab{};
+  for (int l = 0; l < c.n_layer; ++l) {
+    const float* lp = params + (size_t)c.L * D + (size_t)l * lo.total;
+    const auto& m = w.img[l];
+    auto add = [&](const float* src, int ld, int N, int K, int tr, const Img& im) {   // same predicate as use_tc()
+      if (tc::tc_supported(N, K, false)) tab.job[tab.count++] = tc::ImageJob{src, ld, N, K, tr, im.hi, im.lo};
+    };
+    add(lp + lo.in_w, D, 3 * D, D, 0, m.in_f);
+    add(lp + lo.out_w, D, D, D, 0, m.out_f);
+    add(lp + lo.w1, D, F, D, 0, m.w1_f);
+    add(lp + lo.w2, F, D, F, 0, m.w2_f);
+    add(lp + lo.in_w, D, D, 3 * D, 1, m.in_b);     // dx  = dqkv Win : B'[d][j] = Win[j][d]
+    add(lp + lo.out_w, D, D, D, 1, m.out_b);       // dO  = dz1 Wo   : B'[k][n] = Wo[n][k]
+    add(lp + lo.w1, D, D, F, 1, m.w1_b);           // dx1 = dpre W1  : B'[d][f] = W1[f][d]
+    add(lp + lo.w2, F, F, D, 1, m.w2_b);           // dh  = dz2 W2   : B'[f][d] = W2[d][f]
+    if (tab.count + 8 > tc::kMaxImageJobs || l == c.n_layer - 1) {
+      DR4SR_TRY(tc::launch_weight_images(tab, st));
+      tab.count = 0;
+    }
+  }
+  return DR4SR_OK;
 }
 int gemm_tn(GemmArgs& g, float* partial, cudaStream_t st) {   // C partials [kSplit][M*N]
   g.C = partial; g.n_split = kSplit; g.split_stride = (int64_t)g.M * g.N; g.ldc = g.N;
@@ -162,6 +218,7 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
                               w.x0, stream));
     (void)drop;
   }
+  DR4SR_TRY(build_weight_images(*c, params, w, lo, st));
   const float* x = w.x0;
   for (int l = 0; l < c->n_layer; ++l) {
     const float* lp = params + (size_t)c->L * D + (size_t)l * lo.total;
@@ -170,7 +227,7 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
     {  // QKV projection
       GemmArgs g = gemm_args(x, D, lp + lo.in_w, D, y.qkv, 3 * D, T, 3 * D, D, counts);
       g.bias = lp + lo.in_b; g.tag = "gemm_qkv";
-      DR4SR_TRY(gemm_nt(g, st));
+      DR4SR_TRY(gemm_nt(g, w.img[l].in_f, st));
     }
     DR4SR_TRY(launch_attn_fwd(y.qkv, in_item_id, tok_off, y.attn, c->B, c->L, D, c->n_head,
                               make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr), st));
@@ -179,12 +236,12 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
       g.bias = lp + lo.out_b; g.add = x; g.ldadd = D;
       g.dropE = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_OUT, l), tr);
       g.gamma = lp + lo.g1; g.beta = lp + lo.be1; g.ln_eps = c->ln_eps; g.Z = y.z1; g.stats = y.st1; g.tag = "gemm_outproj_ln";
-      DR4SR_TRY(gemm_ln(g, D, st));
+      DR4SR_TRY(gemm_ln(g, D, w.img[l].out_f, st));
     }
     {  // FFN up-projection (pre-activation kept for the backward)
       GemmArgs g = gemm_args(y.x1, D, lp + lo.w1, D, y.pre, F, T, F, D, counts);
       g.bias = lp + lo.b1; g.tag = "gemm_ffn1";
-      DR4SR_TRY(gemm_nt(g, st));
+      DR4SR_TRY(gemm_nt(g, w.img[l].w1_f, st));
     }
     {  // gelu + dropout (prologue) -> down-projection + dropout + residual + LN2
       GemmArgs g = gemm_args(y.pre, F, lp + lo.w2, F, x2, D, T, D, F, counts);
@@ -192,7 +249,7 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
       g.bias = lp + lo.b2; g.add = y.x1; g.ldadd = D;
       g.dropE = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_OUT, l), tr);
       g.gamma = lp + lo.g2; g.beta = lp + lo.be2; g.ln_eps = c->ln_eps; g.Z = y.z2; g.stats = y.st2; g.tag = "gemm_ffn2_ln";
-      DR4SR_TRY(gemm_ln(g, D, st));
+      DR4SR_TRY(gemm_ln(g, D, w.img[l].w2_f, st));
     }
     x = x2;
   }
@@ -244,7 +301,7 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
       GemmArgs g = gemm_args(w.g1, D, lp + lo.w2, F, w.dpre, F, T, F, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_ffn_out;
       g.epi = EPI_GELU_BWD; g.pre = y.pre; g.dropE = d_ffn_h; g.tag = "gemm_bwd_dpre";
-      DR4SR_TRY(gemm_nn(g, st));
+      DR4SR_TRY(gemm_nn(g, w.img[l].w2_b, st));
     }
     {  // dW2[d,f] = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]
       GemmArgs g = gemm_args(w.g1, D, y.pre, F, nullptr, F, D, F, T, counts);
@@ -260,14 +317,14 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
     {  // dx1 = dz2 + dpre W1   -> g0
       GemmArgs g = gemm_args(w.dpre, F, lp + lo.w1, D, w.g0, D, T, D, F, counts);
       g.add = w.g1; g.ldadd = D; g.tag = "gemm_bwd_dx1";
-      DR4SR_TRY(gemm_nn(g, st));
+      DR4SR_TRY(gemm_nn(g, w.img[l].w1_b, st));
     }
     // LN1 backward: g1 = dz1 ; partials -> dgamma1, dbeta1, db_out
     DR4SR_TRY(launch_ln_bwd(w.g0, y.z1, y.st1, lp + lo.g1, w.g1, w.part_ln1, D, T, counts, d_attn_out, st));
     {  // d(attn) = (dz1 * mask) Wo -> g2
       GemmArgs g = gemm_args(w.g1, D, lp + lo.out_w, D, w.g2, D, T, D, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_bwd_dattn";
-      DR4SR_TRY(gemm_nn(g, st));
+      DR4SR_TRY(gemm_nn(g, w.img[l].out_b, st));
     }
     {  // dWo[n,k] = sum_m (dz1*mask)[m,n] * attn[m,k]
       GemmArgs g = gemm_args(w.g1, D, y.attn, D, nullptr, D, D, D, T, counts);
@@ -287,7 +344,7 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
       g.add = w.g1; g.ldadd = D;
       if (l == 0) g.dropE = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
       g.tag = "gemm_bwd_dx";
-      DR4SR_TRY(gemm_nn(g, st));
+      DR4SR_TRY(gemm_nn(g, w.img[l].in_b, st));
     }
     {  // fixed-order reduction of every partial of this layer into the flat gradient buffer
       ReduceTable tab{};
@@ -318,5 +375,11 @@ extern "C" int dr4sr_linear_fwd(const float* x, const float* w, const float* bia
   if (!x || !w || !y || M <= 0 || N % 4 || K % 4) return DR4SR_EINVAL;
   GemmArgs g = gemm_args(x, K, w, K, y, N, M, N, K, m_dev);
   g.bias = bias;
-  return gemm_nt(g, as_stream(stream));
+  return gemm_nt(g, Img{nullptr, nullptr}, as_stream(stream));
+}
+
+extern "C" int dr4sr_set_gemm_backend(int backend) {
+  if (backend != 0 && backend != 1) return DR4SR_EINVAL;
+  g_gemm_backend.store(backend);
+  return DR4SR_OK;
 }

@@ -93,6 +93,11 @@ typedef struct {
   uint64_t step;
 } dr4sr_sasrec_cfg;
 
+/* Dense-layer backend: 0 (default) = tcgen05/TMEM with bf16 hi/lo split operands (3 UMMAs per product,
+ * fp32 accumulate) wherever the shape allows (N % 128 == 0, K % 64 == 0), 1 = exact-fp32 FFMA kernels
+ * everywhere.  Process-wide; used by the parity tests to check both. */
+DR4SR_API int dr4sr_set_gemm_backend(int backend);
+
 DR4SR_API size_t dr4sr_sasrec_param_count(const dr4sr_sasrec_cfg* cfg);
 DR4SR_API size_t dr4sr_sasrec_workspace_bytes(const dr4sr_sasrec_cfg* cfg);
 

@@ -16,6 +16,21 @@ pytestmark = pytest.mark.gpu
 
 DEV = 'cuda:0'
 
+# Dense layers run either on tcgen05 (bf16 hi/lo split operands, 3 UMMAs per product: ~2^-16 relative
+# per product) or on exact-fp32 FFMA kernels.  Both are held to the north-star bar (1e-4 relative on
+# losses / logits); the FFMA path is additionally held to fp32 round-off.
+TOL = {'tc': dict(fwd=1e-4, loss=1e-4, grad=1e-3, adam=1e-4), 'ffma': dict(fwd=1e-5, loss=1e-5, grad=1e-4, adam=2e-5)}
+
+
+@pytest.fixture(params=['tc', 'ffma'], autouse=True)
+def backend(request):
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dr4sr_b200 import _lib
+    _lib.check(_lib.lib().dr4sr_set_gemm_backend(0 if request.param == 'tc' else 1), 'set_gemm_backend')
+    yield request.param
+    _lib.lib().dr4sr_set_gemm_backend(0)
+
 
 def _need_gpu():
     if not torch.cuda.is_available():
@@ -92,8 +107,26 @@ def test_linear_fwd_matches_torch():
         assert rel_err(y.cpu(), want) < 2e-6, (M, N, K)
 
 
+def test_tensor_core_layers_error_budget(backend):
+    """One D=128 encoder forward: report (and bound) the error of each backend against the fp64 spec."""
+    _need_gpu()
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    N, D = 3000, 128
+    m = make_model(N, D).train()
+    o = orc.OracleSASRec(N, embed_dim=D, dropout_rate=0.0).double().train()
+    o.load_state_dict({k: v.detach().cpu().double() for k, v in m.state_dict().items()})
+    batch = synthetic_batch(48, 50, N, seed=77)
+    with torch.no_grad():
+        want = o.encode(batch)
+    q = m.forward(to_dev(batch)).cpu().double()
+    v = valid_mask(batch)
+    err = rel_err(q[v], want[v])
+    print(f'[{backend}] encoder forward rel err vs fp64: {err:.3e}')
+    assert err < TOL[backend]['fwd']
+
+
 @pytest.mark.parametrize('name', ['sasrec_d64.npz', 'sasrec_d128.npz'])
-def test_forward_matches_reference_golden(name):
+def test_forward_matches_reference_golden(name, backend):
     _need_gpu()
     fx = load_fixture(name)
     m = model_from_fixture(fx).train()
@@ -101,31 +134,32 @@ def test_forward_matches_reference_golden(name):
     q = m.forward(batch).cpu()                       # train mode: 'origin' pooling, [B, L, D]
     want = fx['train']['query']
     assert q.shape == want.shape
-    assert rel_err(q, want) < 1e-5
+    assert rel_err(q, want) < TOL[backend]['fwd']
     assert torch.equal(q[~valid_mask(fx['batch'])], torch.zeros_like(q[~valid_mask(fx['batch'])]))
 
 
 @pytest.mark.parametrize('name', ['sasrec_d64.npz', 'sasrec_d128.npz'])
-def test_loss_and_gradients_match_reference_golden(name):
+def test_loss_and_gradients_match_reference_golden(name, backend):
     _need_gpu()
+    tol = TOL[backend]
     fx = load_fixture(name)
     m = model_from_fixture(fx).train()
     batch = to_dev(fx['batch'])
     loss = m.training_step(batch)
-    assert abs(float(loss) - float(fx['train']['loss'])) / abs(float(fx['train']['loss'])) < 1e-5
+    assert abs(float(loss) - float(fx['train']['loss'])) / abs(float(fx['train']['loss'])) < tol['loss']
     per = m.training_step(batch, reduce=False).detach().cpu()
-    assert rel_err(per, fx['train']['loss_per_pos']) < 1e-5
+    assert rel_err(per, fx['train']['loss_per_pos']) < tol['loss']
     m.optimizer.zero_grad()
     loss = m.training_step(batch)
     loss.backward()
     for k, p in m.named_parameters():
         assert p.grad is not None, k
-        assert rel_err(p.grad.cpu(), fx['grad'][k]) < 1e-4, k
+        assert rel_err(p.grad.cpu(), fx['grad'][k]) < tol['grad'], k
     assert float(m.item_embedding.weight.grad[0].abs().max()) == 0.0      # pad row never receives gradient
 
 
 @pytest.mark.parametrize('name', ['sasrec_d64.npz', 'sasrec_d128.npz'])
-def test_adam_steps_match_reference_golden(name):
+def test_adam_steps_match_reference_golden(name, backend):
     _need_gpu()
     fx = load_fixture(name)
     m = model_from_fixture(fx).train()
@@ -135,32 +169,33 @@ def test_adam_steps_match_reference_golden(name):
         loss = m.training_step(batch)
         loss.backward()
         m.optimizer.step()
-        assert abs(float(loss) - want) / want < 2e-5
+        assert abs(float(loss) - want) / want < TOL[backend]['loss']
     for k, p in m.named_parameters():
         # Adam's first steps move every touched weight by ~lr regardless of gradient size, so
         # compare the update against lr
-        assert float((p.detach().cpu() - fx['param_after'][k]).abs().max()) < 2e-5, k
+        assert float((p.detach().cpu() - fx['param_after'][k]).abs().max()) < TOL[backend]['adam'], k
 
 
 @pytest.mark.parametrize('name', ['sasrec_d64.npz', 'sasrec_d128.npz'])
-def test_eval_query_and_topk_match_reference_golden(name):
+def test_eval_query_and_topk_match_reference_golden(name, backend):
     _need_gpu()
+    tol = TOL[backend]
     fx = load_fixture(name)
     m = model_from_fixture(fx)
     load_params(m, {k: v.to(DEV) for k, v in fx['param_after'].items()})
     m.eval()
     ev = to_dev(fx['evalbatch'])
     q = m.forward(ev).cpu()
-    assert rel_err(q, fx['eval']['query']) < 1e-5
+    assert rel_err(q, fx['eval']['query']) < tol['fwd']
     k = fx['eval']['topk_ids'].shape[1]
     s, i = m.topk(ev, k, ev['user_hist'])
     s, i = s.cpu(), i.cpu()
-    assert rel_err(s, fx['eval']['topk_scores']) < 1e-5
+    assert rel_err(s, fx['eval']['topk_scores']) < tol['fwd']
     # ids: identical wherever neighbouring reference scores are separated by more than fp32 noise
     ws = fx['eval']['topk_scores']
     gap = torch.minimum(torch.cat([ws[:, :1] * 0 + 1, (ws[:, :-1] - ws[:, 1:])], 1),
                         torch.cat([(ws[:, :-1] - ws[:, 1:]), ws[:, :1] * 0 + 1], 1))
-    firm = gap > 1e-5
+    firm = gap > (1e-5 if backend == 'ffma' else 3e-5)     # the query itself carries the encoder's error
     assert torch.equal(i[firm], fx['eval']['topk_ids'][firm])
     assert float(firm.float().mean()) > 0.95
 
@@ -207,8 +242,9 @@ def test_topk_with_ties_and_few_live_items():
 
 
 @pytest.mark.parametrize('B,D,N,minlen', [(64, 128, 5000, 1), (9, 64, 777, 50), (5, 64, 300, 1), (1, 128, 1000, 7)])
-def test_training_step_matches_oracle_on_synthetic(B, D, N, minlen):
+def test_training_step_matches_oracle_on_synthetic(B, D, N, minlen, backend):
     _need_gpu()
+    tol = TOL[backend]
     from dr4sr_b200.data.synthetic import synthetic_batch
     m = make_model(N, D).train()
     o = orc.OracleSASRec(N, embed_dim=D, dropout_rate=0.0).train()
@@ -226,14 +262,14 @@ def test_training_step_matches_oracle_on_synthetic(B, D, N, minlen):
     lo.backward()
     loss, q = m.training_step(to_dev(batch), return_query=True)
     loss.backward()
-    assert abs(float(loss) - float(lo)) / abs(float(lo)) < 1e-5
-    assert rel_err(q.detach().cpu(), qo.detach()) < 1e-5
+    assert abs(float(loss) - float(lo)) / abs(float(lo)) < tol['loss']
+    assert rel_err(q.detach().cpu(), qo.detach()) < tol['fwd']
     for (k, p), (_, po) in zip(m.named_parameters(), o.named_parameters()):
         want = po.grad if po.grad is not None else torch.zeros_like(po)
-        assert rel_err(p.grad.cpu(), want) < 1e-4, k
+        assert rel_err(p.grad.cpu(), want) < tol['grad'], k
 
 
-def test_explicit_spec_layer_vs_kernels_three_layers_f256():
+def test_explicit_spec_layer_vs_kernels_three_layers_f256(backend):
     """Non-default encoder shape (3 layers, FFN 256, 4 heads) against the elementary-algebra spec."""
     _need_gpu()
     from dr4sr_b200.data.synthetic import synthetic_batch
@@ -246,7 +282,7 @@ def test_explicit_spec_layer_vs_kernels_three_layers_f256():
         want = orc.sasrec_encode_explicit(o, batch)
     q = m.forward(to_dev(batch)).cpu()
     v = valid_mask(batch)
-    assert rel_err(q[v], want[v]) < 1e-5
+    assert rel_err(q[v], want[v]) < TOL[backend]['fwd']
 
 
 def test_dropout_is_deterministic_unbiased_and_consistent_with_backward():
@@ -317,9 +353,10 @@ def test_neg_sampling_range_uniformity_determinism():
     assert chi2 < (N - 2) + 6 * math.sqrt(2 * (N - 2))            # within 6 sigma of the chi-square mean
 
 
-def test_full_size_step_matches_oracle_config2():
+def test_full_size_step_matches_oracle_config2(backend):
     """BASELINE config 2 shape: B=1024, L=50, D=128, N=100K (one step, dropout off)."""
     _need_gpu()
+    tol = TOL[backend]
     from dr4sr_b200.data.synthetic import synthetic_batch
     B, D, N = 1024, 128, 100_000
     m = make_model(N, D).train()
@@ -330,9 +367,9 @@ def test_full_size_step_matches_oracle_config2():
     lo.backward()
     loss = m.training_step(to_dev(batch))
     loss.backward()
-    assert abs(float(loss) - float(lo)) / abs(float(lo)) < 1e-5
+    assert abs(float(loss) - float(lo)) / abs(float(lo)) < tol['loss']
     for (k, p), (_, po) in zip(m.named_parameters(), o.named_parameters()):
-        assert rel_err(p.grad.cpu(), po.grad) < 1e-4, k
+        assert rel_err(p.grad.cpu(), po.grad) < tol['grad'], k
     # size-independent properties
     g = m.item_embedding.weight.grad
     assert float(g[0].abs().max()) == 0.0
