@@ -33,27 +33,31 @@ __host__ __device__ inline Tile make_tile(int L, int dh) {
   return t;
 }
 
+// Asynchronous 16-byte global -> shared copies (LDGSTS): every thread queues all of its copies for the
+// whole problem back to back and waits once, so a CTA pays one memory round trip instead of one per row.
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // rows [0,len) of one head slice of a packed [T, stride] matrix -> smem [rows][ld]
 __device__ __forceinline__ void load_rows(const float* __restrict__ src, int stride, int len, int dh, float* dst, int ld) {
   const int f4 = dh / 4;
   for (int e = threadIdx.x; e < len * f4; e += blockDim.x) {
     const int r = e / f4, c = (e % f4) * 4;
-    *reinterpret_cast<float4*>(dst + r * ld + c) = *reinterpret_cast<const float4*>(src + (size_t)r * stride + c);
+    cp_async16(dst + r * ld + c, src + (size_t)r * stride + c);
   }
 }
 
-// Q, K, V head slices in one pass: three independent 16-byte loads in flight per iteration
+// Q, K, V head slices of the packed [T, 3D] projection
 __device__ __forceinline__ void load_qkv(const float* __restrict__ src, int D, int len, int dh, float* Q, float* K, float* V, int ld) {
   const int f4 = dh / 4;
   for (int e = threadIdx.x; e < len * f4; e += blockDim.x) {
     const int r = e / f4, c = (e % f4) * 4;
     const float* p = src + (size_t)r * 3 * D + c;
-    const float4 q = *reinterpret_cast<const float4*>(p);
-    const float4 k = *reinterpret_cast<const float4*>(p + D);
-    const float4 v = *reinterpret_cast<const float4*>(p + 2 * D);
-    *reinterpret_cast<float4*>(Q + r * ld + c) = q;
-    *reinterpret_cast<float4*>(K + r * ld + c) = k;
-    *reinterpret_cast<float4*>(V + r * ld + c) = v;
+    cp_async16(Q + r * ld + c, p);
+    cp_async16(K + r * ld + c, p + D);
+    cp_async16(V + r * ld + c, p + 2 * D);
   }
 }
 
@@ -71,6 +75,7 @@ __device__ __forceinline__ void mm_abt(const float* __restrict__ A, const float*
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 2
   for (int d = 0; d < dh; d += 4) {
     float4 av[4], bv[4];
 #pragma unroll
@@ -115,14 +120,38 @@ __device__ __forceinline__ void mm_pv(const float* __restrict__ S, int lds, cons
 #pragma unroll
     for (int a = 0; a < 4; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int x_lo = TRANS ? r0 : 0, x_hi = TRANS ? len : min(len, r0 + (na - 1) * rstep + 1);
-    for (int x = x_lo; x < x_hi; ++x) {
+    // rows >= len read S as 0 through a clamped, always-valid address (their results are discarded)
+    int rs[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) rs[a] = min(r0 + a * rstep, len - 1);
+    int x = x_lo;
+    for (; x + 3 < x_hi; x += 4) {                 // 4 keys per trip: 4 + 16 independent shared loads in flight
+      float4 m[4];
+      float sv[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m[u] = *reinterpret_cast<const float4*>(M + (x + u) * ld + tc * 4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a < na_u) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sv[a][u] = TRANS ? S[(x + u) * lds + rs[a]] : S[rs[a] * lds + x + u];
+        }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a < na_u) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[a].x = fmaf(sv[a][u], m[u].x, acc[a].x); acc[a].y = fmaf(sv[a][u], m[u].y, acc[a].y);
+            acc[a].z = fmaf(sv[a][u], m[u].z, acc[a].z); acc[a].w = fmaf(sv[a][u], m[u].w, acc[a].w);
+          }
+        }
+    }
+    for (; x < x_hi; ++x) {
       const float4 m = *reinterpret_cast<const float4*>(M + x * ld + tc * 4);
 #pragma unroll
       for (int a = 0; a < 4; ++a)
         if (a < na_u) {
-          const int r = r0 + a * rstep;
-          float s = 0.f;
-          if (r < len) s = TRANS ? S[x * lds + r] : S[r * lds + x];
+          const float s = TRANS ? S[x * lds + rs[a]] : S[rs[a] * lds + x];
           acc[a].x = fmaf(s, m.x, acc[a].x); acc[a].y = fmaf(s, m.y, acc[a].y);
           acc[a].z = fmaf(s, m.z, acc[a].z); acc[a].w = fmaf(s, m.w, acc[a].w);
         }
@@ -156,7 +185,7 @@ __device__ __forceinline__ void softmax_rows(float* S, float* Pd, int lds, int l
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ in_ids,
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_fwd_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ in_ids,
                                                                 const int32_t* __restrict__ tok_off, float* __restrict__ out,
                                                                 int L, int D, int n_head, float scale, Dropout drop) {
   extern __shared__ __align__(16) float sm[];
@@ -170,6 +199,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __r
   const float* base_q = qkv + (size_t)off * 3 * D + h * dh;
   load_qkv(base_q, D, len, dh, Q, K, V, t.ld);
   for (int j = threadIdx.x; j < len; j += blockDim.x) pad[j] = in_ids[(size_t)b * L + j] == 0;
+  cp_async_wait_all();
   __syncthreads();
   mm_abt(Q, K, t.ld, len, dh, [&](int i, int j, float v, bool above) {
     S[i * t.lds + j] = (!above && j <= i && !pad[j]) ? v * scale : -INFINITY;
@@ -182,7 +212,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __r
 }
 
 // dQKV from dO, recomputing the probabilities (no [B,H,L,L] tensor is ever stored)
-__global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out,
+__global__ void __launch_bounds__(kAttnThreads, 2) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_out,
                                                                 const int64_t* __restrict__ in_ids,
                                                                 const int32_t* __restrict__ tok_off, float* __restrict__ d_qkv,
                                                                 int L, int D, int n_head, float scale, Dropout drop) {
@@ -200,6 +230,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __r
   load_qkv(base_q, D, len, dh, Q, K, V, t.ld);
   load_rows(d_out + (size_t)off * D + h * dh, D, len, dh, dO, t.ld);
   for (int j = threadIdx.x; j < len; j += blockDim.x) pad[j] = in_ids[(size_t)b * L + j] == 0;
+  cp_async_wait_all();
   __syncthreads();
   const uint32_t base = (uint32_t)(b * n_head + h) * (uint32_t)(L * L);
   mm_abt(Q, K, t.ld, len, dh, [&](int i, int j, float v, bool above) {

@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
         v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
       }
       const uint32_t idx = (uint32_t)row * (uint32_t)D + c;
-      v.x = drop.apply(v.x, idx); v.y = drop.apply(v.y, idx + 1);
-      v.z = drop.apply(v.z, idx + 2); v.w = drop.apply(v.w, idx + 3);
+      const float4 f = drop.factor4(idx);
+      v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
       *reinterpret_cast<float4*>(x0 + (size_t)row * D + c) = v;
     }
   }

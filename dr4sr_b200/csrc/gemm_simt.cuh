@@ -42,12 +42,14 @@ struct GemmArgs {
   const char* tag;         // name under which the optional event timer files this launch
 };
 
+// idx % 4 == 0 everywhere a prologue / epilogue touches a float4 (leading dimensions are multiples of 4)
 __device__ __forceinline__ float4 apply_prologue(float4 v, int pro, const Dropout& d, uint32_t idx) {
   if (pro == PRO_GELU_DROP) {
-    v.x = d.apply(gelu_f(v.x), idx); v.y = d.apply(gelu_f(v.y), idx + 1);
-    v.z = d.apply(gelu_f(v.z), idx + 2); v.w = d.apply(gelu_f(v.w), idx + 3);
+    const float4 f = d.factor4(idx);
+    v.x = gelu_f(v.x) * f.x; v.y = gelu_f(v.y) * f.y; v.z = gelu_f(v.z) * f.z; v.w = gelu_f(v.w) * f.w;
   } else if (pro == PRO_DROPMASK) {
-    v.x *= d.factor(idx); v.y *= d.factor(idx + 1); v.z *= d.factor(idx + 2); v.w *= d.factor(idx + 3);
+    const float4 f = d.factor4(idx);
+    v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
   }
   return v;
 }
@@ -203,10 +205,9 @@ __global__ void __launch_bounds__(256, (BM * BN <= 64 * 128) ? 2 : 1) gemm_simt_
         if (g.epi == EPI_GELU_BWD) {
           const float4 p = *reinterpret_cast<const float4*>(g.pre + (size_t)m * g.ldc + n);
           const uint32_t idx = (uint32_t)m * (uint32_t)g.ldc + n;
-          v.x *= g.dropE.factor(idx) * gelu_grad_f(p.x);
-          v.y *= g.dropE.factor(idx + 1) * gelu_grad_f(p.y);
-          v.z *= g.dropE.factor(idx + 2) * gelu_grad_f(p.z);
-          v.w *= g.dropE.factor(idx + 3) * gelu_grad_f(p.w);
+          const float4 f = g.dropE.factor4(idx);
+          v.x *= f.x * gelu_grad_f(p.x); v.y *= f.y * gelu_grad_f(p.y);
+          v.z *= f.z * gelu_grad_f(p.z); v.w *= f.w * gelu_grad_f(p.w);
         } else {
           if (g.bias) {
             const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(256, (BM * BN <= 64 * 128) ? 2 : 1) gemm_simt_
           }
           if (g.dropE.thresh) {   // gradient through a dropout that sits on this GEMM's output tensor
             const uint32_t idx = (uint32_t)m * (uint32_t)g.ldc + n;
-            v.x *= g.dropE.factor(idx); v.y *= g.dropE.factor(idx + 1);
-            v.z *= g.dropE.factor(idx + 2); v.w *= g.dropE.factor(idx + 3);
+            const float4 f = g.dropE.factor4(idx);
+            v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w;
           }
         }
         *reinterpret_cast<float4*>(Cbase + (size_t)m * g.ldc + n) = v;
@@ -244,10 +245,11 @@ __global__ void __launch_bounds__(256, (BM * BN <= 64 * 128) ? 2 : 1) gemm_simt_
           rr = *reinterpret_cast<const float4*>(g.add + (size_t)m * g.ldadd + n);
         }
         const uint32_t idx = (uint32_t)m * (uint32_t)g.N + n;
-        z[h * 4 + 0] = g.dropE.apply(acc[i][h * 4 + 0] + bb.x, idx) + rr.x;
-        z[h * 4 + 1] = g.dropE.apply(acc[i][h * 4 + 1] + bb.y, idx + 1) + rr.y;
-        z[h * 4 + 2] = g.dropE.apply(acc[i][h * 4 + 2] + bb.z, idx + 2) + rr.z;
-        z[h * 4 + 3] = g.dropE.apply(acc[i][h * 4 + 3] + bb.w, idx + 3) + rr.w;
+        const float4 f = g.dropE.factor4(idx);
+        z[h * 4 + 0] = (acc[i][h * 4 + 0] + bb.x) * f.x + rr.x;
+        z[h * 4 + 1] = (acc[i][h * 4 + 1] + bb.y) * f.y + rr.y;
+        z[h * 4 + 2] = (acc[i][h * 4 + 2] + bb.z) * f.z + rr.z;
+        z[h * 4 + 3] = (acc[i][h * 4 + 3] + bb.w) * f.w + rr.w;
         s += (z[h * 4] + z[h * 4 + 1]) + (z[h * 4 + 2] + z[h * 4 + 3]);
       }
 #pragma unroll

@@ -10,15 +10,17 @@
 // bound by streaming A in and C out of HBM, and the tensor pipe (3 x 8 UMMAs of 128x128x16 per tile
 // and 64-deep k-stage) hides under that traffic.
 //
-// Structure of one CTA (128 threads = 4 warps, one output tile 128 x 128, ~64 KB smem => 3 CTAs/SM):
+// Structure of one CTA (256 threads = 8 warps, one output tile 128 x 128, ~64 KB smem => 3 CTAs/SM):
 //   * weights are pre-split once per step by `weight_image_kernel` into bf16 hi/lo images already in
 //     the UMMA K-major SWIZZLE_128B layout, so a 128 x 64 weight stage is one contiguous 16 KB block
 //     that a single thread fetches with cp.async.bulk (TMA bulk copy, mbarrier complete_tx);
 //   * all threads load the fp32 A stage (coalesced 16-byte loads), apply the prologue (GELU + dropout
 //     or a dropout mask), split to bf16 hi/lo and write the swizzled smem operand;
 //   * one thread issues the 12 UMMAs of the stage and commits to an mbarrier;
-//   * epilogue: tcgen05.ld 32x32b -- thread t owns row t of the tile, so LayerNorm statistics are
-//     purely in-thread (three passes over TMEM: z (stored back with tcgen05.st), variance, normalise).
+//   * epilogue: tcgen05.ld 32x32b -- warp w reads TMEM lanes 32*(w%4).. (tile rows) and the column half
+//     w/4, one row per thread; LayerNorm statistics are in-thread sums combined across the two column
+//     halves through shared memory (three passes over TMEM: z (stored back with tcgen05.st), variance,
+//     normalise).  The A loads of the next k-stage are issued before the current stage is converted.
 #pragma once
 #include <cuda_bf16.h>
 #include "gemm_simt.cuh"
@@ -27,7 +29,7 @@ namespace dr4sr {
 namespace tc {
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;       // CTA tile; k-stage
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;                      // 8 warps: enough ALU parallelism for split / prologue / epilogue
 constexpr uint32_t kStageBytes = kBM * kBK * 2;     // one bf16 operand stage = 16 KB
 constexpr uint32_t kSmemBytes = 4 * kStageBytes + 1024;   // A_hi, A_lo, B_hi, B_lo (+ alignment slack)
 
@@ -185,12 +187,50 @@ struct TcArgs {
 
 enum TcEpi : int { TC_LINEAR = 0, TC_GELU_BWD = 1, TC_LN = 2 };
 
+constexpr int kRowIters = kBM * (kBK / 8) / kThreads;   // 16-byte bf16 chunks per thread per operand stage (= 4)
+
+// fp32 A stage (128 rows x 64 k) -> registers; rows >= Mlim read as zero
+__device__ __forceinline__ void load_a_stage(const GemmArgs& g, int m0, int Mlim, int s, float4 (&v)[kRowIters][2]) {
+  const int chunk = threadIdx.x & 7, rsub = threadIdx.x >> 3;
+#pragma unroll
+  for (int it = 0; it < kRowIters; ++it) {
+    const int gm = m0 + it * (kThreads / 8) + rsub, gk = s * kBK + chunk * 8;
+    if (gm < Mlim) {
+      const float* p = g.A + (size_t)gm * g.lda + gk;
+      v[it][0] = *reinterpret_cast<const float4*>(p);
+      v[it][1] = *reinterpret_cast<const float4*>(p + 4);
+    } else {
+      v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+// registers -> prologue -> bf16 hi/lo -> swizzled smem operand
+__device__ __forceinline__ void store_a_stage(const GemmArgs& g, int m0, int Mlim, int s, float4 (&v)[kRowIters][2], uint8_t* a_hi,
+                                              uint8_t* a_lo) {
+  const int chunk = threadIdx.x & 7, rsub = threadIdx.x >> 3;
+#pragma unroll
+  for (int it = 0; it < kRowIters; ++it) {
+    const int row = it * (kThreads / 8) + rsub, gm = m0 + row, gk = s * kBK + chunk * 8;
+    if (g.proA != PRO_NONE && gm < Mlim) {
+      const uint32_t idx = (uint32_t)gm * (uint32_t)g.lda + gk;
+      v[it][0] = apply_prologue(v[it][0], g.proA, g.dropA, idx);
+      v[it][1] = apply_prologue(v[it][1], g.proA, g.dropA, idx + 4);
+    }
+    uint4 hi, lo;
+    split_bf16x8(v[it][0], v[it][1], hi, lo);
+    const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)(chunk * 8));
+    *reinterpret_cast<uint4*>(a_hi + off) = hi;
+    *reinterpret_cast<uint4*>(a_lo + off) = lo;
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
   const GemmArgs& g = t.g;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_b, bar_mma;
   __shared__ uint32_t tmem_slot;
+  __shared__ float ln_part[2][kBM];
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * kBN;
@@ -215,8 +255,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
   const uint32_t tmem = tmem_slot;
 
   const int nstage = g.K / kBK;
-  const int chunk = tid & 7, rsub = tid >> 3;               // 8 threads per row (8 x 32 B = one 64-wide k block)
+  float4 va[kRowIters][2], vb[kRowIters][2];
+  load_a_stage(g, m0, Mlim, 0, va);
   for (int s = 0; s < nstage; ++s) {
+    if (s + 1 < nstage) load_a_stage(g, m0, Mlim, s + 1, vb);    // in flight while this stage is converted and multiplied
     if (s > 0) {                                            // the previous stage's UMMAs have consumed the smem operands
       mbar_wait(&bar_mma, (uint32_t)((s - 1) & 1));
       tc_fence_after();
@@ -227,33 +269,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
       bulk_g2s(b_hi, reinterpret_cast<const uint8_t*>(t.b_hi) + off, kStageBytes, &bar_b);
       bulk_g2s(b_lo, reinterpret_cast<const uint8_t*>(t.b_lo) + off, kStageBytes, &bar_b);
     }
-    // A stage: 128 rows x 64 k fp32 -> bf16 hi/lo, swizzled.  8 row-iterations of 16 rows; loads first.
-    float4 va[8][2];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = it * 16 + rsub, gm = m0 + row, gk = s * kBK + chunk * 8;
-      if (gm < Mlim) {
-        const float* p = g.A + (size_t)gm * g.lda + gk;
-        va[it][0] = *reinterpret_cast<const float4*>(p);
-        va[it][1] = *reinterpret_cast<const float4*>(p + 4);
-      } else {
-        va[it][0] = va[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = it * 16 + rsub, gm = m0 + row, gk = s * kBK + chunk * 8;
-      if (g.proA != PRO_NONE && gm < Mlim) {
-        const uint32_t idx = (uint32_t)gm * (uint32_t)g.lda + gk;
-        va[it][0] = apply_prologue(va[it][0], g.proA, g.dropA, idx);
-        va[it][1] = apply_prologue(va[it][1], g.proA, g.dropA, idx + 4);
-      }
-      uint4 hi, lo;
-      split_bf16x8(va[it][0], va[it][1], hi, lo);
-      const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)(chunk * 8));
-      *reinterpret_cast<uint4*>(a_hi + off) = hi;
-      *reinterpret_cast<uint4*>(a_lo + off) = lo;
-    }
+    store_a_stage(g, m0, Mlim, s, va, a_hi, a_lo);
     fence_async_smem();                                     // generic-proxy writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
@@ -269,30 +285,35 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
       }
       umma_commit(&bar_mma);                                // arrives when every UMMA above has finished
     }
+    if (s + 1 < nstage) {
+#pragma unroll
+      for (int it = 0; it < kRowIters; ++it) { va[it][0] = vb[it][0]; va[it][1] = vb[it][1]; }
+    }
   }
   mbar_wait(&bar_mma, (uint32_t)((nstage - 1) & 1));
   tc_fence_after();
 
-  // ---------------- epilogue: thread `tid` owns tile row `tid` (TMEM lane tid) ----------------
-  const int m = m0 + tid;
+  // ---------------- epilogue: warp w -> TMEM lanes 32*(w%4)..+31 (tile rows), column half w/4 ----------------
+  const int lane = tid & 31, quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane, m = m0 + row;
   const bool live = m < Mlim;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (kBN / 2));
+  const int ncol0 = half * (kBN / 2);
   if (EPI != TC_LN) {
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int c = 0; c < kBN / 64; ++c) {
       float v[32];
       tmem_ld32(trow + (uint32_t)(c * 32), v);
       if (!live) continue;
-      const int nb = n0 + c * 32;
+      const int nb = n0 + ncol0 + c * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const int n = nb + j;
         float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         if (EPI == TC_GELU_BWD) {
           const float4 p = *reinterpret_cast<const float4*>(g.pre + (size_t)m * g.ldc + n);
-          const uint32_t idx = (uint32_t)m * (uint32_t)g.ldc + n;
-          o.x *= g.dropE.factor(idx) * gelu_grad_f(p.x); o.y *= g.dropE.factor(idx + 1) * gelu_grad_f(p.y);
-          o.z *= g.dropE.factor(idx + 2) * gelu_grad_f(p.z); o.w *= g.dropE.factor(idx + 3) * gelu_grad_f(p.w);
+          const float4 f = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n);
+          o.x *= f.x * gelu_grad_f(p.x); o.y *= f.y * gelu_grad_f(p.y); o.z *= f.z * gelu_grad_f(p.z); o.w *= f.w * gelu_grad_f(p.w);
         } else {
           if (g.bias) {
             const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
@@ -303,8 +324,8 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
             o.x += aa.x; o.y += aa.y; o.z += aa.z; o.w += aa.w;
           }
           if (g.dropE.thresh) {
-            const uint32_t idx = (uint32_t)m * (uint32_t)g.ldc + n;
-            o.x *= g.dropE.factor(idx); o.y *= g.dropE.factor(idx + 1); o.z *= g.dropE.factor(idx + 2); o.w *= g.dropE.factor(idx + 3);
+            const float4 f = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n);
+            o.x *= f.x; o.y *= f.y; o.z *= f.z; o.w *= f.w;
           }
         }
         *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = o;
@@ -315,42 +336,47 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
     const float invN = 1.0f / (float)kBN;
     float sum = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int c = 0; c < kBN / 64; ++c) {
       float v[32];
       tmem_ld32(trow + (uint32_t)(c * 32), v);
-      const int nb = c * 32;
+      const int nb = ncol0 + c * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const int n = nb + j;
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), rr = bb;
         if (g.bias) bb = *reinterpret_cast<const float4*>(g.bias + n);
         if (live) rr = *reinterpret_cast<const float4*>(g.add + (size_t)m * g.ldadd + n);
-        const uint32_t idx = (uint32_t)m * (uint32_t)kBN + n;
-        v[j] = g.dropE.apply(v[j] + bb.x, idx) + rr.x;
-        v[j + 1] = g.dropE.apply(v[j + 1] + bb.y, idx + 1) + rr.y;
-        v[j + 2] = g.dropE.apply(v[j + 2] + bb.z, idx + 2) + rr.z;
-        v[j + 3] = g.dropE.apply(v[j + 3] + bb.w, idx + 3) + rr.w;
+        const float4 f = g.dropE.factor4((uint32_t)m * (uint32_t)kBN + n);
+        v[j] = (v[j] + bb.x) * f.x + rr.x;
+        v[j + 1] = (v[j + 1] + bb.y) * f.y + rr.y;
+        v[j + 2] = (v[j + 2] + bb.z) * f.z + rr.z;
+        v[j + 3] = (v[j + 3] + bb.w) * f.w + rr.w;
         sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
         if (live && g.Z) *reinterpret_cast<float4*>(g.Z + (size_t)m * kBN + n) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
       tmem_st32(trow + (uint32_t)(c * 32), v);
     }
-    const float mu = sum * invN;
+    ln_part[half][row] = sum;
+    __syncthreads();
+    const float mu = (ln_part[0][row] + ln_part[1][row]) * invN;
+    __syncthreads();
     float var = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int c = 0; c < kBN / 64; ++c) {
       float v[32];
       tmem_ld32(trow + (uint32_t)(c * 32), v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; var = fmaf(d, d, var); }
     }
-    const float rstd = rsqrtf(var * invN + g.ln_eps);
+    ln_part[half][row] = var;
+    __syncthreads();
+    const float rstd = rsqrtf((ln_part[0][row] + ln_part[1][row]) * invN + g.ln_eps);
 #pragma unroll 1
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int c = 0; c < kBN / 64; ++c) {
       float v[32];
       tmem_ld32(trow + (uint32_t)(c * 32), v);
       if (!live) continue;
-      const int nb = c * 32;
+      const int nb = ncol0 + c * 32;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const int n = nb + j;
@@ -362,7 +388,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
         *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = y;
       }
     }
-    if (live && g.stats) { g.stats[2 * m] = mu; g.stats[2 * m + 1] = rstd; }
+    if (live && half == 0 && g.stats) { g.stats[2 * m] = mu; g.stats[2 * m + 1] = rstd; }
   }
   tc_fence_before();
   __syncthreads();
@@ -385,6 +411,177 @@ inline int launch_gemm_tc(const GemmArgs& g, const uint16_t* b_hi, const uint16_
   dim3 grid(g.N / kBN, ceil_div(g.M, kBM));
   gemm_tc_kernel<EPI><<<grid, kThreads, kSmemBytes, st>>>(t);
   DR4SR_LAUNCH_CHECK("gemm_tc_kernel");
+  return DR4SR_OK;
+}
+
+// ---- weight-gradient GEMM: dW[i,j] = sum_m A[m,i] * B[m,j] over the live tokens -----------------------
+// Both operands are token-major activations, i.e. MN-major for this product (the reduction index m is
+// the slow one), so they are staged in the UMMA MN-major SWIZZLE_128B layout (64 features x 8 tokens per
+// 1 KB atom) and multiplied with a_major = b_major = MN.  All weight gradients of a layer go in ONE
+// launch (job table); blockIdx.y splits the tokens, each split writes its partial tile, and the
+// fixed-order reducer (launch_reduce_segments) sums them -> deterministic.
+struct WgradJob {
+  const float* A; int lda; int proA; Dropout dropA;    // [tokens, M_out] (dY)
+  const float* B; int ldb; int proB; Dropout dropB;    // [tokens, N_out] (X)
+  int M_out, N_out;
+  float* partial;                                      // [n_split][M_out * N_out]
+  int tile0;                                           // first linear tile index of this job
+};
+constexpr int kMaxWgradJobs = 4;
+struct WgradTable { WgradJob job[kMaxWgradJobs]; int count; int total_tiles; int T_cap; const int* tok_dev; int n_split; };
+
+// instruction descriptor with both operands MN-major
+constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);
+// MN-major SW128 stage [64 tokens x 128 features]: atom(ib, mb) at ib * 8192 + mb * 1024
+__device__ __forceinline__ uint64_t sw128_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;                  // leading byte offset: next 64-feature block
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next 8-token group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t sw128_offset_mn(uint32_t tok, uint32_t feat) {   // tok < 64, feat < 128, feat % 8 == 0
+  return (feat >> 6) * 8192u + (tok >> 3) * 1024u + (tok & 7u) * 128u + (((((feat & 63u) >> 3) ^ (tok & 7u)) & 7u) << 4);
+}
+
+__global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable tab) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  int ji = 0;
+  while (ji + 1 < tab.count && (int)blockIdx.x >= tab.job[ji + 1].tile0) ++ji;
+  const WgradJob& job = tab.job[ji];
+  const int tile = blockIdx.x - job.tile0, ntn = job.N_out / kBN;
+  const int i0 = (tile / ntn) * kBM, j0 = (tile % ntn) * kBN;
+
+  const int R = min(tab.T_cap, tab.tok_dev ? *tab.tok_dev : tab.T_cap);
+  int len = (R + tab.n_split - 1) / tab.n_split;
+  len = (len + kBK - 1) / kBK * kBK;
+  const int kbeg = min(R, (int)blockIdx.y * len), kend = min(R, kbeg + len);
+  const int nstage = (kend - kbeg + kBK - 1) / kBK;
+  float* out = job.partial + (size_t)blockIdx.y * job.M_out * job.N_out;
+
+  if (nstage == 0) {                                   // no tokens in this split: the partial is zero
+    for (int e = tid; e < kBM * kBN / 4; e += kThreads) {
+      const int r = e / (kBN / 4), c = (e % (kBN / 4)) * 4;
+      *reinterpret_cast<float4*>(out + (size_t)(i0 + r) * job.N_out + j0 + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return;
+  }
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_hi = smem;
+  uint8_t* a_lo = smem + kStageBytes;
+  uint8_t* b_hi = smem + 2 * kStageBytes;
+  uint8_t* b_lo = smem + 3 * kStageBytes;
+  if (tid == 0) {
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, kBN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  // a stage = 64 tokens x 128 features per operand = 1024 16-byte chunks -> 4 per thread per operand;
+  // 16 consecutive lanes read one token's 512 contiguous bytes
+  const int fchunk = tid & 15, tsub = tid >> 4;        // feature chunk (8 floats), token within a group of 16
+  for (int s = 0; s < nstage; ++s) {
+    float4 ra[4][2], rb[4][2];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int tok = it * 16 + tsub, gm = kbeg + s * kBK + tok;
+      if (gm < kend) {
+        const float* pa = job.A + (size_t)gm * job.lda + i0 + fchunk * 8;
+        const float* pb = job.B + (size_t)gm * job.ldb + j0 + fchunk * 8;
+        ra[it][0] = *reinterpret_cast<const float4*>(pa); ra[it][1] = *reinterpret_cast<const float4*>(pa + 4);
+        rb[it][0] = *reinterpret_cast<const float4*>(pb); rb[it][1] = *reinterpret_cast<const float4*>(pb + 4);
+      } else {
+        ra[it][0] = ra[it][1] = rb[it][0] = rb[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (s > 0) {
+      mbar_wait(&bar_mma, (uint32_t)((s - 1) & 1));
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int tok = it * 16 + tsub, gm = kbeg + s * kBK + tok;
+      if (gm < kend) {
+        if (job.proA != PRO_NONE) {
+          const uint32_t idx = (uint32_t)gm * (uint32_t)job.lda + i0 + fchunk * 8;
+          ra[it][0] = apply_prologue(ra[it][0], job.proA, job.dropA, idx);
+          ra[it][1] = apply_prologue(ra[it][1], job.proA, job.dropA, idx + 4);
+        }
+        if (job.proB != PRO_NONE) {
+          const uint32_t idx = (uint32_t)gm * (uint32_t)job.ldb + j0 + fchunk * 8;
+          rb[it][0] = apply_prologue(rb[it][0], job.proB, job.dropB, idx);
+          rb[it][1] = apply_prologue(rb[it][1], job.proB, job.dropB, idx + 4);
+        }
+      }
+      uint4 hi, lo;
+      const uint32_t off = sw128_offset_mn((uint32_t)tok, (uint32_t)(fchunk * 8));
+      split_bf16x8(ra[it][0], ra[it][1], hi, lo);
+      *reinterpret_cast<uint4*>(a_hi + off) = hi;
+      *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      split_bf16x8(rb[it][0], rb[it][1], hi, lo);
+      *reinterpret_cast<uint4*>(b_hi + off) = hi;
+      *reinterpret_cast<uint4*>(b_lo + off) = lo;
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+#pragma unroll
+      for (int k = 0; k < kBK / 16; ++k) {             // 16 tokens = two 8-token groups = 2048 bytes
+        const uint32_t ko = (uint32_t)k * 2048u;
+        umma_bf16(tmem, sw128_desc_mn(ah + ko), sw128_desc_mn(bh + ko), kIdescMN, (s > 0 || k > 0) ? 1u : 0u);
+        umma_bf16(tmem, sw128_desc_mn(ah + ko), sw128_desc_mn(bl + ko), kIdescMN, 1u);
+        umma_bf16(tmem, sw128_desc_mn(al + ko), sw128_desc_mn(bh + ko), kIdescMN, 1u);
+      }
+      umma_commit(&bar_mma);
+    }
+  }
+  mbar_wait(&bar_mma, (uint32_t)((nstage - 1) & 1));
+  tc_fence_after();
+  const int lane = tid & 31, quad = warp & 3, half = warp >> 2;
+  const int row = quad * 32 + lane;
+  const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * (kBN / 2));
+#pragma unroll 1
+  for (int c = 0; c < kBN / 64; ++c) {
+    float v[32];
+    tmem_ld32(trow + (uint32_t)(c * 32), v);
+    float* dst = out + (size_t)(i0 + row) * job.N_out + j0 + half * (kBN / 2) + c * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kBN);
+}
+
+inline bool wgrad_supported(int M_out, int N_out) { return M_out % kBM == 0 && N_out % kBN == 0; }
+
+inline int launch_wgrad_tc(WgradTable& tab, cudaStream_t st) {
+  if (tab.count <= 0 || tab.count > kMaxWgradJobs) return DR4SR_EINVAL;
+  int tiles = 0;
+  for (int i = 0; i < tab.count; ++i) {
+    if (!wgrad_supported(tab.job[i].M_out, tab.job[i].N_out) || tab.job[i].lda % 4 || tab.job[i].ldb % 4) return DR4SR_EINVAL;
+    tab.job[i].tile0 = tiles;
+    tiles += (tab.job[i].M_out / kBM) * (tab.job[i].N_out / kBN);
+  }
+  tab.total_tiles = tiles;
+  ProfScope prof("wgrad_tc", st);
+  if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "wgrad_tc smem attribute");
+    return DR4SR_ECUDA;
+  }
+  wgrad_tc_kernel<<<dim3(tiles, tab.n_split), kThreads, kSmemBytes, st>>>(tab);
+  DR4SR_LAUNCH_CHECK("wgrad_tc_kernel");
   return DR4SR_OK;
 }
 

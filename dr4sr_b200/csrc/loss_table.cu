@@ -121,26 +121,35 @@ __global__ void __launch_bounds__(256) table_grad_kernel(const float* __restrict
   }
 }
 
-// dP[t] = sum over sequences with len > t of dx0[(b,t)]: grid (L, D/128 chunks); fixed order over b.
-__global__ void __launch_bounds__(128) pos_grad_kernel(const float* __restrict__ dx0, const int32_t* __restrict__ tok_off, int B,
-                                                       int D, float* __restrict__ pos_grad) {
-  const int t = blockIdx.x;
-  const int col = blockIdx.y * 128 + threadIdx.x;
-  if (col >= D) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 3 < B; b += 4) {
-    const int o0 = tok_off[b], o1 = tok_off[b + 1], o2 = tok_off[b + 2], o3 = tok_off[b + 3], o4 = tok_off[b + 4];
-    if (o1 - o0 > t) s0 += dx0[(size_t)(o0 + t) * D + col];
-    if (o2 - o1 > t) s1 += dx0[(size_t)(o1 + t) * D + col];
-    if (o3 - o2 > t) s2 += dx0[(size_t)(o2 + t) * D + col];
-    if (o4 - o3 > t) s3 += dx0[(size_t)(o3 + t) * D + col];
+// dP[t] = sum_b dx0[(b,t)].  Each CTA streams the packed rows of a contiguous slice of sequences (the rows
+// of a sequence are adjacent, so this is a linear read of dx0) and accumulates them per position in
+// shared memory: warp w owns the positions t % 8 == w and lane c the columns 4c.., so every accumulator
+// has a single writer and rows are added in a fixed order.  The [L, D] partial of each CTA goes to the
+// workspace and the fixed-order reducer sums the kPosChunks partials -> deterministic.
+constexpr int kPosChunks = 2 * kNumSMs;
+__global__ void __launch_bounds__(256) pos_grad_kernel(const float* __restrict__ dx0, const int32_t* __restrict__ tok_off, int B, int L,
+                                                       int D, float* __restrict__ partial) {
+  extern __shared__ __align__(16) float acc[];           // [L][D]
+  for (int e = threadIdx.x; e < L * D; e += blockDim.x) acc[e] = 0.f;
+  __syncthreads();
+  const int per = (B + gridDim.x - 1) / gridDim.x;
+  const int b0 = min(B, (int)blockIdx.x * per), b1 = min(B, b0 + per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = b0; b < b1; ++b) {
+    const int off = tok_off[b], len = min(tok_off[b + 1] - off, L);
+    for (int t = warp; t < len; t += 8) {
+      for (int c = lane * 4; c < D; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(dx0 + (size_t)(off + t) * D + c);
+        float4* a = reinterpret_cast<float4*>(acc + t * D + c);
+        float4 o = *a;
+        o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+        *a = o;
+      }
+    }
   }
-  for (; b < B; ++b) {
-    const int o0 = tok_off[b];
-    if (tok_off[b + 1] - o0 > t) s0 += dx0[(size_t)(o0 + t) * D + col];
-  }
-  pos_grad[(size_t)t * D + col] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  float* out = partial + (size_t)blockIdx.x * L * D;
+  for (int e = threadIdx.x; e < L * D; e += blockDim.x) out[e] = acc[e];
 }
 
 // torch.optim.Adam (_single_tensor_adam op order): g += wd p; m = lerp(m, g, 1-b1);
@@ -208,10 +217,13 @@ extern "C" int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t s
   return DR4SR_OK;
 }
 
+extern "C" size_t dr4sr_table_grad_workspace_bytes(int32_t L, int32_t D) { return sizeof(float) * (size_t)kPosChunks * L * D; }
+
 extern "C" int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, const float* dscore,
                                 const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
                                 const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
-                                int32_t D, int64_t N, float* table_grad, float* pos_grad, dr4sr_stream_t stream) {
+                                int32_t D, int64_t N, float* table_grad, float* pos_grad, void* ws, size_t ws_bytes,
+                                dr4sr_stream_t stream) {
   (void)N;
   if (!in_item_id || !tok_off || !row_seq || !counts || !table_grad || D % 4) return DR4SR_EINVAL;
   if (item_id && (!q_packed || !dscore || !neg_item)) return DR4SR_EINVAL;
@@ -225,9 +237,22 @@ extern "C" int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, 
   DR4SR_LAUNCH_CHECK("table_grad_kernel");
   }
   if (pos_grad && dx0_packed) {
-    ProfScope prof("pos_grad", st);
-    pos_grad_kernel<<<dim3(L, ceil_div(D, 128)), 128, 0, st>>>(dx0_packed, tok_off, B, D, pos_grad);
-    DR4SR_LAUNCH_CHECK("pos_grad_kernel");
+    if (!ws || ws_bytes < dr4sr_table_grad_workspace_bytes(L, D)) return DR4SR_EWORKSPACE;
+    float* partial = reinterpret_cast<float*>(ws);
+    const size_t smem = sizeof(float) * (size_t)L * D;
+    {
+      ProfScope prof("pos_grad", st);
+      if (cudaFuncSetAttribute(pos_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_cuda_error(cudaGetLastError(), "pos_grad smem attribute");
+        return DR4SR_ECUDA;
+      }
+      pos_grad_kernel<<<kPosChunks, 256, smem, st>>>(dx0_packed, tok_off, B, L, D, partial);
+      DR4SR_LAUNCH_CHECK("pos_grad_kernel");
+    }
+    ReduceTable tab{};
+    tab.seg[0] = ReduceSeg{partial, pos_grad, kPosChunks, (int64_t)L * D, L * D};
+    tab.count = 1;
+    DR4SR_TRY(launch_reduce_segments(tab, st));
   }
   return DR4SR_OK;
 }

@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         o.z = rstd * (g[c].z - s1 - xh[c].z * s2); o.w = rstd * (g[c].w - s1 - xh[c].w * s2);
         *reinterpret_cast<float4*>(dz + (size_t)row * D + col) = o;
         const uint32_t idx = (uint32_t)row * (uint32_t)D + col;
-        acc_bias[c].x += o.x * bias_drop.factor(idx); acc_bias[c].y += o.y * bias_drop.factor(idx + 1);
-        acc_bias[c].z += o.z * bias_drop.factor(idx + 2); acc_bias[c].w += o.w * bias_drop.factor(idx + 3);
+        const float4 f = bias_drop.factor4(idx);
+        acc_bias[c].x += o.x * f.x; acc_bias[c].y += o.y * f.y; acc_bias[c].z += o.z * f.z; acc_bias[c].w += o.w * f.w;
       }
     }
   }

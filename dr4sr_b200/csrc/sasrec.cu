@@ -13,7 +13,7 @@ namespace {
 
 std::atomic<int> g_gemm_backend{0};   // 0 = tcgen05 where the shape allows, 1 = FFMA everywhere (dr4sr_set_gemm_backend)
 
-constexpr int kSplit = 32;   // token splits of the weight-gradient GEMMs (partials reduced in fixed order)
+constexpr int kSplit = 64;   // token splits of the weight-gradient GEMMs (partials reduced in fixed order)
 
 struct LayerOffsets {   // offsets (floats) inside one layer's slice of the flat parameter buffer
   size_t in_w, in_b, out_w, out_b, w1, b1, w2, b2, g1, be1, g2, be2, total;
@@ -42,7 +42,7 @@ struct Workspace {
   float* x0;
   struct Layer { float *qkv, *attn, *z1, *st1, *x1, *pre, *z2, *st2, *x2; } layer[8];
   // backward scratch
-  float *g0, *g1, *g2, *dqkv, *dpre;
+  float *g0, *g1, *g2, *g3, *dqkv, *dpre;
   float *part_w;     // [kSplit][3DD + DD + FD + DF] weight-gradient partials of the current layer
   float *part_ln2, *part_ln1;   // [kLnBwdBlocks][3D]
   float *part_cs_in, *part_cs_b1;   // [kColsumBlocks][3D], [kColsumBlocks][F]
@@ -67,7 +67,7 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
     y.qkv = take(T * 3 * D); y.attn = take(T * D); y.z1 = take(T * D); y.st1 = take(T * 2); y.x1 = take(T * D);
     y.pre = take(T * F); y.z2 = take(T * D); y.st2 = take(T * 2); y.x2 = take(T * D);
   }
-  w.g0 = take(T * D); w.g1 = take(T * D); w.g2 = take(T * D); w.dqkv = take(T * 3 * D); w.dpre = take(T * F);
+  w.g0 = take(T * D); w.g1 = take(T * D); w.g2 = take(T * D); w.g3 = take(T * D); w.dqkv = take(T * 3 * D); w.dpre = take(T * F);
   w.part_w = take((size_t)kSplit * (3 * D * D + D * D + 2 * F * D));
   w.part_ln2 = take((size_t)kLnBwdBlocks * 3 * D);
   w.part_ln1 = take((size_t)kLnBwdBlocks * 3 * D);
@@ -295,28 +295,18 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
     const Dropout d_attn_out = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_OUT, l), tr);
     const Dropout d_attn_p = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr);
 
-    // LN2 backward: g1 = dz2 ; partials -> dgamma2, dbeta2, db2
-    DR4SR_TRY(launch_ln_bwd(gin, y.z2, y.st2, lp + lo.g2, w.g1, w.part_ln2, D, T, counts, d_ffn_out, st));
+    // LN2 backward: g3 = dz2 ; partials -> dgamma2, dbeta2, db2
+    DR4SR_TRY(launch_ln_bwd(gin, y.z2, y.st2, lp + lo.g2, w.g3, w.part_ln2, D, T, counts, d_ffn_out, st));
     {  // dpre = ((dz2 * mask_out) W2) * mask_h * gelu'(pre)
-      GemmArgs g = gemm_args(w.g1, D, lp + lo.w2, F, w.dpre, F, T, F, D, counts);
+      GemmArgs g = gemm_args(w.g3, D, lp + lo.w2, F, w.dpre, F, T, F, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_ffn_out;
       g.epi = EPI_GELU_BWD; g.pre = y.pre; g.dropE = d_ffn_h; g.tag = "gemm_bwd_dpre";
       DR4SR_TRY(gemm_nn(g, w.img[l].w2_b, st));
     }
-    {  // dW2[d,f] = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]
-      GemmArgs g = gemm_args(w.g1, D, y.pre, F, nullptr, F, D, F, T, counts);
-      g.proA = PRO_DROPMASK; g.dropA = d_ffn_out; g.proB = PRO_GELU_DROP; g.dropB = d_ffn_h; g.tag = "gemm_wgrad_w2";
-      DR4SR_TRY(gemm_tn(g, w.part_w + pw_w2, st));
-    }
-    {  // dW1[f,d] = sum_m dpre[m,f] * x1[m,d]
-      GemmArgs g = gemm_args(w.dpre, F, y.x1, D, nullptr, D, F, D, T, counts);
-      g.tag = "gemm_wgrad_w1";
-      DR4SR_TRY(gemm_tn(g, w.part_w + pw_w1, st));
-    }
     DR4SR_TRY(launch_colsum(w.dpre, F, T, counts, w.part_cs_b1, st));
     {  // dx1 = dz2 + dpre W1   -> g0
       GemmArgs g = gemm_args(w.dpre, F, lp + lo.w1, D, w.g0, D, T, D, F, counts);
-      g.add = w.g1; g.ldadd = D; g.tag = "gemm_bwd_dx1";
+      g.add = w.g3; g.ldadd = D; g.tag = "gemm_bwd_dx1";
       DR4SR_TRY(gemm_nn(g, w.img[l].w1_b, st));
     }
     // LN1 backward: g1 = dz1 ; partials -> dgamma1, dbeta1, db_out
@@ -326,17 +316,7 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
       g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_bwd_dattn";
       DR4SR_TRY(gemm_nn(g, w.img[l].out_b, st));
     }
-    {  // dWo[n,k] = sum_m (dz1*mask)[m,n] * attn[m,k]
-      GemmArgs g = gemm_args(w.g1, D, y.attn, D, nullptr, D, D, D, T, counts);
-      g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_wgrad_out";
-      DR4SR_TRY(gemm_tn(g, w.part_w + pw_out, st));
-    }
     DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, w.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
-    {  // dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
-      GemmArgs g = gemm_args(w.dqkv, 3 * D, xin, D, nullptr, D, 3 * D, D, T, counts);
-      g.tag = "gemm_wgrad_in";
-      DR4SR_TRY(gemm_tn(g, w.part_w + pw_in, st));
-    }
     DR4SR_TRY(launch_colsum(w.dqkv, 3 * D, T, counts, w.part_cs_in, st));
     {  // dx = dz1 + dqkv Win  (layer 0: times the embedding-dropout mask) -> g0 / dx0
       float* dst = l == 0 ? dx0_packed : w.g0;
@@ -345,6 +325,41 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
       if (l == 0) g.dropE = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
       g.tag = "gemm_bwd_dx";
       DR4SR_TRY(gemm_nn(g, w.img[l].in_b, st));
+    }
+    // weight gradients (reduction over the live tokens, kSplit partial tiles each):
+    //   dW2[d,f]  = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]      dW1[f,d]  = sum_m dpre[m,f] * x1[m,d]
+    //   dWo[n,k]  = sum_m (dz1*mask)[m,n] * attn[m,k]                     dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
+    if (g_gemm_backend.load(std::memory_order_relaxed) == 0 && tc::wgrad_supported(D, F) && tc::wgrad_supported(F, D) &&
+        tc::wgrad_supported(D, D) && tc::wgrad_supported(3 * D, D)) {
+      tc::WgradTable tab{};
+      Dropout none; none.key = 0; none.thresh = 0; none.scale = 1.f;
+      tab.job[0] = tc::WgradJob{w.dqkv, 3 * D, PRO_NONE, none, xin, D, PRO_NONE, none, 3 * D, D, w.part_w + pw_in, 0};
+      tab.job[1] = tc::WgradJob{w.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, w.part_w + pw_w2, 0};
+      tab.job[2] = tc::WgradJob{w.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, w.part_w + pw_w1, 0};
+      tab.job[3] = tc::WgradJob{w.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, w.part_w + pw_out, 0};
+      tab.count = 4; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
+      DR4SR_TRY(tc::launch_wgrad_tc(tab, st));
+    } else {
+      {
+        GemmArgs g = gemm_args(w.g3, D, y.pre, F, nullptr, F, D, F, T, counts);
+        g.proA = PRO_DROPMASK; g.dropA = d_ffn_out; g.proB = PRO_GELU_DROP; g.dropB = d_ffn_h; g.tag = "gemm_wgrad_w2";
+        DR4SR_TRY(gemm_tn(g, w.part_w + pw_w2, st));
+      }
+      {
+        GemmArgs g = gemm_args(w.dpre, F, y.x1, D, nullptr, D, F, D, T, counts);
+        g.tag = "gemm_wgrad_w1";
+        DR4SR_TRY(gemm_tn(g, w.part_w + pw_w1, st));
+      }
+      {
+        GemmArgs g = gemm_args(w.g1, D, y.attn, D, nullptr, D, D, D, T, counts);
+        g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_wgrad_out";
+        DR4SR_TRY(gemm_tn(g, w.part_w + pw_out, st));
+      }
+      {
+        GemmArgs g = gemm_args(w.dqkv, 3 * D, xin, D, nullptr, D, 3 * D, D, T, counts);
+        g.tag = "gemm_wgrad_in";
+        DR4SR_TRY(gemm_tn(g, w.part_w + pw_in, st));
+      }
     }
     {  // fixed-order reduction of every partial of this layer into the flat gradient buffer
       ReduceTable tab{};

@@ -65,6 +65,7 @@ class SASRecEngine:
             raise _lib.Dr4srError(f'unsupported SASRec shape D={self.D} F={self.F} L={self.L} heads={self.H} '
                                   f'layers={self.n_layer} (D in {{64,128}}, F % 64 == 0, L <= 64)')
         self.param_count = int(n)
+        self._tg_ws = torch.empty(self.lib.dr4sr_table_grad_workspace_bytes(self.L, self.D), dtype=torch.uint8, device=self.device)
 
     # ---- configuration ------------------------------------------------------------------------
     def cfg(self, B: int, step: Optional[int] = None) -> SasrecCfg:
@@ -143,7 +144,8 @@ class SASRecEngine:
         B = in_ids.size(0)
         check(self.lib.dr4sr_table_grad(_p(b.dx0) if with_dx0 else None, _p(b.q_packed), _p(b.dscore), _p(in_ids), _p(item_id),
                                         _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L, self.D, self.N,
-                                        _p(table_grad), _p(pos_grad), _stream()), 'dr4sr_table_grad')
+                                        _p(table_grad), _p(pos_grad), _p(self._tg_ws), self._tg_ws.numel(), _stream()),
+              'dr4sr_table_grad')
 
 
 # ---- stateless wrappers ---------------------------------------------------------------------------

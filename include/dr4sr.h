@@ -142,12 +142,15 @@ DR4SR_API int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t st
  * (nn.Embedding input lookup model/sasrec.py:46, weight[item_id] / weight[neg_item]
  * model/basemodel.py:206-207): table_grad[in_id] += dx0; [item_id] += ds+ q; [neg] += ds- q.
  * table_grad [N,D] is accumulated into (caller zeroes it; dr4sr_adam can zero it while reading).
- * pos_grad [L,D] (optional): dP[t] = sum_b dx0[b,t], overwritten.
+ * pos_grad [L,D] (optional): dP[t] = sum_b dx0[b,t], overwritten; needs ws of
+ * dr4sr_table_grad_workspace_bytes(L, D) bytes (per-CTA partials, summed in a fixed order).
  */
+DR4SR_API size_t dr4sr_table_grad_workspace_bytes(int32_t L, int32_t D);
 DR4SR_API int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, const float* dscore,
                      const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
                      const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
-                     int32_t D, int64_t N, float* table_grad, float* pos_grad, dr4sr_stream_t stream);
+                     int32_t D, int64_t N, float* table_grad, float* pos_grad, void* ws, size_t ws_bytes,
+                     dr4sr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense Adam, replaces torch.optim.Adam.step as configured at model/basemodel.py:85-86
