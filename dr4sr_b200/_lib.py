@@ -17,6 +17,12 @@ LIB_PATH = os.path.join(CSRC, 'libdr4sr.so')
 c_i32, c_i64, c_u64, c_f32, c_sz, c_p = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_size_t, C.c_void_p
 
 
+class FmlpCfg(C.Structure):
+    """Mirror of dr4sr_fmlp_cfg."""
+    _fields_ = [('B', c_i32), ('L', c_i32), ('D', c_i32), ('n_layer', c_i32), ('N', c_i64), ('dropout_p', c_f32),
+                ('ln_eps', c_f32), ('seed', c_u64), ('step', c_u64)]
+
+
 class SasrecCfg(C.Structure):
     """Mirror of dr4sr_sasrec_cfg."""
     _fields_ = [('B', c_i32), ('L', c_i32), ('D', c_i32), ('F', c_i32), ('n_head', c_i32), ('n_layer', c_i32),
@@ -37,6 +43,10 @@ SIGNATURES = {
     'dr4sr_sasrec_workspace_bytes': (c_sz, [C.POINTER(SasrecCfg)]),
     'dr4sr_sasrec_fwd': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p, c_p, c_p]),
     'dr4sr_sasrec_bwd': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
+    'dr4sr_fmlp_param_count': (c_sz, [C.POINTER(FmlpCfg)]),
+    'dr4sr_fmlp_workspace_bytes': (c_sz, [C.POINTER(FmlpCfg)]),
+    'dr4sr_fmlp_fwd': (c_i32, [C.POINTER(FmlpCfg), c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p]),
+    'dr4sr_fmlp_bwd': (c_i32, [C.POINTER(FmlpCfg), c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
     'dr4sr_score_bce': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p]),
     'dr4sr_sum': (c_i32, [c_p, c_i64, c_p, c_p]),
     'dr4sr_table_grad_workspace_bytes': (c_sz, [c_i32, c_i32]),

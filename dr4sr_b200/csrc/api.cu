@@ -15,6 +15,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_err, sizeof(g_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
 }
 
+std::atomic<int> g_gemm_backend{0};
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -43,6 +44,11 @@ using namespace dr4sr;
 
 extern "C" int dr4sr_abi_version(void) { return DR4SR_ABI_VERSION; }
 extern "C" const char* dr4sr_last_cuda_error(void) { return g_err; }
+extern "C" int dr4sr_set_gemm_backend(int backend) {
+  if (backend != 0 && backend != 1) return DR4SR_EINVAL;
+  g_gemm_backend.store(backend);
+  return DR4SR_OK;
+}
 extern "C" long long dr4sr_launch_count(void) { return g_launches.load(); }
 
 extern "C" int dr4sr_prof_enable(int on) {

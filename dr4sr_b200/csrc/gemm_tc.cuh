@@ -144,7 +144,7 @@ struct ImageJob { const float* src; int ld; int N, K; int transpose; uint16_t* h
 constexpr int kMaxImageJobs = 16;
 struct ImageTable { ImageJob job[kMaxImageJobs]; int count; };
 
-__global__ void __launch_bounds__(256) weight_image_kernel(ImageTable tab) {
+static __global__ void __launch_bounds__(256) weight_image_kernel(ImageTable tab) {
   const ImageJob j = tab.job[blockIdx.y];
   const int chunks = j.N * (j.K / 8);                 // 16-byte chunks (8 consecutive k of one row)
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += gridDim.x * blockDim.x) {
@@ -446,7 +446,7 @@ __device__ __forceinline__ uint32_t sw128_offset_mn(uint32_t tok, uint32_t feat)
   return (feat >> 6) * 8192u + (tok >> 3) * 1024u + (tok & 7u) * 128u + (((((feat & 63u) >> 3) ^ (tok & 7u)) & 7u) << 4);
 }
 
-__global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable tab) {
+static __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable tab) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_slot;

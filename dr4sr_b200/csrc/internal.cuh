@@ -15,7 +15,11 @@ int launch_attn_bwd(const float* qkv, const float* d_out, const int64_t* in_ids,
 //   [2D..3D) = sum dz * bias_drop.factor (gradient of the bias that sits under the dropout before this LN)
 constexpr int kLnBwdBlocks = 2 * kNumSMs;
 int launch_ln_bwd(const float* dy, const float* z, const float* stats, const float* gamma, float* dz, float* partials,
-                  int D, int T_cap, const int32_t* tok_dev, Dropout bias_drop, cudaStream_t st);
+                  int D, int T_cap, const int32_t* tok_dev, Dropout bias_drop, cudaStream_t st,
+                  Dropout dy_drop = Dropout{0u, 0u, 1.0f});
+// y = dropout(LayerNorm(z)) over packed rows, stats = {mean, rstd}
+int launch_ln_fwd(const float* z, const float* gamma, const float* beta, float eps, float* y, float* stats, int D, int T_cap,
+                  const int32_t* tok_dev, Dropout out_drop, cudaStream_t st);
 // column sums of x[T, N] -> partials[blk][N]
 constexpr int kColsumBlocks = 2 * kNumSMs;
 int launch_colsum(const float* x, int N, int T_cap, const int32_t* tok_dev, float* partials, cudaStream_t st);

@@ -11,7 +11,7 @@ template <int NCHUNK>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                                                      const float* __restrict__ stats, const float* __restrict__ gamma,
                                                      float* __restrict__ dz, float* __restrict__ partials, int D, int T_cap,
-                                                     const int32_t* __restrict__ tok_dev, Dropout bias_drop) {
+                                                     const int32_t* __restrict__ tok_dev, Dropout bias_drop, Dropout dy_drop) {
   const int T = min(T_cap, tok_dev ? *tok_dev : T_cap);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float invD = 1.0f / (float)D;
@@ -33,6 +33,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       const int col = c * 128 + lane * 4;
       if (on[c]) {
         g[c] = *reinterpret_cast<const float4*>(dy + (size_t)row * D + col);
+        if (dy_drop.thresh) {   // the normalised output went through a dropout (FMLP embedding stage)
+          const float4 f = dy_drop.factor4((uint32_t)row * (uint32_t)D + col);
+          g[c].x *= f.x; g[c].y *= f.y; g[c].z *= f.z; g[c].w *= f.w;
+        }
         const float4 zz = *reinterpret_cast<const float4*>(z + (size_t)row * D + col);
         xh[c] = make_float4((zz.x - mu) * rstd, (zz.y - mu) * rstd, (zz.z - mu) * rstd, (zz.w - mu) * rstd);
         acc_g[c].x += g[c].x * xh[c].x; acc_g[c].y += g[c].y * xh[c].y; acc_g[c].z += g[c].z * xh[c].z; acc_g[c].w += g[c].w * xh[c].w;
@@ -76,6 +80,43 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][k][col];
     partials[(size_t)blockIdx.x * 3 * D + e] = s;
+  }
+}
+
+// y = dropout(LayerNorm(z)) row-wise, stats[row] = {mean, rstd}; warp per row, two-pass moments in registers
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, float* __restrict__ y,
+                                                     float* __restrict__ stats, int D, int T_cap, const int32_t* __restrict__ tok_dev,
+                                                     Dropout out_drop) {
+  const int T = min(T_cap, tok_dev ? *tok_dev : T_cap);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float invD = 1.0f / (float)D;
+  for (int row = blockIdx.x * 8 + warp; row < T; row += gridDim.x * 8) {
+    float4 v[2];
+    float s = 0.f;
+    int k = 0;
+    for (int c = lane * 4; c < D; c += 128, ++k) {
+      v[k] = *reinterpret_cast<const float4*>(z + (size_t)row * D + c);
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float mu = warp_sum(s) * invD;
+    float q = 0.f;
+    k = 0;
+    for (int c = lane * 4; c < D; c += 128, ++k) {
+      const float a = v[k].x - mu, b = v[k].y - mu, cc = v[k].z - mu, d = v[k].w - mu;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invD + eps);
+    k = 0;
+    for (int c = lane * 4; c < D; c += 128, ++k) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+      const float4 f = out_drop.factor4((uint32_t)row * (uint32_t)D + c);
+      float4 o;
+      o.x = ((v[k].x - mu) * rstd * g.x + be.x) * f.x; o.y = ((v[k].y - mu) * rstd * g.y + be.y) * f.y;
+      o.z = ((v[k].z - mu) * rstd * g.z + be.z) * f.z; o.w = ((v[k].w - mu) * rstd * g.w + be.w) * f.w;
+      *reinterpret_cast<float4*>(y + (size_t)row * D + c) = o;
+    }
+    if (lane == 0) { stats[2 * row] = mu; stats[2 * row + 1] = rstd; }
   }
 }
 
@@ -141,14 +182,24 @@ __global__ void __launch_bounds__(256) reduce_segments_kernel(ReduceTable tab) {
 }  // namespace
 
 int launch_ln_bwd(const float* dy, const float* z, const float* stats, const float* gamma, float* dz, float* partials,
-                  int D, int T_cap, const int32_t* tok_dev, Dropout bias_drop, cudaStream_t st) {
+                  int D, int T_cap, const int32_t* tok_dev, Dropout bias_drop, cudaStream_t st, Dropout dy_drop) {
   if (D % 4 || D > 256) return DR4SR_EINVAL;
   ProfScope prof("ln_bwd", st);
   if (D <= 128)
-    ln_bwd_kernel<1><<<kLnBwdBlocks, 256, 0, st>>>(dy, z, stats, gamma, dz, partials, D, T_cap, tok_dev, bias_drop);
+    ln_bwd_kernel<1><<<kLnBwdBlocks, 256, 0, st>>>(dy, z, stats, gamma, dz, partials, D, T_cap, tok_dev, bias_drop, dy_drop);
   else
-    ln_bwd_kernel<2><<<kLnBwdBlocks, 256, 0, st>>>(dy, z, stats, gamma, dz, partials, D, T_cap, tok_dev, bias_drop);
+    ln_bwd_kernel<2><<<kLnBwdBlocks, 256, 0, st>>>(dy, z, stats, gamma, dz, partials, D, T_cap, tok_dev, bias_drop, dy_drop);
   DR4SR_LAUNCH_CHECK("ln_bwd_kernel");
+  return DR4SR_OK;
+}
+
+int launch_ln_fwd(const float* z, const float* gamma, const float* beta, float eps, float* y, float* stats, int D, int T_cap,
+                  const int32_t* tok_dev, Dropout out_drop, cudaStream_t st) {
+  if (D % 4 || D > 256) return DR4SR_EINVAL;
+  ProfScope prof("ln_fwd", st);
+  const int blocks = ceil_div(T_cap, 8) < 8 * kNumSMs ? ceil_div(T_cap, 8) : 8 * kNumSMs;
+  ln_fwd_kernel<<<blocks, 256, 0, st>>>(z, gamma, beta, eps, y, stats, D, T_cap, tok_dev, out_drop);
+  DR4SR_LAUNCH_CHECK("ln_fwd_kernel");
   return DR4SR_OK;
 }
 

@@ -3,17 +3,11 @@
 // Replaces SASRecQueryEncoder.forward (reference model/sasrec.py:39-75) = embedding + learned
 // positions + dropout -> 2 x post-norm TransformerEncoderLayer (model/sasrec.py:21-34) -> pooling,
 // and its autograd backward.  Spec: SURVEY.md Appendix C.1, C.2, C.5.
-#include <atomic>
-#include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
-#include "internal.cuh"
+#include "dense.cuh"
 
 namespace dr4sr {
 namespace {
 
-std::atomic<int> g_gemm_backend{0};   // 0 = tcgen05 where the shape allows, 1 = FFMA everywhere (dr4sr_set_gemm_backend)
-
-constexpr int kSplit = 64;   // token splits of the weight-gradient GEMMs (partials reduced in fixed order)
 
 struct LayerOffsets {   // offsets (floats) inside one layer's slice of the flat parameter buffer
   size_t in_w, in_b, out_w, out_b, w1, b1, w2, b2, g1, be1, g2, be2, total;
@@ -48,7 +42,6 @@ struct Workspace {
   float *part_cs_in, *part_cs_b1;   // [kColsumBlocks][3D], [kColsumBlocks][F]
   // bf16 hi/lo weight images (UMMA SW128 K-major) of every layer: forward operands W[n,k] and the
   // transposed backward-data operands W^T, rebuilt at the start of every forward
-  struct Img { uint16_t *hi, *lo; };
   struct LayerImg { Img in_f, out_f, w1_f, w2_f, in_b, out_b, w1_b, w2_b; } img[8];
   size_t bytes;
 };
@@ -74,7 +67,7 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
   w.part_cs_in = take((size_t)kColsumBlocks * 3 * D);
   w.part_cs_b1 = take((size_t)kColsumBlocks * F);
   auto take_img = [&](size_t elems) {   // hi + lo images, bf16; 1 KB aligned (align_up keeps 256 B, images are multiples of 16 KB)
-    Workspace::Img im;
+    Img im;
     im.hi = reinterpret_cast<uint16_t*>(take((elems + 1) / 2));
     im.lo = reinterpret_cast<uint16_t*>(take((elems + 1) / 2));
     return im;
@@ -98,36 +91,10 @@ int check_cfg(const dr4sr_sasrec_cfg* c) {
   return DR4SR_OK;
 }
 
-using Img = Workspace::Img;
-bool use_tc(const GemmArgs& g, const Img& im, bool ln) {
-  return g_gemm_backend.load(std::memory_order_relaxed) == 0 && im.hi && tc::tc_supported(g.N, g.K, ln);
-}
-// y = LN(drop(A W^T + b) + res), rows complete inside a CTA (BN == D)
-int gemm_ln(GemmArgs& g, int D, const Img& im, cudaStream_t st) {
-  if (use_tc(g, im, true)) return tc::launch_gemm_tc<tc::TC_LN>(g, im.hi, im.lo, st);
-  if (D == 128) return launch_gemm<64, 128, true, true, true>(g, st);
-  return launch_gemm<64, 64, true, true, true>(g, st);
-}
-int gemm_nt(GemmArgs& g, const Img& im, cudaStream_t st) {
-  if (use_tc(g, im, false)) return tc::launch_gemm_tc<tc::TC_LINEAR>(g, im.hi, im.lo, st);
-  if (g.N >= 256) return launch_gemm<128, 128, true, true, false>(g, st);
-  if (g.N > 64) return launch_gemm<64, 128, true, true, false>(g, st);
-  return launch_gemm<64, 64, true, true, false>(g, st);
-}
-// backward-data: C = A W, the tensor-core path consumes the transposed image of W
-int gemm_nn(GemmArgs& g, const Img& im, cudaStream_t st) {
-  if (use_tc(g, im, false)) {
-    return g.epi == EPI_GELU_BWD ? tc::launch_gemm_tc<tc::TC_GELU_BWD>(g, im.hi, im.lo, st)
-                                 : tc::launch_gemm_tc<tc::TC_LINEAR>(g, im.hi, im.lo, st);
-  }
-  if (g.N >= 256) return launch_gemm<128, 128, true, false, false>(g, st);
-  if (g.N > 64) return launch_gemm<64, 128, true, false, false>(g, st);
-  return launch_gemm<64, 64, true, false, false>(g, st);
-}
 // bf16 hi/lo images of all layers' weights (one launch per <= 2 layers)
 int build_weight_images(const dr4sr_sasrec_cfg& c, const float* params, const Workspace& w, const LayerOffsets& lo, cudaStream_t st) {
   const int D = c.D, F = c.F;
-  if (g_gemm_backend.load(std::memory_order_relaxed) != 0) return DR4SR_OK;   // FFMA path needs none
+  if (!tc_enabled()) return DR4SR_OK;   // FFMA path needs none
   tc::ImageTable tab{};
   for (int l = 0; l < c.n_layer; ++l) {
     const float* lp = params + (size_t)c.L * D + (size_t)l * lo.total;
@@ -150,11 +117,6 @@ int build_weight_images(const dr4sr_sasrec_cfg& c, const float* params, const Wo
   }
   return DR4SR_OK;
 }
-int gemm_tn(GemmArgs& g, float* partial, cudaStream_t st) {   // C partials [kSplit][M*N]
-  g.C = partial; g.n_split = kSplit; g.split_stride = (int64_t)g.M * g.N; g.ldc = g.N;
-  return launch_gemm<64, 64, false, false, false>(g, st);
-}
-
 __global__ void __launch_bounds__(256) gather_last_kernel(const float* __restrict__ x, const int32_t* __restrict__ tok_off, int B,
                                                           int D, float* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,7 +291,7 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
     // weight gradients (reduction over the live tokens, kSplit partial tiles each):
     //   dW2[d,f]  = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]      dW1[f,d]  = sum_m dpre[m,f] * x1[m,d]
     //   dWo[n,k]  = sum_m (dz1*mask)[m,n] * attn[m,k]                     dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
-    if (g_gemm_backend.load(std::memory_order_relaxed) == 0 && tc::wgrad_supported(D, F) && tc::wgrad_supported(F, D) &&
+    if (tc_enabled() && tc::wgrad_supported(D, F) && tc::wgrad_supported(F, D) &&
         tc::wgrad_supported(D, D) && tc::wgrad_supported(3 * D, D)) {
       tc::WgradTable tab{};
       Dropout none; none.key = 0; none.thresh = 0; none.scale = 1.f;
@@ -393,8 +355,3 @@ extern "C" int dr4sr_linear_fwd(const float* x, const float* w, const float* bia
   return gemm_nt(g, Img{nullptr, nullptr}, as_stream(stream));
 }
 
-extern "C" int dr4sr_set_gemm_backend(int backend) {
-  if (backend != 0 && backend != 1) return DR4SR_EINVAL;
-  g_gemm_backend.store(backend);
-  return DR4SR_OK;
-}

@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import SasrecCfg, check
+from ._lib import FmlpCfg, SasrecCfg, check
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -146,6 +146,115 @@ class SASRecEngine:
                                         _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L, self.D, self.N,
                                         _p(table_grad), _p(pos_grad), _p(self._tg_ws), self._tg_ws.numel(), _stream()),
               'dr4sr_table_grad')
+
+
+@dataclass
+class _FmlpBuffers:
+    ws: torch.Tensor
+    q_last: torch.Tensor
+    dq: torch.Tensor
+    dz0: torch.Tensor
+    dscore: torch.Tensor
+    loss_pos: torch.Tensor
+    loss: torch.Tensor
+    ones: torch.Tensor
+    full: torch.Tensor
+    tok_off1: torch.Tensor
+    row_seq1: torch.Tensor
+    counts: torch.Tensor          # 1-D target problem: counts[1] = number of non-pad targets
+    tok_offD: torch.Tensor
+    row_seqD: torch.Tensor
+    countsD: torch.Tensor         # dense [B, L] problem
+    q_packed: torch.Tensor = None  # alias of q_last (engine-generic name used by the data-parallel hooks)
+
+
+class FMLPEngine:
+    """Kernels + workspaces of the FMLP encoder (reference model/fmlp.py:8-39, module/layers.py:740-808)."""
+
+    def __init__(self, num_items: int, embed_dim: int, max_seq_len: int, layer_num: int, dropout_rate: float, seed: int,
+                 device: torch.device, layer_norm_eps: float = 1e-12) -> None:
+        self.lib = _lib.lib()
+        self.N, self.D, self.L, self.n_layer = int(num_items), int(embed_dim), int(max_seq_len), int(layer_num)
+        self.p, self.eps, self.seed = float(dropout_rate), float(layer_norm_eps), int(seed) & (2 ** 64 - 1)
+        self.device = torch.device(device)
+        self.step = 0
+        self.fwd_token = 0
+        self._bufs: Dict[int, _FmlpBuffers] = {}
+        n = self.lib.dr4sr_fmlp_param_count(C.byref(self.cfg(1)))
+        if n == 0:
+            raise _lib.Dr4srError(f'unsupported FMLP shape D={self.D} L={self.L} layers={self.n_layer} (D in {{64,128}}, L == 50)')
+        self.param_count = int(n)
+        self._tg_ws = torch.empty(self.lib.dr4sr_table_grad_workspace_bytes(self.L, self.D), dtype=torch.uint8, device=self.device)
+
+    def cfg(self, B: int) -> FmlpCfg:
+        return FmlpCfg(B=B, L=self.L, D=self.D, n_layer=self.n_layer, N=self.N, dropout_p=self.p, ln_eps=self.eps,
+                       seed=self.seed, step=self.step)
+
+    def buffers(self, B: int) -> _FmlpBuffers:
+        b = self._bufs.get(B)
+        if b is None:
+            dev, T, D = self.device, B * self.L, self.D
+            f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+            ws_bytes = self.lib.dr4sr_fmlp_workspace_bytes(C.byref(self.cfg(B)))
+            b = _FmlpBuffers(
+                ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev), q_last=torch.zeros(B, D, **f32),
+                dq=torch.zeros(B, D, **f32), dz0=torch.zeros(T, D, **f32), dscore=torch.zeros(B, 2, **f32),
+                loss_pos=torch.zeros(B, **f32), loss=torch.zeros((), **f32),
+                ones=torch.ones(B, dtype=torch.int64, device=dev), full=torch.full((B,), self.L, dtype=torch.int64, device=dev),
+                tok_off1=torch.zeros(B + 1, **i32), row_seq1=torch.zeros(B, **i32), counts=torch.zeros(4, **i32),
+                tok_offD=torch.zeros(B + 1, **i32), row_seqD=torch.zeros(T, **i32), countsD=torch.zeros(4, **i32))
+            b.q_packed = b.q_last
+            check(self.lib.dr4sr_prep_batch(_p(b.full), None, B, self.L, 0, _p(b.tok_offD), _p(b.row_seqD), _p(b.countsD), _stream()),
+                  'dr4sr_prep_batch')
+            self._bufs[B] = b
+        return b
+
+    def prep(self, item_id: Optional[torch.Tensor], B: int) -> _FmlpBuffers:
+        b = self.buffers(B)
+        if item_id is not None:
+            item_id = _req(item_id, torch.int64, 'item_id')
+        check(self.lib.dr4sr_prep_batch(_p(b.ones), _p(item_id), B, 1, 1, _p(b.tok_off1), _p(b.row_seq1), _p(b.counts), _stream()),
+              'dr4sr_prep_batch')
+        return b
+
+    def encode(self, b: _FmlpBuffers, table: torch.Tensor, flat: torch.Tensor, in_ids: torch.Tensor, train: bool) -> torch.Tensor:
+        in_ids = _req(in_ids, torch.int64, 'in_item_id')
+        if in_ids.size(1) != self.L:
+            raise _lib.Dr4srError(f'FMLP expects sequences of length {self.L}, got {in_ids.size(1)}')
+        B = in_ids.size(0)
+        check(self.lib.dr4sr_fmlp_fwd(C.byref(self.cfg(B)), _p(_req(table, torch.float32, 'table')), _p(flat), _p(in_ids), _p(b.ws),
+                                      b.ws.numel(), 1 if train else 0, _p(b.q_last), _stream()), 'dr4sr_fmlp_fwd')
+        return b.q_last
+
+    def score_bce(self, b: _FmlpBuffers, table: torch.Tensor, item_id: torch.Tensor, neg_item: torch.Tensor, want_grad: bool,
+                  loss_weight: Optional[torch.Tensor] = None, upstream: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B = item_id.numel()
+        check(self.lib.dr4sr_score_bce(_p(b.q_last), _p(table), _p(_req(item_id, torch.int64, 'item_id')),
+                                       _p(_req(neg_item, torch.int64, 'neg_item')), _p(b.tok_off1), _p(b.row_seq1), _p(b.counts), B, 1,
+                                       self.D, _p(loss_weight), _p(upstream), _p(b.loss_pos), _p(b.dscore),
+                                       _p(b.dq) if want_grad else None, _stream()), 'dr4sr_score_bce')
+        return b.loss_pos
+
+    def reduce_loss(self, b: _FmlpBuffers) -> torch.Tensor:
+        check(self.lib.dr4sr_sum(_p(b.loss_pos), b.loss_pos.numel(), _p(b.loss), _stream()), 'dr4sr_sum')
+        return b.loss
+
+    def encode_bwd(self, b: _FmlpBuffers, table: torch.Tensor, flat: torch.Tensor, in_ids: torch.Tensor, grads_flat: torch.Tensor) -> None:
+        B = in_ids.size(0)
+        check(self.lib.dr4sr_fmlp_bwd(C.byref(self.cfg(B)), _p(table), _p(flat), _p(in_ids), _p(b.ws), b.ws.numel(), _p(b.dq),
+                                      _p(grads_flat), _p(b.dz0), _stream()), 'dr4sr_fmlp_bwd')
+
+    def table_grad(self, b: _FmlpBuffers, in_ids: torch.Tensor, item_id: torch.Tensor, neg_item: torch.Tensor,
+                   table_grad: torch.Tensor, pos_grad: torch.Tensor) -> None:
+        B = in_ids.size(0)
+        # targets / negatives: dE[item_id] += ds+ q, dE[neg] += ds- q   (1 slot per sequence)
+        check(self.lib.dr4sr_table_grad(None, _p(b.q_last), _p(b.dscore), _p(item_id), _p(item_id), _p(neg_item), _p(b.tok_off1),
+                                        _p(b.row_seq1), _p(b.counts), B, 1, self.D, self.N, _p(table_grad), None, None, 0, _stream()),
+              'dr4sr_table_grad')
+        # inputs: dE[in_id] += dz0 for every slot of the dense batch; dP[t] = sum_b dz0[b, t]
+        check(self.lib.dr4sr_table_grad(_p(b.dz0), None, None, _p(in_ids), None, None, _p(b.tok_offD), _p(b.row_seqD), _p(b.countsD),
+                                        B, self.L, self.D, self.N, _p(table_grad), _p(pos_grad), _p(self._tg_ws), self._tg_ws.numel(),
+                                        _stream()), 'dr4sr_table_grad')
 
 
 # ---- stateless wrappers ---------------------------------------------------------------------------

@@ -42,6 +42,35 @@ def normal_initialization(module: nn.Module, initial_range: float = 0.02) -> Non
         module.weight.data.fill_(1.0)
 
 
+class _TrainStep(torch.autograd.Function):
+    """training_step as one autograd node.  forward = the model's forward + loss kernels, backward = its
+    backward kernels; gradients are written by the kernels into the model's flat buffers and published as
+    ``.grad`` -- nothing flows back through autograd edges."""
+
+    @staticmethod
+    def forward(ctx, table, model, batch, reduce, return_query):
+        model._check_flat()
+        loss, query, state = model._step_forward(batch, reduce, return_query)
+        eng = model.engine
+        eng.fwd_token += 1
+        ctx.model, ctx.state, ctx.reduce, ctx.token = model, state, reduce, eng.fwd_token
+        ctx.set_materialize_grads(False)
+        return (loss, query) if return_query else loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dloss, dquery=None):
+        model = ctx.model
+        if ctx.token != model.engine.fwd_token:
+            raise RuntimeError('dr4sr_b200: backward() of a stale training_step (the engine keeps the activations of the '
+                               'most recent forward only)')
+        if dloss is None:
+            raise RuntimeError('dr4sr_b200: training_step loss received no gradient')
+        model._step_backward(ctx.state, ctx.reduce, dloss.contiguous(), dquery)
+        model._publish_grads()
+        return None, None, None, None, None
+
+
 class BaseModel(nn.Module):
     def __init__(self, config: Dict, dataset_list: List) -> None:
         super().__init__()
@@ -180,8 +209,16 @@ class BaseModel(nn.Module):
             grp.dirty = True
         return self._table_grad
 
-    def training_step(self, batch, reduce=True, return_query=False):
+    def _step_forward(self, batch, reduce, return_query):
+        """-> (loss tensor, query or None, opaque state for _step_backward)"""
         raise NotImplementedError
+
+    def _step_backward(self, state, reduce, dloss, dquery) -> None:
+        raise NotImplementedError
+
+    def training_step(self, batch, reduce=True, return_query=False):
+        """Reference model/basemodel.py:204-214: loss (and query) of one batch; `.backward()` fills `.grad`."""
+        return _TrainStep.apply(self.item_embedding.weight, self, batch, reduce, return_query)
 
     def _item_dead(self, domain: str) -> torch.Tensor:
         """u8 mask of ids outside the eval domain (always id 0), built once per domain and kept on

@@ -45,66 +45,6 @@ class SASRecQueryEncoder(nn.Module):
         raise RuntimeError('SASRecQueryEncoder is a parameter container here; call SASRec.forward(batch)')
 
 
-class _EncodeScoreBCE(torch.autograd.Function):
-    """training_step as one autograd node: forward = encoder + sampled BCE kernels, backward = BCE
-    backward + encoder backward + table scatter-add.  Gradients are written by the kernels into the
-    model's flat buffers and published as ``.grad``; nothing flows back through autograd edges."""
-
-    @staticmethod
-    def forward(ctx, table, model, batch, reduce, return_query):
-        eng = model.engine
-        model._check_flat()
-        in_ids, item_id, neg = batch['in_' + model.fiid], batch[model.fiid], batch['neg_item']
-        b = eng.prep(batch['seqlen'], item_id)
-        model._dp_sum(b.counts[1:2])          # data parallel: normalise by the global number of valid targets
-        if model.training:
-            eng.step += 1
-        q_dense = None
-        if return_query:
-            q_dense = torch.empty(in_ids.size(0), eng.L, eng.D, dtype=torch.float32, device=in_ids.device)
-        eng.encode(b, table, model._flat, in_ids, train=model.training, q_dense=q_dense)
-        eng.score_bce(b, table, item_id, neg.view(item_id.shape), want_grad=False)
-        loss = eng.reduce_loss(b).clone() if reduce else b.loss_pos.clone()
-        if reduce:
-            model._dp_sum(loss)
-        ctx.model, ctx.bufs, ctx.reduce = model, b, reduce
-        ctx.ids = (in_ids, item_id, neg.view(item_id.shape))
-        eng.fwd_token += 1
-        ctx.token = eng.fwd_token
-        ctx.set_materialize_grads(False)
-        if return_query:
-            return loss, q_dense
-        return loss
-
-    @staticmethod
-    @torch.autograd.function.once_differentiable
-    def backward(ctx, dloss, dquery=None):
-        model, b = ctx.model, ctx.bufs
-        eng = model.engine
-        if ctx.token != eng.fwd_token:
-            raise RuntimeError('dr4sr_b200: backward() of a stale training_step (the engine keeps the activations of '
-                               'the most recent forward per batch size only)')
-        in_ids, item_id, neg = ctx.ids
-        table = model.item_embedding.weight.data
-        if dloss is None:
-            raise RuntimeError('dr4sr_b200: training_step loss received no gradient')
-        dloss = dloss.contiguous()
-        if ctx.reduce:
-            eng.score_bce(b, table, item_id, neg, want_grad=True, upstream=dloss)
-        else:
-            eng.score_bce(b, table, item_id, neg, want_grad=True, loss_weight=dloss)
-        if dquery is not None:
-            valid = torch.arange(eng.L, device=dquery.device).view(1, -1) < batch_len(b)
-            n = int(b.counts[0])
-            b.dq[:n] += dquery[valid]
-        eng.encode_bwd(b, table, model._flat, in_ids, model._flat_grad)
-        tg = model._table_grad_buffer()
-        eng.table_grad(b, in_ids, item_id, neg, tg, model._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
-        model._dp_sum(model._flat_grad, tg)
-        model._publish_grads()
-        return None, None, None, None, None
-
-
 def batch_len(b) -> torch.Tensor:
     return (b.tok_off[1:] - b.tok_off[:-1]).view(-1, 1)
 
@@ -144,7 +84,42 @@ class SASRec(BaseModel):
         eng.encode(b, table, self._flat, in_ids, train=False, want_last=True)
         return b.q_last.clone()
 
+    def _step_forward(self, batch, reduce, return_query):
+        eng = self.engine
+        table = self.item_embedding.weight.data
+        in_ids, item_id, neg = batch['in_' + self.fiid], batch[self.fiid], batch['neg_item']
+        neg = neg.view(item_id.shape)
+        b = eng.prep(batch['seqlen'], item_id)
+        self._dp_sum(b.counts[1:2])           # data parallel: normalise by the global number of valid targets
+        if self.training:
+            eng.step += 1
+        q_dense = None
+        if return_query:
+            q_dense = torch.empty(in_ids.size(0), eng.L, eng.D, dtype=torch.float32, device=in_ids.device)
+        eng.encode(b, table, self._flat, in_ids, train=self.training, q_dense=q_dense)
+        eng.score_bce(b, table, item_id, neg, want_grad=False)
+        loss = eng.reduce_loss(b).clone() if reduce else b.loss_pos.clone()
+        if reduce:
+            self._dp_sum(loss)
+        return loss, q_dense, (b, in_ids, item_id, neg)
+
+    def _step_backward(self, state, reduce, dloss, dquery) -> None:
+        eng = self.engine
+        b, in_ids, item_id, neg = state
+        table = self.item_embedding.weight.data
+        if reduce:
+            eng.score_bce(b, table, item_id, neg, want_grad=True, upstream=dloss)
+        else:
+            eng.score_bce(b, table, item_id, neg, want_grad=True, loss_weight=dloss)
+        if dquery is not None:
+            valid = torch.arange(eng.L, device=dquery.device).view(1, -1) < batch_len(b)
+            b.dq[: int(b.counts[0])] += dquery[valid]
+        eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad)
+        tg = self._table_grad_buffer()
+        eng.table_grad(b, in_ids, item_id, neg, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
+        self._dp_sum(self._flat_grad, tg)
+
     def training_step(self, batch, reduce=True, return_query=False, align=False):
         if align:
             raise NotImplementedError('the align branch (model/sasrec.py:111-119) has no caller in the reference')
-        return _EncodeScoreBCE.apply(self.item_embedding.weight, self, batch, reduce, return_query)
+        return super().training_step(batch, reduce, return_query)

@@ -120,6 +120,34 @@ DR4SR_API int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* cfg, const float* table, 
                      float* grads, float* dx0_packed, dr4sr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * FMLP encoder, replaces FMLP.add_position_embedding + FMLPEncoder (model/fmlp.py:18-39,
+ * module/layers.py:740-808): x0 = drop(LN(E[ids] + P)); per layer y = LN(drop(filter(x)) + x),
+ * z = LN(drop(W2 gelu(W1 y + b1) + b2) + y) with inner width 4D; query = last position.  Inputs are
+ * pre-padded, every slot is live (dense [B, L, D]); L must be 50 (the reference hard-codes it).
+ * Flat parameter layout (state_dict order): position_embeddings [L,D], LayerNorm.weight [D], .bias [D];
+ * per layer: filterlayer.complex_weight [L/2+1, D, 2], filterlayer.LayerNorm.weight/.bias [D],
+ * intermediate.dense_1.weight [4D,D], .bias [4D], dense_2.weight [D,4D], .bias [D],
+ * intermediate.LayerNorm.weight/.bias [D].
+ * fwd: q_last [B,D] out.  bwd: dq_last [B,D] in; grads (flat, overwritten; the position block is left
+ * to dr4sr_table_grad's pos_grad); dz0_dense [B*L, D] out = gradient w.r.t. E[ids] + P per slot.
+ */
+typedef struct {
+  int32_t B, L, D, n_layer;
+  int64_t N;
+  float dropout_p;
+  float ln_eps;
+  uint64_t seed;
+  uint64_t step;
+} dr4sr_fmlp_cfg;
+DR4SR_API size_t dr4sr_fmlp_param_count(const dr4sr_fmlp_cfg* cfg);
+DR4SR_API size_t dr4sr_fmlp_workspace_bytes(const dr4sr_fmlp_cfg* cfg);
+DR4SR_API int dr4sr_fmlp_fwd(const dr4sr_fmlp_cfg* cfg, const float* table, const float* params, const int64_t* in_item_id,
+                   void* ws, size_t ws_bytes, int32_t train, float* q_last, dr4sr_stream_t stream);
+DR4SR_API int dr4sr_fmlp_bwd(const dr4sr_fmlp_cfg* cfg, const float* table, const float* params, const int64_t* in_item_id,
+                   void* ws, size_t ws_bytes, const float* dq_last, float* grads, float* dz0_dense,
+                   dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Sampled scoring + BCE, replaces BaseModel.training_step (model/basemodel.py:205-210) and
  * BinaryCrossEntropyLoss.forward (model/loss_func.py:9-35) with one negative per slot, forward and
  * backward in one pass:
