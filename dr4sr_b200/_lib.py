@@ -23,6 +23,12 @@ class FmlpCfg(C.Structure):
                 ('ln_eps', c_f32), ('seed', c_u64), ('step', c_u64)]
 
 
+class GruCfg(C.Structure):
+    """Mirror of dr4sr_gru_cfg."""
+    _fields_ = [('B', c_i32), ('L', c_i32), ('D', c_i32), ('H', c_i32), ('n_layer', c_i32), ('N', c_i64), ('dropout_p', c_f32),
+                ('seed', c_u64), ('step', c_u64)]
+
+
 class SasrecCfg(C.Structure):
     """Mirror of dr4sr_sasrec_cfg."""
     _fields_ = [('B', c_i32), ('L', c_i32), ('D', c_i32), ('F', c_i32), ('n_head', c_i32), ('n_layer', c_i32),
@@ -43,6 +49,11 @@ SIGNATURES = {
     'dr4sr_sasrec_workspace_bytes': (c_sz, [C.POINTER(SasrecCfg)]),
     'dr4sr_sasrec_fwd': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p, c_p, c_p]),
     'dr4sr_sasrec_bwd': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
+    'dr4sr_unpack_rows': (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
+    'dr4sr_gru_param_count': (c_sz, [C.POINTER(GruCfg)]),
+    'dr4sr_gru_workspace_bytes': (c_sz, [C.POINTER(GruCfg)]),
+    'dr4sr_gru_fwd': (c_i32, [C.POINTER(GruCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p, c_p, c_p]),
+    'dr4sr_gru_bwd': (c_i32, [C.POINTER(GruCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
     'dr4sr_fmlp_param_count': (c_sz, [C.POINTER(FmlpCfg)]),
     'dr4sr_fmlp_workspace_bytes': (c_sz, [C.POINTER(FmlpCfg)]),
     'dr4sr_fmlp_fwd': (c_i32, [C.POINTER(FmlpCfg), c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p]),

@@ -149,6 +149,25 @@ __global__ void __launch_bounds__(256) unpack_dense_kernel(const float* __restri
 
 using namespace dr4sr;
 
+extern "C" int dr4sr_unpack_rows(const float* x_packed, const int32_t* tok_off, int32_t B, int32_t L, int32_t D, float* q_last,
+                                 float* q_dense, dr4sr_stream_t stream) {
+  if (!x_packed || !tok_off || D % 4) return DR4SR_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  if (q_last) {
+    ProfScope prof("gather_last", st);
+    gather_last_kernel<<<ceil_div(B, 8), 256, 0, st>>>(x_packed, tok_off, B, D, q_last);
+    DR4SR_LAUNCH_CHECK("gather_last_kernel");
+  }
+  if (q_dense) {
+    const int T = B * L;
+    const int blocks = ceil_div(T, 8) < 8 * kNumSMs ? ceil_div(T, 8) : 8 * kNumSMs;
+    ProfScope prof("unpack_dense", st);
+    unpack_dense_kernel<<<blocks, 256, 0, st>>>(x_packed, tok_off, B, L, D, q_dense);
+    DR4SR_LAUNCH_CHECK("unpack_dense_kernel");
+  }
+  return DR4SR_OK;
+}
+
 extern "C" size_t dr4sr_sasrec_param_count(const dr4sr_sasrec_cfg* c) {
   if (check_cfg(c) != DR4SR_OK) return 0;
   return (size_t)c->L * c->D + (size_t)c->n_layer * layer_offsets(c->D, c->F).total;
@@ -215,17 +234,7 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
     }
     x = x2;
   }
-  if (q_last) {
-    ProfScope prof("gather_last", st);
-    gather_last_kernel<<<ceil_div(c->B, 8), 256, 0, st>>>(x, tok_off, c->B, D, q_last);
-    DR4SR_LAUNCH_CHECK("gather_last_kernel");
-  }
-  if (q_dense) {
-    const int blocks = ceil_div(T, 8) < 8 * kNumSMs ? ceil_div(T, 8) : 8 * kNumSMs;
-    ProfScope prof("unpack_dense", st);
-    unpack_dense_kernel<<<blocks, 256, 0, st>>>(x, tok_off, c->B, c->L, D, q_dense);
-    DR4SR_LAUNCH_CHECK("unpack_dense_kernel");
-  }
+  DR4SR_TRY(dr4sr_unpack_rows(x, tok_off, c->B, c->L, D, q_last, q_dense, stream));
   return DR4SR_OK;
 }
 

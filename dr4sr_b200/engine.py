@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import FmlpCfg, SasrecCfg, check
+from ._lib import FmlpCfg, GruCfg, SasrecCfg, check
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -60,10 +60,15 @@ class SASRecEngine:
         self.step = 0                       # dropout stream counter (bumped per training forward)
         self.fwd_token = 0                  # identifies whose activations the workspace holds
         self._bufs: Dict[int, _Buffers] = {}
-        n = self.lib.dr4sr_sasrec_param_count(C.byref(self.cfg(1)))
+        self._fn_count, self._fn_ws = self.lib.dr4sr_sasrec_param_count, self.lib.dr4sr_sasrec_workspace_bytes
+        self._fn_fwd, self._fn_bwd, self._name = self.lib.dr4sr_sasrec_fwd, self.lib.dr4sr_sasrec_bwd, 'dr4sr_sasrec'
+        self._finish_init(f'unsupported SASRec shape D={self.D} F={self.F} L={self.L} heads={self.H} layers={self.n_layer} '
+                          f'(D in {{64,128}}, F % 64 == 0, L <= 64)')
+
+    def _finish_init(self, why: str) -> None:
+        n = self._fn_count(C.byref(self.cfg(1)))
         if n == 0:
-            raise _lib.Dr4srError(f'unsupported SASRec shape D={self.D} F={self.F} L={self.L} heads={self.H} '
-                                  f'layers={self.n_layer} (D in {{64,128}}, F % 64 == 0, L <= 64)')
+            raise _lib.Dr4srError(why)
         self.param_count = int(n)
         self._tg_ws = torch.empty(self.lib.dr4sr_table_grad_workspace_bytes(self.L, self.D), dtype=torch.uint8, device=self.device)
 
@@ -76,7 +81,7 @@ class SASRecEngine:
         b = self._bufs.get(B)
         if b is None:
             dev, T, D = self.device, B * self.L, self.D
-            ws_bytes = self.lib.dr4sr_sasrec_workspace_bytes(C.byref(self.cfg(B)))
+            ws_bytes = self._fn_ws(C.byref(self.cfg(B)))
             f32 = dict(dtype=torch.float32, device=dev)
             b = _Buffers(
                 tok_off=torch.zeros(B + 1, dtype=torch.int32, device=dev),
@@ -107,10 +112,10 @@ class SASRecEngine:
         in_ids = _req(in_ids, torch.int64, 'in_item_id')
         B = in_ids.size(0)
         cfg = self.cfg(B)
-        check(self.lib.dr4sr_sasrec_fwd(C.byref(cfg), _p(_req(table, torch.float32, 'table')),
+        check(self._fn_fwd(C.byref(cfg), _p(_req(table, torch.float32, 'table')),
                                         _p(_req(flat, torch.float32, 'params')), _p(in_ids), _p(b.tok_off), _p(b.row_seq),
                                         _p(b.counts), _p(b.ws), b.ws.numel(), 1 if train else 0, _p(b.q_packed),
-                                        _p(b.q_last) if want_last else None, _p(q_dense), _stream()), 'dr4sr_sasrec_fwd')
+                                        _p(b.q_last) if want_last else None, _p(q_dense), _stream()), self._name + '_fwd')
         return b.q_packed
 
     def score_bce(self, b: _Buffers, table: torch.Tensor, item_id: torch.Tensor, neg_item: torch.Tensor,
@@ -135,8 +140,8 @@ class SASRecEngine:
         B = in_ids.size(0)
         cfg = self.cfg(B)
         dq = b.dq if dq is None else dq
-        check(self.lib.dr4sr_sasrec_bwd(C.byref(cfg), _p(table), _p(flat), _p(in_ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
-                                        _p(b.ws), b.ws.numel(), _p(dq), _p(grads_flat), _p(b.dx0), _stream()), 'dr4sr_sasrec_bwd')
+        check(self._fn_bwd(C.byref(cfg), _p(table), _p(flat), _p(in_ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
+                                        _p(b.ws), b.ws.numel(), _p(dq), _p(grads_flat), _p(b.dx0), _stream()), self._name + '_bwd')
         return b.dx0
 
     def table_grad(self, b: _Buffers, in_ids: torch.Tensor, item_id: Optional[torch.Tensor], neg_item: Optional[torch.Tensor],
@@ -146,6 +151,30 @@ class SASRecEngine:
                                         _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L, self.D, self.N,
                                         _p(table_grad), _p(pos_grad), _p(self._tg_ws), self._tg_ws.numel(), _stream()),
               'dr4sr_table_grad')
+
+
+class GRUEngine(SASRecEngine):
+    """Kernels + workspaces of the GRU4Rec encoder (reference model/gru4rec.py:12-22); same packed-row
+    machinery, scoring, scatter and buffers as the SASRec engine."""
+
+    def __init__(self, num_items: int, embed_dim: int, max_seq_len: int, hidden_size: int, layer_num: int, dropout_rate: float,
+                 seed: int, device: torch.device) -> None:
+        self.lib = _lib.lib()
+        self.N, self.D, self.L, self.Hh = int(num_items), int(embed_dim), int(max_seq_len), int(hidden_size)
+        self.n_layer, self.p, self.seed = int(layer_num), float(dropout_rate), int(seed) & (2 ** 64 - 1)
+        self.device = torch.device(device)
+        self.step = 0
+        self.fwd_token = 0
+        self._bufs = {}
+        self._fn_count, self._fn_ws = self.lib.dr4sr_gru_param_count, self.lib.dr4sr_gru_workspace_bytes
+        self._fn_fwd, self._fn_bwd, self._name = self.lib.dr4sr_gru_fwd, self.lib.dr4sr_gru_bwd, 'dr4sr_gru'
+        self._finish_init(f'unsupported GRU4Rec shape D={self.D} H={self.Hh} layers={self.n_layer} '
+                          f'(D in {{64,128}}, H in {{64,128,256}}, layers <= 4)')
+        self._tg_ws = torch.empty(self.lib.dr4sr_table_grad_workspace_bytes(self.L, self.D), dtype=torch.uint8, device=self.device)
+
+    def cfg(self, B: int, step: Optional[int] = None) -> GruCfg:
+        return GruCfg(B=B, L=self.L, D=self.D, H=self.Hh, n_layer=self.n_layer, N=self.N, dropout_p=self.p, seed=self.seed,
+                      step=self.step if step is None else step)
 
 
 @dataclass

@@ -1,0 +1,63 @@
+"""GRU4Rec on libdr4sr (reference model/gru4rec.py:9-36)."""
+from __future__ import annotations
+
+import torch
+
+from .. import engine as _engine
+from ..module.layers import GRULayer, LambdaLayer, SeqPoolingLayer, VStackLayer
+from .basemodel import BaseModel
+from .sasrec import SASRec
+
+
+class GRU4Rec(BaseModel):
+    def __init__(self, config, dataset_list) -> None:
+        super().__init__(config, dataset_list)
+        m = self.config['model']
+        # same nesting as the reference => same state_dict keys (query_encoder.0.{1,3}.*, query_encoder.1.*)
+        self.query_encoder = VStackLayer(
+            torch.nn.Sequential(
+                LambdaLayer(lambda x: x['in_' + self.fiid]),
+                self.item_embedding,
+                torch.nn.Dropout(m['dropout_rate']),
+                GRULayer(self.embed_dim, m['hidden_size'], m['layer_num']),
+            ),
+            torch.nn.Linear(m['hidden_size'], self.embed_dim))
+        self.training_pooling_layer = SeqPoolingLayer(pooling_type='origin')
+        self.eval_pooling_layer = SeqPoolingLayer(pooling_type='last')
+
+    def _build_engine(self) -> None:
+        m = self.config['model']
+        self.engine = _engine.GRUEngine(self.num_items, self.embed_dim, self.max_seq_len, m['hidden_size'], m['layer_num'],
+                                        m['dropout_rate'], self.config['train'].get('seed', 0), self.item_embedding.weight.device)
+
+    def _flat_parameters(self):
+        gru = self.query_encoder[0][3].gru
+        out = []
+        for l in range(gru.num_layers):
+            out += [getattr(gru, f'weight_ih_l{l}'), getattr(gru, f'weight_hh_l{l}')]
+        lin = self.query_encoder[1]
+        return out + [lin.weight, lin.bias]
+
+    # forward / training-step kernels are the packed-row flow of SASRec with the GRU engine underneath
+    forward = SASRec.forward
+    _step_forward = SASRec._step_forward
+
+    def _step_backward(self, state, reduce, dloss, dquery) -> None:
+        eng = self.engine
+        b, in_ids, item_id, neg = state
+        table = self.item_embedding.weight.data
+        if reduce:
+            eng.score_bce(b, table, item_id, neg, want_grad=True, upstream=dloss)
+        else:
+            eng.score_bce(b, table, item_id, neg, want_grad=True, loss_weight=dloss)
+        if dquery is not None:
+            from .sasrec import batch_len
+            valid = torch.arange(eng.L, device=dquery.device).view(1, -1) < batch_len(b)
+            b.dq[: int(b.counts[0])] += dquery[valid]
+        eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad)
+        tg = self._table_grad_buffer()
+        eng.table_grad(b, in_ids, item_id, neg, tg, None)          # no positional table in GRU4Rec
+        self._dp_sum(self._flat_grad, tg)
+
+    def training_step(self, batch, reduce=True, return_query=False, align=False):
+        return super().training_step(batch, reduce, return_query)

@@ -119,6 +119,36 @@ DR4SR_API int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* cfg, const float* table, 
                      const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed,
                      float* grads, float* dx0_packed, dr4sr_stream_t stream);
 
+/* Packed rows -> the reference's layouts: q_last [B,D] = row seqlen-1 of every sequence ('last' pooling,
+ * module/layers.py:69-73), q_dense [B,L,D] = rows scattered back with zeros at t >= seqlen ('origin'
+ * pooling, module/layers.py:41-50).  Either output may be NULL. */
+DR4SR_API int dr4sr_unpack_rows(const float* x_packed, const int32_t* tok_off, int32_t B, int32_t L, int32_t D, float* q_last,
+                      float* q_dense, dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GRU4Rec encoder, replaces GRU4Rec.query_encoder (model/gru4rec.py:12-22, module/layers.py:117-136):
+ * x0 = drop(E[ids]); n_layer bias-free GRU layers (D -> H -> H, h0 = 0, gate rows [r; z; n]);
+ * y = W_out h + b_out per slot; pooling as for SASRec.  Packed rows (pads are trailing).
+ * Flat parameter layout (state_dict order): per layer gru.weight_ih_l{k} [3H, in], gru.weight_hh_l{k}
+ * [3H, H]; then linear.weight [D, H], linear.bias [D].  H in {64, 128, 256}, D in {64, 128}.
+ * Same calling convention as dr4sr_sasrec_fwd / dr4sr_sasrec_bwd.
+ */
+typedef struct {
+  int32_t B, L, D, H, n_layer;
+  int64_t N;
+  float dropout_p;
+  uint64_t seed;
+  uint64_t step;
+} dr4sr_gru_cfg;
+DR4SR_API size_t dr4sr_gru_param_count(const dr4sr_gru_cfg* cfg);
+DR4SR_API size_t dr4sr_gru_workspace_bytes(const dr4sr_gru_cfg* cfg);
+DR4SR_API int dr4sr_gru_fwd(const dr4sr_gru_cfg* cfg, const float* table, const float* params, const int64_t* in_item_id,
+                  const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, void* ws, size_t ws_bytes,
+                  int32_t train, float* q_packed, float* q_last, float* q_dense, dr4sr_stream_t stream);
+DR4SR_API int dr4sr_gru_bwd(const dr4sr_gru_cfg* cfg, const float* table, const float* params, const int64_t* in_item_id,
+                  const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, void* ws, size_t ws_bytes,
+                  float* dq_packed, float* grads, float* dx0_packed, dr4sr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * FMLP encoder, replaces FMLP.add_position_embedding + FMLPEncoder (model/fmlp.py:18-39,
  * module/layers.py:740-808): x0 = drop(LN(E[ids] + P)); per layer y = LN(drop(filter(x)) + x),

@@ -1,0 +1,107 @@
+"""GPU parity tests of the GRU4Rec path (embedding dropout, input-projection GEMMs, cluster-resident
+recurrence forward / backward-through-time, output projection) against the golden vectors of the
+unmodified reference and the CPU oracle."""
+import pytest
+import torch
+
+from oracle import dr4sr_oracle as orc
+from tests.helpers import load_fixture, rel_err, load_params
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+TOL = {'tc': dict(fwd=1e-4, loss=1e-4, grad=1e-3, adam=1e-4), 'ffma': dict(fwd=1e-5, loss=1e-5, grad=1e-4, adam=2e-5)}
+
+
+@pytest.fixture(params=['tc', 'ffma'], autouse=True)
+def backend(request):
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dr4sr_b200 import _lib
+    _lib.check(_lib.lib().dr4sr_set_gemm_backend(0 if request.param == 'tc' else 1), 'set_gemm_backend')
+    yield request.param
+    _lib.lib().dr4sr_set_gemm_backend(0)
+
+
+def make_model(N, D, H=256, layers=2, p=0.0, wd=0.0, seed=2023):
+    from dr4sr_b200.model.gru4rec import GRU4Rec
+    from dr4sr_b200.utils.config import default_config, SyntheticCatalog
+    cfg = default_config('GRU4Rec', model__embed_dim=D, model__hidden_size=H, model__layer_num=layers, model__dropout_rate=p,
+                         train__device=DEV, train__weight_decay=wd, train__seed=seed)
+    torch.manual_seed(seed)
+    m = GRU4Rec(cfg, [SyntheticCatalog(N)] * 3)
+    m._init_model()
+    return m
+
+
+def to_dev(batch):
+    return {k: v.to(DEV) for k, v in batch.items()}
+
+
+@pytest.mark.parametrize('name', ['gru4rec_d64.npz', 'gru4rec_d128.npz'])
+def test_gru4rec_matches_reference_golden(name, backend):
+    tol = TOL[backend]
+    fx = load_fixture(name)
+    N, D = fx['param']['item_embedding.weight'].shape
+    H = fx['param']['query_encoder.0.3.gru.weight_hh_l0'].shape[1]
+    m = make_model(N, D, H, wd=float(fx['adam']['weight_decay'])).train()
+    load_params(m, {k: v.to(DEV) for k, v in fx['param'].items()})
+    batch = to_dev(fx['batch'])
+    q = m.forward(batch).cpu()
+    assert rel_err(q, fx['train']['query']) < tol['fwd']
+    m.optimizer.zero_grad()
+    loss = m.training_step(batch)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(fx['train']['loss'])) / abs(float(fx['train']['loss'])) < tol['loss']
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        assert rel_err(p.grad.cpu(), fx['grad'][k]) < tol['grad'], k
+    # three Adam steps with the reference's weight decay (configs/gru4rec.yaml: 1e-4)
+    load_params(m, {k: v.to(DEV) for k, v in fx['param'].items()})
+    for want in fx['adam']['losses'].tolist():
+        m.optimizer.zero_grad()
+        loss = m.training_step(batch)
+        loss.backward()
+        m.optimizer.step()
+        assert abs(float(loss.detach()) - want) / want < tol['loss']
+    for k, p in m.named_parameters():
+        assert float((p.detach().cpu() - fx['param_after'][k]).abs().max()) < tol['adam'], k
+    m.eval()
+    ev = to_dev(fx['evalbatch'])
+    q = m.forward(ev).cpu()
+    assert rel_err(q, fx['eval']['query']) < tol['fwd']
+
+
+@pytest.mark.parametrize('B,D,H,N,minlen', [(100, 128, 256, 3000, 1), (9, 64, 256, 500, 50), (70, 64, 128, 400, 1)])
+def test_gru4rec_training_step_matches_oracle(B, D, H, N, minlen, backend):
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    tol = TOL[backend]
+    m = make_model(N, D, H).train()
+    o = orc.OracleGRU4Rec(N, embed_dim=D, hidden_size=H, dropout_rate=0.0).train()
+    o.load_state_dict({k: v.detach().cpu() for k, v in m.state_dict().items()})
+    batch = synthetic_batch(B, 50, N, seed=B + H, min_len=minlen)
+    lo, qo = o.training_step(batch, return_query=True)
+    lo.backward()
+    loss, q = m.training_step(to_dev(batch), return_query=True)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(lo.detach())) / abs(float(lo.detach())) < tol['loss']
+    assert rel_err(q.detach().cpu(), qo.detach()) < tol['fwd']
+    for (k, p), (_, po) in zip(m.named_parameters(), o.named_parameters()):
+        want = po.grad if po.grad is not None else torch.zeros_like(po)
+        assert rel_err(p.grad.cpu(), want) < tol['grad'], k
+
+
+def test_gru_explicit_spec_vs_kernels(backend):
+    """Hidden states against the elementary-algebra GRU spec."""
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    N, D, H = 300, 64, 64
+    m = make_model(N, D, H).eval()
+    batch = synthetic_batch(11, 50, N, seed=8)
+    gru = m.query_encoder[0][3].gru
+    lin = m.query_encoder[1]
+    x = m.item_embedding.weight.detach().cpu()[batch['in_item_id']]
+    hs = orc.gru_explicit(x, [gru.weight_ih_l0.detach().cpu(), gru.weight_ih_l1.detach().cpu()],
+                          [gru.weight_hh_l0.detach().cpu(), gru.weight_hh_l1.detach().cpu()])
+    y = hs @ lin.weight.detach().cpu().T + lin.bias.detach().cpu()
+    want = orc.pool_last(y, batch['seqlen'])
+    q = m.forward(to_dev(batch)).cpu()
+    assert rel_err(q, want) < TOL[backend]['fwd']
