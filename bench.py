@@ -160,6 +160,7 @@ def kernel_work(name: str, T: int, B: int, c: dict):
             'gemm_ffn2_ln': 2 * T * D * F, 'gemm_bwd_dpre': 2 * T * D * F, 'gemm_bwd_dx1': 2 * T * D * F,
             'gemm_bwd_dattn': 2 * T * D * D, 'gemm_bwd_dx': 2 * T * 3 * D * D, 'gemm_wgrad_w2': 2 * T * D * F,
             'gemm_wgrad_w1': 2 * T * D * F, 'gemm_wgrad_out': 2 * T * D * D, 'gemm_wgrad_in': 2 * T * 3 * D * D}
+    gemm['wgrad_tc'] = 2 * T * (3 * D * D + D * D + 2 * D * F)
     if name in gemm:
         return dict(bound='tensor', work=gemm[name], unit='TFLOP/s')
     byts = {'adam_table': 24 * N * D, 'embed_fwd': 2 * U, 'score_bce': 4 * U, 'table_grad_scatter': 5 * U, 'ln_bwd': 3 * U,
@@ -177,6 +178,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--model', default='SASRec', choices=['SASRec', 'GRU4Rec', 'FMLP'],
+                    help='SASRec = BASELINE configs[1] (the headline); GRU4Rec / FMLP = configs[2]')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -184,7 +187,6 @@ def main():
     import torch.distributed as dist
     from dr4sr_b200 import _lib
     from dr4sr_b200.data.synthetic import synthetic_batch
-    from dr4sr_b200.model.sasrec import SASRec
     from dr4sr_b200.utils.config import SyntheticCatalog, default_config
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -201,11 +203,25 @@ def main():
 
     c = CFG2
     B, L, N = c['batch_per_gpu'], c['max_seq_len'], c['num_items']
-    cfg = default_config('SASRec', model__embed_dim=c['embed_dim'], model__hidden_size=c['hidden_size'],
-                         model__layer_num=c['layer_num'], model__head_num=c['head_num'], model__dropout_rate=c['dropout_rate'],
-                         train__device=str(dev), train__batch_size=B)
+    if args.model == 'SASRec':
+        from dr4sr_b200.model.sasrec import SASRec as Model
+        cfg = default_config('SASRec', model__embed_dim=c['embed_dim'], model__hidden_size=c['hidden_size'],
+                             model__layer_num=c['layer_num'], model__head_num=c['head_num'],
+                             model__dropout_rate=c['dropout_rate'], train__device=str(dev), train__batch_size=B)
+        layout, workload = 'post', ('SASRec synthetic |items|=100K d=128 L=50 batch=1024 per GPU, sampled BCE, dropout 0.5, dense Adam '
+                                    '(BASELINE configs[1])')
+    elif args.model == 'GRU4Rec':
+        from dr4sr_b200.model.gru4rec import GRU4Rec as Model
+        cfg = default_config('GRU4Rec', model__embed_dim=c['embed_dim'], train__device=str(dev), train__batch_size=B)
+        layout, workload = 'post', ('GRU4Rec synthetic |items|=100K d=128 hidden=256 L=50 batch=1024 per GPU, sampled BCE, dropout 0.2, '
+                                    'dense Adam wd 1e-4 (BASELINE configs[2])')
+    else:
+        from dr4sr_b200.model.fmlp import FMLP as Model
+        cfg = default_config('FMLP', model__embed_dim=c['embed_dim'], train__device=str(dev), train__batch_size=B)
+        layout, workload = 'pre', ('FMLP synthetic |items|=100K d=128 L=50 batch=1024 per GPU, pre-padded, single target, dropout 0.5, '
+                                   'dense Adam (BASELINE configs[2])')
     torch.manual_seed(2023)
-    model = SASRec(cfg, [SyntheticCatalog(N)] * 3)
+    model = Model(cfg, [SyntheticCatalog(N)] * 3)
     model._init_model()
     if world > 1:
         model.enable_data_parallel(dist.group.WORLD)
@@ -213,11 +229,11 @@ def main():
     lib = _lib.lib()
 
     P = 8   # distinct batches cycled, per rank
-    host = [synthetic_batch(B, L, N, seed=1000 * rank + i, with_neg=False) for i in range(P)]
+    host = [synthetic_batch(B, L, N, seed=1000 * rank + i, with_neg=False, layout=layout) for i in range(P)]
     keys = ('user_id', 'in_item_id', 'item_id', 'seqlen')
     pinned = [{k: b[k].pin_memory() for k in keys} for b in host]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in pinned]
-    live_tokens = sum(int(b['seqlen'].clamp(max=L).sum()) for b in host) / P
+    live_tokens = sum(int(b['seqlen'].clamp(max=L).sum()) for b in host) / P if layout == 'post' else float(B * L)
 
     def step(batch):
         batch = dict(batch)
@@ -303,8 +319,7 @@ def main():
         'metric': METRIC, 'value': total_seqs / (ms_dev * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'SASRec synthetic |items|=100K d=128 L=50 batch=1024 per GPU, sampled BCE, dropout 0.5, dense '
-                               'Adam (BASELINE configs[1])',
+        'config': {'workload': workload,
                    'global_batch': B * world, 'seq_len': L, 'parallelism': f'dp{world}' if world > 1 else 'single',
                    'l2': 'no explicit flush: the step streams the 51 MB table + m + v + grad (205 MB) plus activations, '
                          'larger than the 126 MB L2; 8 distinct batches are cycled',
@@ -314,7 +329,7 @@ def main():
                 'ms_per_step': ms_e2e / args.steps},
         'roofline': roof, 'kernels': breakdown[:12],
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == 'SASRec':
         r = cpu_step_rate(steps=6, warmup=1, budget_s=25.0)
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
     if rank == 0:
