@@ -55,6 +55,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int) -> None:
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.window = (0.0, float('inf'))
 
     def __enter__(self):
         try:
@@ -68,7 +69,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line)
+            self.lines.append((time.time(), line))
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -80,7 +81,10 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
-        for line in self.lines:
+        lo, hi = self.window
+        for ts, line in self.lines:
+            if ts < lo - 0.15 or ts > hi + 0.15:       # nvidia-smi reports every 100 ms: keep the samples of the timed region
+                continue
             f = [x.strip() for x in line.split(',')]
             if len(f) < 8:
                 continue
@@ -136,6 +140,49 @@ def cpu_step_rate(steps: int, warmup: int, budget_s: float = 25.0):
                        f'reference B x N multinomial negatives), torch {torch.__version__} CPU, {cores} threads')
 
 
+def torch_gpu_step_rate(dev, steps: int = 20, warmup: int = 5):
+    """The oracle port's torch modules moved to the GPU: what the reference's own PyTorch path costs on
+    this B200 (its launch-bound eager step).  Context for the north-star's '>= 15x the reference on
+    1xB200'; NOT the reference arm (the driver's reference arm is the CPU run)."""
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    from oracle import dr4sr_oracle as orc
+    c = CFG2
+    B, L, N = c['batch_per_gpu'], c['max_seq_len'], c['num_items']
+    torch.manual_seed(2023)
+    m = orc.OracleSASRec(N, embed_dim=c['embed_dim'], max_seq_len=L, head_num=c['head_num'], hidden_size=c['hidden_size'],
+                         dropout_rate=c['dropout_rate'], layer_num=c['layer_num']).init_reference_style().to(dev).train()
+    opt = m.make_adam(lr=1e-3)
+    batch = {k: v.to(dev) for k, v in synthetic_batch(B, L, N, seed=7, with_neg=False).items()}
+    ar = torch.arange(L, device=dev)
+    causal = torch.triu(torch.ones(L, L, dtype=torch.bool, device=dev), 1)
+
+    def one():
+        b = dict(batch)
+        w = torch.ones(B, N, device=dev)
+        w[:, 0] = 0
+        b['neg_item'] = torch.multinomial(w, L, replacement=True).reshape_as(b['item_id']).unsqueeze(-1)   # basemodel.py:50-61
+        opt.zero_grad()
+        enc = m.query_encoder
+        x = enc.item_encoder(b['in_item_id']) + enc.position_emb(ar).unsqueeze(0)
+        out = enc.transformer_layer(src=enc.dropout(x), mask=causal, src_key_padding_mask=b['in_item_id'] == 0)
+        q = out.masked_fill(ar.view(1, L, 1) >= b['seqlen'].view(-1, 1, 1), 0.0)
+        pos, neg = orc.sampled_scores(q, m.item_embedding.weight, b['item_id'], b['neg_item'])
+        loss = orc.bce_loss(pos, neg)
+        loss.backward()
+        opt.step()
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {'value': B * steps / dt, 'unit': UNIT, 'ms_per_step': 1e3 * dt / steps,
+            'what': 'oracle port (torch eager, fp32, reference B x N multinomial negatives) on the same B200'}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -174,8 +221,8 @@ def kernel_work(name: str, T: int, B: int, c: dict):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
-    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--model', default='SASRec', choices=['SASRec', 'GRU4Rec', 'FMLP'],
@@ -262,12 +309,16 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for i in range(max(args.warmup, 3)):
-        step(resident[i % P])
-    launches0 = lib.dr4sr_launch_count()
     with ClockSampler(local) as clk:
+        for i in range(max(args.warmup, 3)):
+            step(resident[i % P])
+        torch.cuda.synchronize()
+        launches0 = lib.dr4sr_launch_count()
+        t_beg = time.time()
         ms_dev = timed(lambda i: step(resident[i % P]), args.steps)
-    launches = lib.dr4sr_launch_count() - launches0
+        clk.window = (t_beg, time.time())
+        launches = lib.dr4sr_launch_count() - launches0
+        time.sleep(0.25)                               # let the last sample of the window arrive
     clocks = clk.summary()
 
     # ---- e2e: host (pinned) batches -> H2D -> step -> D2H of the loss, every step ----
@@ -332,6 +383,10 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.model == 'SASRec':
         r = cpu_step_rate(steps=6, warmup=1, budget_s=25.0)
         line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'], 'sample': r['sample']}
+        try:
+            line['cpu_baseline']['same_port_on_this_gpu'] = torch_gpu_step_rate(dev)
+        except Exception as exc:       # context only: never fail the bench line on it
+            line['cpu_baseline']['same_port_on_this_gpu'] = {'error': str(exc)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -62,6 +62,9 @@ SIGNATURES = {
     'dr4sr_sum': (c_i32, [c_p, c_i64, c_p, c_p]),
     'dr4sr_table_grad_workspace_bytes': (c_sz, [c_i32, c_i32]),
     'dr4sr_table_grad': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_sz, c_p]),
+    'dr4sr_shard_plan': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    'dr4sr_gather_rows': (c_i32, [c_p, c_p, c_i64, c_i64, c_i32, c_p, c_p]),
+    'dr4sr_scatter_add_rows': (c_i32, [c_p, c_p, c_i64, c_i64, c_i32, c_p, c_p]),
     'dr4sr_adam': (c_i32, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_i32, c_p]),
     'dr4sr_topk_workspace_bytes': (c_sz, [c_i32, c_i64, c_i32]),
     'dr4sr_topk': (c_i32, [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i64, c_i32, c_i32, c_p, c_p, c_p, c_sz, c_p]),

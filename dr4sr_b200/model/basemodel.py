@@ -90,7 +90,18 @@ class BaseModel(nn.Module):
         self.max_seq_len = config['data']['max_seq_len']
         self.num_users = head.num_users
         self.num_items = head.num_items
-        self.item_embedding = nn.Embedding(self.num_items, self.embed_dim, padding_idx=0)
+        # config['train']['table_shard'] = (rank, world): this process holds rows [lo, hi) of the item table only
+        # (multi-GPU, see dr4sr_b200/sharded.py); absent => the whole table, as in the reference (basemodel.py:42)
+        self._shard = None
+        self._shard_rows = None
+        ts = config['train'].get('table_shard')
+        if ts is not None:
+            from ..dist import shard_rows
+            self._shard_rows = shard_rows(self.num_items, int(ts[1]))[int(ts[0])]
+            lo, hi = self._shard_rows
+            self.item_embedding = nn.Embedding(hi - lo, self.embed_dim, padding_idx=0 if lo == 0 else None)
+        else:
+            self.item_embedding = nn.Embedding(self.num_items, self.embed_dim, padding_idx=0)
         self.eval_domain = self.domain_name_list[0]
         self.engine = None
         self._dead_cache: Dict[str, torch.Tensor] = {}
@@ -175,6 +186,32 @@ class BaseModel(nn.Module):
         on the N*B global batch (up to fp32 summation order)."""
         self._dp_group = group
 
+    def enable_sharded_table(self, group) -> None:
+        """Row-sharded item table (config['train']['table_shard'] must have sized the embedding as the shard):
+        rows are fetched / their gradients returned by all-to-all, Adam runs on the shard; the encoder stays
+        data parallel."""
+        from ..sharded import ShardedTable
+        if self._shard_rows is None:
+            raise _engine._lib.Dr4srError("enable_sharded_table needs config['train']['table_shard'] = (rank, world)")
+        self._dp_group = group
+        self._shard = ShardedTable(self.num_items, self.embed_dim, group, self.item_embedding.weight.device)
+        assert (self._shard.lo, self._shard.hi) == tuple(self._shard_rows)
+
+    def _rows_for(self, bufs, in_ids, item_id, neg):
+        """(table, in_ids, item_id, neg) the kernels run on: the parameter itself, or the staged local rows."""
+        if self._shard is None:
+            return self.item_embedding.weight.data, in_ids, item_id, neg
+        return self._shard.fetch(self.item_embedding.weight.data, bufs, in_ids, item_id, neg)
+
+    def _scatter_target(self) -> torch.Tensor:
+        return self._table_grad_buffer() if self._shard is None else self._shard.local_grad()
+
+    def _finish_table_grad(self, tg: torch.Tensor) -> None:
+        if self._shard is None:
+            self._dp_sum(tg)
+        else:
+            self._shard.push_grads(self._table_grad_buffer())
+
     def _dp_sum(self, *tensors) -> None:
         grp = getattr(self, '_dp_group', None)
         if grp is not None:
@@ -233,7 +270,11 @@ class BaseModel(nn.Module):
     @torch.no_grad()
     def topk(self, batch, k, user_h=None):
         query = self.forward(batch)
-        return _engine.topk(query, self.item_embedding.weight.data, self._item_dead(self.eval_domain), user_h, k)
+        dead = self._item_dead(self.eval_domain)
+        if self._shard is not None:
+            lo, hi = self._shard_rows
+            return self._shard.topk(_engine.topk, query, self.item_embedding.weight.data, dead[lo:hi].contiguous(), user_h, k)
+        return _engine.topk(query, self.item_embedding.weight.data, dead, user_h, k)
 
     def set_eval_domain(self, domain):
         self.eval_domain = domain

@@ -44,8 +44,7 @@ class GRU4Rec(BaseModel):
 
     def _step_backward(self, state, reduce, dloss, dquery) -> None:
         eng = self.engine
-        b, in_ids, item_id, neg = state
-        table = self.item_embedding.weight.data
+        b, table, in_ids, item_id, neg = state
         if reduce:
             eng.score_bce(b, table, item_id, neg, want_grad=True, upstream=dloss)
         else:
@@ -55,9 +54,10 @@ class GRU4Rec(BaseModel):
             valid = torch.arange(eng.L, device=dquery.device).view(1, -1) < batch_len(b)
             b.dq[: int(b.counts[0])] += dquery[valid]
         eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad)
-        tg = self._table_grad_buffer()
+        tg = self._scatter_target()
         eng.table_grad(b, in_ids, item_id, neg, tg, None)          # no positional table in GRU4Rec
-        self._dp_sum(self._flat_grad, tg)
+        self._dp_sum(self._flat_grad)
+        self._finish_table_grad(tg)
 
     def training_step(self, batch, reduce=True, return_query=False, align=False):
         return super().training_step(batch, reduce, return_query)

@@ -76,7 +76,7 @@ class SASRec(BaseModel):
         eng = self.engine
         in_ids = batch['in_' + self.fiid]
         b = eng.prep(batch['seqlen'], None)
-        table = self.item_embedding.weight.data
+        table, in_ids, _, _ = self._rows_for(b, in_ids, None, None)
         if self.training or not need_pooling:
             q_dense = torch.empty(in_ids.size(0), eng.L, eng.D, dtype=torch.float32, device=in_ids.device)
             eng.encode(b, table, self._flat, in_ids, train=self.training, q_dense=q_dense)
@@ -86,7 +86,6 @@ class SASRec(BaseModel):
 
     def _step_forward(self, batch, reduce, return_query):
         eng = self.engine
-        table = self.item_embedding.weight.data
         in_ids, item_id, neg = batch['in_' + self.fiid], batch[self.fiid], batch['neg_item']
         neg = neg.view(item_id.shape)
         b = eng.prep(batch['seqlen'], item_id)
@@ -96,17 +95,17 @@ class SASRec(BaseModel):
         q_dense = None
         if return_query:
             q_dense = torch.empty(in_ids.size(0), eng.L, eng.D, dtype=torch.float32, device=in_ids.device)
+        table, in_ids, item_id, neg = self._rows_for(b, in_ids, item_id, neg)     # sharded table: staged rows + remapped ids
         eng.encode(b, table, self._flat, in_ids, train=self.training, q_dense=q_dense)
         eng.score_bce(b, table, item_id, neg, want_grad=False)
         loss = eng.reduce_loss(b).clone() if reduce else b.loss_pos.clone()
         if reduce:
             self._dp_sum(loss)
-        return loss, q_dense, (b, in_ids, item_id, neg)
+        return loss, q_dense, (b, table, in_ids, item_id, neg)
 
     def _step_backward(self, state, reduce, dloss, dquery) -> None:
         eng = self.engine
-        b, in_ids, item_id, neg = state
-        table = self.item_embedding.weight.data
+        b, table, in_ids, item_id, neg = state
         if reduce:
             eng.score_bce(b, table, item_id, neg, want_grad=True, upstream=dloss)
         else:
@@ -115,9 +114,10 @@ class SASRec(BaseModel):
             valid = torch.arange(eng.L, device=dquery.device).view(1, -1) < batch_len(b)
             b.dq[: int(b.counts[0])] += dquery[valid]
         eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad)
-        tg = self._table_grad_buffer()
+        tg = self._scatter_target()
         eng.table_grad(b, in_ids, item_id, neg, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
-        self._dp_sum(self._flat_grad, tg)
+        self._dp_sum(self._flat_grad)
+        self._finish_table_grad(tg)
 
     def training_step(self, batch, reduce=True, return_query=False, align=False):
         if align:

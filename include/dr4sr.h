@@ -211,6 +211,27 @@ DR4SR_API int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, c
                      dr4sr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Row-sharded item table (multi-GPU; no reference counterpart -- the reference is single-device).
+ * Rank r owns rows [lo_r, hi_r) of E (balanced contiguous ranges: the first num_rows % world ranks hold one
+ * extra row).  dr4sr_shard_plan turns the live slots of a batch into row requests bucketed by owner:
+ *   request 3*row+k of packed row `row`: k=0 input id, k=1 positive target, k=2 negative (targets only
+ *   where item_id != 0; id 0 is never requested)
+ *   send_counts [world] i32 (out): requests per owner;  send_ids [3*B*L] i64 (out): ids grouped by owner;
+ *   scratch [world+1] i32;  in_loc / item_loc / neg_loc [B,L] i64 (out): the ids remapped to rows of the
+ *   staged local table (0 = pad row, 1 + position in send_ids otherwise) -- every other entry point then
+ *   runs unchanged on (local table, remapped ids).
+ * dr4sr_gather_rows: out[r] = src[ids[r] - lo];  dr4sr_scatter_add_rows: dst[ids[r] - lo] += rows[r].
+ */
+DR4SR_API int dr4sr_shard_plan(const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item, const int32_t* tok_off,
+                     const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L, int64_t num_rows, int32_t world,
+                     int32_t* send_counts, int32_t* scratch, int64_t* send_ids, int64_t* in_loc, int64_t* item_loc,
+                     int64_t* neg_loc, dr4sr_stream_t stream);
+DR4SR_API int dr4sr_gather_rows(const float* src, const int64_t* ids, int64_t lo, int64_t m, int32_t D, float* out,
+                      dr4sr_stream_t stream);
+DR4SR_API int dr4sr_scatter_add_rows(float* dst, const int64_t* ids, int64_t lo, int64_t m, int32_t D, const float* rows,
+                           dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Dense Adam, replaces torch.optim.Adam.step as configured at model/basemodel.py:85-86
  * (betas .9/.999, eps 1e-8, L2 weight decay added to the gradient, no amsgrad).  One pass over
  * (p, g, m, v); step is 1-based; zero_grad != 0 clears g after reading it.
