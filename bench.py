@@ -210,7 +210,7 @@ def kernel_work(name: str, T: int, B: int, c: dict):
     gemm['wgrad_tc'] = 2 * T * (3 * D * D + D * D + 2 * D * F)
     if name in gemm:
         return dict(bound='tensor', work=gemm[name], unit='TFLOP/s')
-    byts = {'adam_table': 24 * N * D, 'embed_fwd': 2 * U, 'score_bce': 4 * U, 'table_grad_scatter': 5 * U, 'ln_bwd': 3 * U,
+    byts = {'adam_table': 24 * c.get('adam_rows', N) * D, 'embed_fwd': 2 * U, 'score_bce': 4 * U, 'table_grad_scatter': 5 * U, 'ln_bwd': 3 * U,
             'attn_fwd': 4 * U, 'attn_bwd': 7 * U, 'colsum': 2 * U, 'pos_grad': U}
     if name in byts:
         return dict(bound='hbm', work=byts[name], unit='GB/s')
@@ -225,6 +225,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--items', type=int, default=None, help='catalog size override (BASELINE configs[3]: 10_000_000)')
+    ap.add_argument('--batch', type=int, default=None, help='sequences per GPU override')
+    ap.add_argument('--table', default='auto', choices=['auto', 'replicated', 'sharded'],
+                    help='multi-GPU layout of the item table: replicated = data parallel with a dense gradient all-reduce; '
+                         'sharded = row-sharded table with all-to-all row exchange (auto: sharded above 1M items)')
     ap.add_argument('--model', default='SASRec', choices=['SASRec', 'GRU4Rec', 'FMLP'],
                     help='SASRec = BASELINE configs[1] (the headline); GRU4Rec / FMLP = configs[2]')
     args = ap.parse_args()
@@ -248,15 +253,21 @@ def main():
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
 
-    c = CFG2
+    c = dict(CFG2)
+    if args.items:
+        c['num_items'] = args.items
+    if args.batch:
+        c['batch_per_gpu'] = args.batch
     B, L, N = c['batch_per_gpu'], c['max_seq_len'], c['num_items']
+    sharded = world > 1 and (args.table == 'sharded' or (args.table == 'auto' and N > 1_000_000))
+    c['adam_rows'] = N // world if sharded else N
     if args.model == 'SASRec':
         from dr4sr_b200.model.sasrec import SASRec as Model
         cfg = default_config('SASRec', model__embed_dim=c['embed_dim'], model__hidden_size=c['hidden_size'],
                              model__layer_num=c['layer_num'], model__head_num=c['head_num'],
                              model__dropout_rate=c['dropout_rate'], train__device=str(dev), train__batch_size=B)
         layout, workload = 'post', ('SASRec synthetic |items|=100K d=128 L=50 batch=1024 per GPU, sampled BCE, dropout 0.5, dense Adam '
-                                    '(BASELINE configs[1])')
+                                    '(BASELINE configs[1])').replace('100K', f'{N:,}').replace('batch=1024', f'batch={B}')
     elif args.model == 'GRU4Rec':
         from dr4sr_b200.model.gru4rec import GRU4Rec as Model
         cfg = default_config('GRU4Rec', model__embed_dim=c['embed_dim'], train__device=str(dev), train__batch_size=B)
@@ -267,10 +278,14 @@ def main():
         cfg = default_config('FMLP', model__embed_dim=c['embed_dim'], train__device=str(dev), train__batch_size=B)
         layout, workload = 'pre', ('FMLP synthetic |items|=100K d=128 L=50 batch=1024 per GPU, pre-padded, single target, dropout 0.5, '
                                    'dense Adam (BASELINE configs[2])')
-    torch.manual_seed(2023)
+    if sharded:
+        cfg['train']['table_shard'] = (rank, world)
+    torch.manual_seed(2023 + (rank if sharded else 0))
     model = Model(cfg, [SyntheticCatalog(N)] * 3)
     model._init_model()
-    if world > 1:
+    if sharded:
+        model.enable_sharded_table(dist.group.WORLD)
+    elif world > 1:
         model.enable_data_parallel(dist.group.WORLD)
     model.train()
     lib = _lib.lib()
@@ -371,9 +386,10 @@ def main():
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': workload,
-                   'global_batch': B * world, 'seq_len': L, 'parallelism': f'dp{world}' if world > 1 else 'single',
-                   'l2': 'no explicit flush: the step streams the 51 MB table + m + v + grad (205 MB) plus activations, '
-                         'larger than the 126 MB L2; 8 distinct batches are cycled',
+                   'global_batch': B * world, 'seq_len': L, 'parallelism': (f'dp{world} encoder + row-sharded table (all-to-all)' if sharded else f'dp{world} (replicated table, dense grad all-reduce)') if world > 1 else 'single',
+                   'num_items': N,
+                   'l2': f'no explicit flush: the step streams the table + m + v + grad ({4 * N * c["embed_dim"] * 4 / 1e6:.0f} MB per replica) plus '
+                         'activations, larger than the 126 MB L2; 8 distinct batches are cycled',
                    'live_tokens_per_batch': live_tokens},
         'clocks': clocks, 'gpu_launches': int(launches),
         'e2e': {'value': total_seqs / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
