@@ -43,6 +43,7 @@ SIGNATURES = {
     'dr4sr_prof_enable': (c_i32, [c_i32]),
     'dr4sr_prof_collect': (c_sz, [C.c_char_p, c_sz]),
     'dr4sr_prep_batch': (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p]),
+    'dr4sr_gather_i64': (c_i32, [c_p, c_i32, c_p, c_i64, c_p, c_p]),
     'dr4sr_neg_sample': (c_i32, [c_p, c_i64, c_i64, c_u64, c_u64, c_p]),
     'dr4sr_set_gemm_backend': (c_i32, [c_i32]),
     'dr4sr_sasrec_param_count': (c_sz, [C.POINTER(SasrecCfg)]),

@@ -98,10 +98,31 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
   }
 }
 
+// out[r, :] = src[idx[r], :] for int64 rows of `width` elements (batch assembly from device-resident columns)
+__global__ void __launch_bounds__(256) gather_i64_kernel(const int64_t* __restrict__ src, int width, const int64_t* __restrict__ idx,
+                                                         int64_t m, int64_t* __restrict__ out) {
+  const int64_t total = m * width;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = e / width;
+    out[e] = src[idx[r] * width + (e - r * width)];
+  }
+}
+
 }  // namespace
 }  // namespace dr4sr
 
 using namespace dr4sr;
+
+extern "C" int dr4sr_gather_i64(const int64_t* src, int32_t width, const int64_t* idx, int64_t m, int64_t* out, dr4sr_stream_t stream) {
+  if (!src || !idx || !out || width <= 0 || m < 0) return DR4SR_EINVAL;
+  if (m == 0) return DR4SR_OK;
+  const int64_t total = m * width;
+  const int blocks = ceil_div(total, 256) < 4 * kNumSMs ? ceil_div(total, 256) : 4 * kNumSMs;
+  ProfScope prof("gather_batch", as_stream(stream));
+  gather_i64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, width, idx, m, out);
+  DR4SR_LAUNCH_CHECK("gather_i64_kernel");
+  return DR4SR_OK;
+}
 
 extern "C" int dr4sr_prep_batch(const int64_t* seqlen, const int64_t* item_id, int32_t B, int32_t L, int32_t target_is_1d,
                                 int32_t* tok_off, int32_t* row_seq, int32_t* counts, dr4sr_stream_t stream) {

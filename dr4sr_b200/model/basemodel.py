@@ -107,6 +107,14 @@ class BaseModel(nn.Module):
         self._dead_cache: Dict[str, torch.Tensor] = {}
         self._neg_step = 0
 
+    @staticmethod
+    def _get_dataset_class(config):
+        """Reference model/basemodel.py:63-77; the shipped configs all use 'general' = SeparateDataset."""
+        from ..data.dataset import SeparateDataset
+        if config['data']['dataset_class'] == 'general':
+            return SeparateDataset
+        raise NotImplementedError(f"dataset_class {config['data']['dataset_class']!r}: only 'general' is used by the shipped configs")
+
     # ---- hooks a subclass provides ----------------------------------------------------------
     def _build_engine(self) -> None:
         raise NotImplementedError

@@ -117,6 +117,20 @@ class FMLP(BaseModel):
         eng.table_grad(b, in_ids, item_id, neg, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
         self._dp_sum(self._flat_grad, tg)
 
+    def composite_forward(self, batch):
+        """Twice-differentiable torch evaluation (MetaModel's outer step only), model/fmlp.py:18-39."""
+        import torch.nn.functional as F
+        ids = batch['in_' + self.fiid]
+        L = ids.size(1)
+        x = self.item_embedding(ids) + self.position_embeddings(torch.arange(L, device=ids.device)).unsqueeze(0)
+        x = self.dropout(self.LayerNorm(x))
+        for blk in self.item_encoder.layer:
+            f, i = blk.filterlayer, blk.intermediate
+            spec = torch.fft.rfft(x, dim=1, norm='ortho') * torch.view_as_complex(f.complex_weight)
+            y = f.LayerNorm(f.out_dropout(torch.fft.irfft(spec, n=L, dim=1, norm='ortho')) + x)
+            x = i.LayerNorm(i.dropout(i.dense_2(F.gelu(i.dense_1(y)))) + y)
+        return x[:, -1]
+
     def current_epoch_trainloaders(self, nepoch):
         return super().current_epoch_trainloaders(nepoch)
 

@@ -59,5 +59,14 @@ class GRU4Rec(BaseModel):
         self._dp_sum(self._flat_grad)
         self._finish_table_grad(tg)
 
+    def composite_forward(self, batch):
+        """Twice-differentiable torch evaluation (MetaModel's outer step only), model/gru4rec.py:23-31."""
+        ids = batch['in_' + self.fiid]
+        seq = self.query_encoder[0]
+        h = seq[3].gru(seq[2](self.item_embedding(ids)))[0]
+        out = self.query_encoder[1](h)
+        ar = torch.arange(ids.size(1), device=ids.device)
+        return out.masked_fill(ar.view(1, -1, 1) >= batch['seqlen'].view(-1, 1, 1), 0.0)
+
     def training_step(self, batch, reduce=True, return_query=False, align=False):
         return super().training_step(batch, reduce, return_query)

@@ -119,6 +119,18 @@ class SASRec(BaseModel):
         self._dp_sum(self._flat_grad)
         self._finish_table_grad(tg)
 
+    def composite_forward(self, batch):
+        """Twice-differentiable torch evaluation of the same parameters (MetaModel's outer step only):
+        the reference's own module graph, model/sasrec.py:39-75, 'origin' pooling."""
+        enc = self.query_encoder
+        ids = batch['in_' + self.fiid]
+        L = ids.size(1)
+        ar = torch.arange(L, device=ids.device)
+        x = enc.item_encoder(ids) + enc.position_emb(ar).unsqueeze(0)
+        causal = torch.triu(torch.ones(L, L, dtype=torch.bool, device=ids.device), 1)
+        out = enc.transformer_layer(src=enc.dropout(x), mask=causal, src_key_padding_mask=ids == 0)
+        return out.masked_fill(ar.view(1, L, 1) >= batch['seqlen'].view(-1, 1, 1), 0.0)
+
     def training_step(self, batch, reduce=True, return_query=False, align=False):
         if align:
             raise NotImplementedError('the align branch (model/sasrec.py:111-119) has no caller in the reference')

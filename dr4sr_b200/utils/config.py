@@ -21,6 +21,10 @@ def default_config(model: str = 'SASRec', dataset: str = 'synthetic', **over) ->
         'gru4rec': {'model': {'hidden_size': 256, 'dropout_rate': 0.2, 'layer_num': 2},
                     'train': {'learning_rate': 0.001, 'weight_decay': 0.0001}},
         'fmlp': {'model': {'layer_num': 2, 'dropout_rate': 0.5}},
+        'metamodel': {'model': {'sub_model': 'FMLP', 'hidden_size': 128, 'layer_num': 2, 'head_num': 2, 'dropout_rate': 0.5,
+                                'activation': 'gelu', 'tau_min': 1, 'layer_norm_eps': 1e-12},
+                      'train': {'interval': 30, 'meta_optimizer': 'sgd', 'meta_learning_rate': 0.001, 'hpo_learning_rate': 0.001,
+                                'meta_weight_decay': 0.001, 'descent_step': 30, 'warmup_epoch': 10, 'early_stop_patience': 20}},
     }[model.lower()]
     for sec, vals in per_model.items():
         cfg[sec].update(vals)

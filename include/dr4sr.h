@@ -65,6 +65,10 @@ DR4SR_API size_t dr4sr_prof_collect(char* buf, size_t cap);
 DR4SR_API int dr4sr_prep_batch(const int64_t* seqlen, const int64_t* item_id, int32_t B, int32_t L, int32_t target_is_1d,
                      int32_t* tok_off, int32_t* row_seq, int32_t* counts, dr4sr_stream_t stream);
 
+/* Batch assembly, replaces SeparateDataset.__getitem__ + default_collate (data/dataset.py:149-164, one Python
+ * call per sample): out[r, :] = src[idx[r], :] for a device-resident int64 column of `width` elements per row. */
+DR4SR_API int dr4sr_gather_i64(const int64_t* src, int32_t width, const int64_t* idx, int64_t m, int64_t* out, dr4sr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Negative sampling, replaces BaseModel._neg_sampling (model/basemodel.py:50-61): one id per target
  * slot, i.i.d. uniform on {1..N-1}, with replacement (no B x N weight matrix).  Counter-based RNG:
