@@ -160,7 +160,24 @@ gru_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, con
   cluster.sync();
 
   const int ub = tid % TL::UB, bb = tid / TL::UB;
+  float* hs = hb + kTile * TL::LD;              // [kTile][UPC] staging of this CTA's new hidden units
   for (int t = 0; t < maxlen; ++t) {
+    // input-projection terms of this step: issued now, consumed after the recurrent product (latency hidden)
+    float gi_r[TL::BT][TL::UT], gi_z[TL::BT][TL::UT], gi_n[TL::BT][TL::UT];
+    bool live[TL::BT];
+#pragma unroll
+    for (int i = 0; i < TL::BT; ++i) {
+      const int bl = bb + i * TL::BB;
+      live[i] = t < s_len[bl];
+#pragma unroll
+      for (int u = 0; u < TL::UT; ++u) {
+        gi_r[i][u] = gi_z[i][u] = gi_n[i][u] = 0.f;
+        if (live[i]) {
+          const float* gir = gi + (size_t)(s_off[bl] + t) * 3 * H + rank * TL::UPC + ub + u * TL::UB;
+          gi_r[i][u] = gir[0]; gi_z[i][u] = gir[H]; gi_n[i][u] = gir[2 * H];
+        }
+      }
+    }
     // gh[b][row] = <h_{t-1}[b], W[row]> for the thread's BT sequences x (3 gates x UT units)
     float acc[TL::BT][3][TL::UT];
 #pragma unroll
@@ -190,45 +207,37 @@ gru_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, con
             acc[i][g][u] = fmaf(hv[i].w, wv[g][u].w, acc[i][g][u]);
           }
     }
-    // gates for the thread's (sequence, unit) pairs; new h kept in registers until every CTA has finished reading hb
-    float hnew[TL::BT][TL::UT];
-    bool live[TL::BT];
+    // gates; the new h of this CTA's units goes to the staging tile (finished sequences keep their state)
 #pragma unroll
     for (int i = 0; i < TL::BT; ++i) {
       const int bl = bb + i * TL::BB;
-      live[i] = t < s_len[bl];
       const size_t row = (size_t)(s_off[bl] + t);
 #pragma unroll
       for (int u = 0; u < TL::UT; ++u) {
-        const int unit = rank * TL::UPC + ub + u * TL::UB;
+        const int ul = ub + u * TL::UB, unit = rank * TL::UPC + ul;
         const float hp = hb[bl * TL::LD + unit];
-        hnew[i][u] = hp;
+        float hv = hp;
         if (live[i]) {
-          const float* gir = gi + row * 3 * H;
-          const float r = sigmoidf_(gir[unit] + acc[i][0][u]);
-          const float z = sigmoidf_(gir[H + unit] + acc[i][1][u]);
+          const float r = sigmoidf_(gi_r[i][u] + acc[i][0][u]);
+          const float z = sigmoidf_(gi_z[i][u] + acc[i][1][u]);
           const float hn = acc[i][2][u];
-          const float n = tanhf(gir[2 * H + unit] + r * hn);
-          const float hv = (1.0f - z) * n + z * hp;
-          hnew[i][u] = hv;
+          const float n = tanhf(gi_n[i][u] + r * hn);
+          hv = (1.0f - z) * n + z * hp;
           h_out[row * H + unit] = hv;
           hprev_out[row * H + unit] = hp;
           float* gr = gates + row * 4 * H;
           gr[unit] = r; gr[H + unit] = z; gr[2 * H + unit] = n; gr[3 * H + unit] = hn;
         }
+        hs[bl * TL::UPC + ul] = hv;
       }
     }
-    cluster.sync();                               // every CTA is done reading h_{t-1}
-#pragma unroll
-    for (int i = 0; i < TL::BT; ++i) {
-      if (!live[i]) continue;                     // finished sequences keep their state (never read again)
-      const int bl = bb + i * TL::BB;
-#pragma unroll
-      for (int u = 0; u < TL::UT; ++u) {
-        const int unit = rank * TL::UPC + ub + u * TL::UB;
-#pragma unroll
-        for (int r = 0; r < kCluster; ++r) cluster.map_shared_rank(hb, r)[bl * TL::LD + unit] = hnew[i][u];
-      }
+    cluster.sync();                               // every CTA is done reading h_{t-1}; staging tiles are complete
+    // push the staged [kTile x UPC] block into every CTA's h buffer: 16-byte distributed-shared-memory stores
+    constexpr int F4 = TL::UPC / 4;
+    for (int e = tid; e < kCluster * kTile * F4; e += kGruThreads) {
+      const int r = e / (kTile * F4), rem = e % (kTile * F4), bl = rem / F4, c = (rem % F4) * 4;
+      *reinterpret_cast<float4*>(cluster.map_shared_rank(hb, r) + bl * TL::LD + rank * TL::UPC + c) =
+          *reinterpret_cast<const float4*>(hs + bl * TL::UPC + c);
     }
     cluster.sync();                               // h_t visible in every CTA
   }
@@ -332,21 +341,30 @@ gru_bwd_kernel(const float* __restrict__ dh_up, const float* __restrict__ w_hh, 
         for (int c = 0; c < CT; ++c) *reinterpret_cast<float4*>(part + (bl0 + i * BL) * TL::LD + (cl + c * CL) * 4) = acc[i][c];
     }
     cluster.sync();                                   // all partials written
-    // (3) reduce-scatter: this CTA's units gather their column from every CTA's partial (fixed rank order)
-    for (int e = tid; e < kTile * TL::UPC; e += kGruThreads) {
-      const int bl = e / TL::UPC, ul = e % TL::UPC;
-      const int unit = rank * TL::UPC + ul;
-      float s = 0.f;
+    // (3) reduce-scatter: this CTA's units gather their columns from every CTA's partial (fixed rank order),
+    //     16-byte distributed-shared-memory loads
+    {
+      constexpr int F4 = TL::UPC / 4;
+      for (int e = tid; e < kTile * F4; e += kGruThreads) {
+        const int bl = e / F4, c = (e % F4) * 4;
+        float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int r = 0; r < kCluster; ++r) s += cluster.map_shared_rank(part, r)[bl * TL::LD + unit];
-      dhc[bl * TL::UPC + ul] += s;
+        for (int r = 0; r < kCluster; ++r) {
+          const float4 v = *reinterpret_cast<const float4*>(cluster.map_shared_rank(part, r) + bl * TL::LD + rank * TL::UPC + c);
+          sacc.x += v.x; sacc.y += v.y; sacc.z += v.z; sacc.w += v.w;
+        }
+        float4* d = reinterpret_cast<float4*>(dhc + bl * TL::UPC + c);
+        float4 o = *d;
+        o.x += sacc.x; o.y += sacc.y; o.z += sacc.z; o.w += sacc.w;
+        *d = o;
+      }
     }
     cluster.sync();                                   // partials consumed before the next step overwrites them
   }
 }
 
 template <int H>
-size_t fwd_smem() { using TL = Tiling<H>; return sizeof(float) * (size_t)(TL::ROWS * TL::LD + kTile * TL::LD); }
+size_t fwd_smem() { using TL = Tiling<H>; return sizeof(float) * (size_t)(TL::ROWS * TL::LD + kTile * TL::LD + kTile * TL::UPC); }
 template <int H>
 size_t bwd_smem() {
   using TL = Tiling<H>;

@@ -35,11 +35,15 @@ struct Workspace {
   // saved activations
   float* x0;
   struct Layer { float *qkv, *attn, *z1, *st1, *x1, *pre, *z2, *st2, *x2; } layer[8];
-  // backward scratch
-  float *g0, *g1, *g2, *g3, *dqkv, *dpre;
-  float *part_w;     // [kSplit][3DD + DD + FD + DF] weight-gradient partials of the current layer
-  float *part_ln2, *part_ln1;   // [kLnBwdBlocks][3D]
-  float *part_cs_in, *part_cs_b1;   // [kColsumBlocks][3D], [kColsumBlocks][F]
+  // backward scratch.  g0 / g2 belong to the data-gradient chain; everything in `Bwd` is per layer because the
+  // weight-gradient work of layer l runs on a side stream while the main stream already works on layer l-1
+  float *g0, *g2;
+  struct Bwd {
+    float *g1, *g3, *dqkv, *dpre;
+    float *part_w;                    // [kSplit][3DD + DD + FD + DF] weight-gradient partials
+    float *part_ln2, *part_ln1;       // [kLnBwdBlocks][3D]
+    float *part_cs_in, *part_cs_b1;   // [kColsumBlocks][3D], [kColsumBlocks][F]
+  } bwd[8];
   // bf16 hi/lo weight images (UMMA SW128 K-major) of every layer: forward operands W[n,k] and the
   // transposed backward-data operands W^T, rebuilt at the start of every forward
   struct LayerImg { Img in_f, out_f, w1_f, w2_f, in_b, out_b, w1_b, w2_b; } img[8];
@@ -60,12 +64,16 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
     y.qkv = take(T * 3 * D); y.attn = take(T * D); y.z1 = take(T * D); y.st1 = take(T * 2); y.x1 = take(T * D);
     y.pre = take(T * F); y.z2 = take(T * D); y.st2 = take(T * 2); y.x2 = take(T * D);
   }
-  w.g0 = take(T * D); w.g1 = take(T * D); w.g2 = take(T * D); w.g3 = take(T * D); w.dqkv = take(T * 3 * D); w.dpre = take(T * F);
-  w.part_w = take((size_t)kSplit * (3 * D * D + D * D + 2 * F * D));
-  w.part_ln2 = take((size_t)kLnBwdBlocks * 3 * D);
-  w.part_ln1 = take((size_t)kLnBwdBlocks * 3 * D);
-  w.part_cs_in = take((size_t)kColsumBlocks * 3 * D);
-  w.part_cs_b1 = take((size_t)kColsumBlocks * F);
+  w.g0 = take(T * D); w.g2 = take(T * D);
+  for (int l = 0; l < c.n_layer; ++l) {
+    auto& b = w.bwd[l];
+    b.g1 = take(T * D); b.g3 = take(T * D); b.dqkv = take(T * 3 * D); b.dpre = take(T * F);
+    b.part_w = take((size_t)kSplit * (3 * D * D + D * D + 2 * F * D));
+    b.part_ln2 = take((size_t)kLnBwdBlocks * 3 * D);
+    b.part_ln1 = take((size_t)kLnBwdBlocks * 3 * D);
+    b.part_cs_in = take((size_t)kColsumBlocks * 3 * D);
+    b.part_cs_b1 = take((size_t)kColsumBlocks * F);
+  }
   auto take_img = [&](size_t elems) {   // hi + lo images, bf16; 1 KB aligned (align_up keeps 256 B, images are multiples of 16 KB)
     Img im;
     im.hi = reinterpret_cast<uint16_t*>(take((elems + 1) / 2));
@@ -117,6 +125,23 @@ int build_weight_images(const dr4sr_sasrec_cfg& c, const float* params, const Wo
   }
   return DR4SR_OK;
 }
+// Side stream for the weight-gradient work of the backward (fork/join with events; also legal inside a
+// CUDA-graph capture of the main stream).  One per device, created on first use, never destroyed.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork[8] = {}, join = nullptr; bool ok = false; };
+SideStream& side_stream() {
+  static SideStream per_dev[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideStream& x = per_dev[dev & 63];
+  if (!x.ok) {
+    bool good = cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && good; ++i) good = cudaEventCreateWithFlags(&x.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+    x.ok = good;
+  }
+  return x;
+}
+
 __global__ void __launch_bounds__(256) gather_last_kernel(const float* __restrict__ x, const int32_t* __restrict__ tok_off, int B,
                                                           int D, float* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -255,103 +280,120 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
   const size_t pw_in = 0, pw_out = (size_t)kSplit * 3 * D * D, pw_w1 = pw_out + (size_t)kSplit * D * D,
                pw_w2 = pw_w1 + (size_t)kSplit * F * D;
 
+  SideStream& side = side_stream();
+  cudaStream_t sw = side.ok ? side.s : st;            // weight-gradient stream (falls back to in-order if creation failed)
   float* gin = dq_packed;   // gradient w.r.t. the current layer's output
   for (int l = c->n_layer - 1; l >= 0; --l) {
     const float* lp = params + (size_t)c->L * D + (size_t)l * lo.total;
     float* lg = grads + (size_t)c->L * D + (size_t)l * lo.total;
     auto& y = w.layer[l];
+    auto& s = w.bwd[l];
     const float* xin = l == 0 ? w.x0 : w.layer[l - 1].x2;
     const Dropout d_ffn_out = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_OUT, l), tr);
     const Dropout d_ffn_h = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_H, l), tr);
     const Dropout d_attn_out = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_OUT, l), tr);
     const Dropout d_attn_p = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr);
 
+    // ---- data-gradient chain (main stream) ----
     // LN2 backward: g3 = dz2 ; partials -> dgamma2, dbeta2, db2
-    DR4SR_TRY(launch_ln_bwd(gin, y.z2, y.st2, lp + lo.g2, w.g3, w.part_ln2, D, T, counts, d_ffn_out, st));
+    DR4SR_TRY(launch_ln_bwd(gin, y.z2, y.st2, lp + lo.g2, s.g3, s.part_ln2, D, T, counts, d_ffn_out, st));
     {  // dpre = ((dz2 * mask_out) W2) * mask_h * gelu'(pre)
-      GemmArgs g = gemm_args(w.g3, D, lp + lo.w2, F, w.dpre, F, T, F, D, counts);
+      GemmArgs g = gemm_args(s.g3, D, lp + lo.w2, F, s.dpre, F, T, F, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_ffn_out;
       g.epi = EPI_GELU_BWD; g.pre = y.pre; g.dropE = d_ffn_h; g.tag = "gemm_bwd_dpre";
       DR4SR_TRY(gemm_nn(g, w.img[l].w2_b, st));
     }
-    DR4SR_TRY(launch_colsum(w.dpre, F, T, counts, w.part_cs_b1, st));
     {  // dx1 = dz2 + dpre W1   -> g0
-      GemmArgs g = gemm_args(w.dpre, F, lp + lo.w1, D, w.g0, D, T, D, F, counts);
-      g.add = w.g3; g.ldadd = D; g.tag = "gemm_bwd_dx1";
+      GemmArgs g = gemm_args(s.dpre, F, lp + lo.w1, D, w.g0, D, T, D, F, counts);
+      g.add = s.g3; g.ldadd = D; g.tag = "gemm_bwd_dx1";
       DR4SR_TRY(gemm_nn(g, w.img[l].w1_b, st));
     }
     // LN1 backward: g1 = dz1 ; partials -> dgamma1, dbeta1, db_out
-    DR4SR_TRY(launch_ln_bwd(w.g0, y.z1, y.st1, lp + lo.g1, w.g1, w.part_ln1, D, T, counts, d_attn_out, st));
+    DR4SR_TRY(launch_ln_bwd(w.g0, y.z1, y.st1, lp + lo.g1, s.g1, s.part_ln1, D, T, counts, d_attn_out, st));
     {  // d(attn) = (dz1 * mask) Wo -> g2
-      GemmArgs g = gemm_args(w.g1, D, lp + lo.out_w, D, w.g2, D, T, D, D, counts);
+      GemmArgs g = gemm_args(s.g1, D, lp + lo.out_w, D, w.g2, D, T, D, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_bwd_dattn";
       DR4SR_TRY(gemm_nn(g, w.img[l].out_b, st));
     }
-    DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, w.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
-    DR4SR_TRY(launch_colsum(w.dqkv, 3 * D, T, counts, w.part_cs_in, st));
+    DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, s.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
+    if (side.ok) {   // everything the weight gradients of this layer read is now final: fork
+      if (cudaEventRecord(side.fork[l], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[l], 0) != cudaSuccess) {
+        set_cuda_error(cudaGetLastError(), "backward fork");
+        return DR4SR_ECUDA;
+      }
+    }
     {  // dx = dz1 + dqkv Win  (layer 0: times the embedding-dropout mask) -> g0 / dx0
       float* dst = l == 0 ? dx0_packed : w.g0;
-      GemmArgs g = gemm_args(w.dqkv, 3 * D, lp + lo.in_w, D, dst, D, T, D, 3 * D, counts);
-      g.add = w.g1; g.ldadd = D;
+      GemmArgs g = gemm_args(s.dqkv, 3 * D, lp + lo.in_w, D, dst, D, T, D, 3 * D, counts);
+      g.add = s.g1; g.ldadd = D;
       if (l == 0) g.dropE = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
       g.tag = "gemm_bwd_dx";
       DR4SR_TRY(gemm_nn(g, w.img[l].in_b, st));
     }
-    // weight gradients (reduction over the live tokens, kSplit partial tiles each):
+
+    // ---- weight / bias gradients of this layer (side stream; overlaps the next layer's chain) ----
+    DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
+    DR4SR_TRY(launch_colsum(s.dqkv, 3 * D, T, counts, s.part_cs_in, sw));
     //   dW2[d,f]  = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]      dW1[f,d]  = sum_m dpre[m,f] * x1[m,d]
     //   dWo[n,k]  = sum_m (dz1*mask)[m,n] * attn[m,k]                     dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
     if (tc_enabled() && tc::wgrad_supported(D, F) && tc::wgrad_supported(F, D) &&
         tc::wgrad_supported(D, D) && tc::wgrad_supported(3 * D, D)) {
       tc::WgradTable tab{};
-      Dropout none; none.key = 0; none.thresh = 0; none.scale = 1.f;
-      tab.job[0] = tc::WgradJob{w.dqkv, 3 * D, PRO_NONE, none, xin, D, PRO_NONE, none, 3 * D, D, w.part_w + pw_in, 0};
-      tab.job[1] = tc::WgradJob{w.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, w.part_w + pw_w2, 0};
-      tab.job[2] = tc::WgradJob{w.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, w.part_w + pw_w1, 0};
-      tab.job[3] = tc::WgradJob{w.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, w.part_w + pw_out, 0};
+      const Dropout none = no_dropout();
+      tab.job[0] = tc::WgradJob{s.dqkv, 3 * D, PRO_NONE, none, xin, D, PRO_NONE, none, 3 * D, D, s.part_w + pw_in, 0};
+      tab.job[1] = tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
+      tab.job[2] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
+      tab.job[3] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
       tab.count = 4; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
-      DR4SR_TRY(tc::launch_wgrad_tc(tab, st));
+      DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
     } else {
       {
-        GemmArgs g = gemm_args(w.g3, D, y.pre, F, nullptr, F, D, F, T, counts);
+        GemmArgs g = gemm_args(s.g3, D, y.pre, F, nullptr, F, D, F, T, counts);
         g.proA = PRO_DROPMASK; g.dropA = d_ffn_out; g.proB = PRO_GELU_DROP; g.dropB = d_ffn_h; g.tag = "gemm_wgrad_w2";
-        DR4SR_TRY(gemm_tn(g, w.part_w + pw_w2, st));
+        DR4SR_TRY(gemm_tn(g, s.part_w + pw_w2, sw));
       }
       {
-        GemmArgs g = gemm_args(w.dpre, F, y.x1, D, nullptr, D, F, D, T, counts);
+        GemmArgs g = gemm_args(s.dpre, F, y.x1, D, nullptr, D, F, D, T, counts);
         g.tag = "gemm_wgrad_w1";
-        DR4SR_TRY(gemm_tn(g, w.part_w + pw_w1, st));
+        DR4SR_TRY(gemm_tn(g, s.part_w + pw_w1, sw));
       }
       {
-        GemmArgs g = gemm_args(w.g1, D, y.attn, D, nullptr, D, D, D, T, counts);
+        GemmArgs g = gemm_args(s.g1, D, y.attn, D, nullptr, D, D, D, T, counts);
         g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_wgrad_out";
-        DR4SR_TRY(gemm_tn(g, w.part_w + pw_out, st));
+        DR4SR_TRY(gemm_tn(g, s.part_w + pw_out, sw));
       }
       {
-        GemmArgs g = gemm_args(w.dqkv, 3 * D, xin, D, nullptr, D, 3 * D, D, T, counts);
+        GemmArgs g = gemm_args(s.dqkv, 3 * D, xin, D, nullptr, D, 3 * D, D, T, counts);
         g.tag = "gemm_wgrad_in";
-        DR4SR_TRY(gemm_tn(g, w.part_w + pw_in, st));
+        DR4SR_TRY(gemm_tn(g, s.part_w + pw_in, sw));
       }
     }
     {  // fixed-order reduction of every partial of this layer into the flat gradient buffer
       ReduceTable tab{};
       int k = 0;
       auto seg = [&](const float* src, float* dst, int ns, int64_t stride, int n) { tab.seg[k++] = ReduceSeg{src, dst, ns, stride, n}; };
-      seg(w.part_w + pw_in, lg + lo.in_w, kSplit, (int64_t)3 * D * D, 3 * D * D);
-      seg(w.part_w + pw_out, lg + lo.out_w, kSplit, (int64_t)D * D, D * D);
-      seg(w.part_w + pw_w1, lg + lo.w1, kSplit, (int64_t)F * D, F * D);
-      seg(w.part_w + pw_w2, lg + lo.w2, kSplit, (int64_t)D * F, D * F);
-      seg(w.part_cs_in, lg + lo.in_b, kColsumBlocks, 3 * D, 3 * D);
-      seg(w.part_cs_b1, lg + lo.b1, kColsumBlocks, F, F);
-      seg(w.part_ln1, lg + lo.g1, kLnBwdBlocks, 3 * D, D);
-      seg(w.part_ln1 + D, lg + lo.be1, kLnBwdBlocks, 3 * D, D);
-      seg(w.part_ln1 + 2 * D, lg + lo.out_b, kLnBwdBlocks, 3 * D, D);
-      seg(w.part_ln2, lg + lo.g2, kLnBwdBlocks, 3 * D, D);
-      seg(w.part_ln2 + D, lg + lo.be2, kLnBwdBlocks, 3 * D, D);
-      seg(w.part_ln2 + 2 * D, lg + lo.b2, kLnBwdBlocks, 3 * D, D);
+      seg(s.part_w + pw_in, lg + lo.in_w, kSplit, (int64_t)3 * D * D, 3 * D * D);
+      seg(s.part_w + pw_out, lg + lo.out_w, kSplit, (int64_t)D * D, D * D);
+      seg(s.part_w + pw_w1, lg + lo.w1, kSplit, (int64_t)F * D, F * D);
+      seg(s.part_w + pw_w2, lg + lo.w2, kSplit, (int64_t)D * F, D * F);
+      seg(s.part_cs_in, lg + lo.in_b, kColsumBlocks, 3 * D, 3 * D);
+      seg(s.part_cs_b1, lg + lo.b1, kColsumBlocks, F, F);
+      seg(s.part_ln1, lg + lo.g1, kLnBwdBlocks, 3 * D, D);
+      seg(s.part_ln1 + D, lg + lo.be1, kLnBwdBlocks, 3 * D, D);
+      seg(s.part_ln1 + 2 * D, lg + lo.out_b, kLnBwdBlocks, 3 * D, D);
+      seg(s.part_ln2, lg + lo.g2, kLnBwdBlocks, 3 * D, D);
+      seg(s.part_ln2 + D, lg + lo.be2, kLnBwdBlocks, 3 * D, D);
+      seg(s.part_ln2 + 2 * D, lg + lo.b2, kLnBwdBlocks, 3 * D, D);
       tab.count = k;
-      DR4SR_TRY(launch_reduce_segments(tab, st));
+      DR4SR_TRY(launch_reduce_segments(tab, sw));
     }
     gin = w.g0;
+  }
+  if (side.ok) {   // join: the caller's stream sees every gradient
+    if (cudaEventRecord(side.join, sw) != cudaSuccess || cudaStreamWaitEvent(st, side.join, 0) != cudaSuccess) {
+      set_cuda_error(cudaGetLastError(), "backward join");
+      return DR4SR_ECUDA;
+    }
   }
   return DR4SR_OK;
 }
