@@ -16,6 +16,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
 }
 
 std::atomic<int> g_gemm_backend{0};
+std::atomic<int> g_attn_backend{0};
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -47,6 +48,11 @@ extern "C" const char* dr4sr_last_cuda_error(void) { return g_err; }
 extern "C" int dr4sr_set_gemm_backend(int backend) {
   if (backend != 0 && backend != 1) return DR4SR_EINVAL;
   g_gemm_backend.store(backend);
+  return DR4SR_OK;
+}
+extern "C" int dr4sr_set_attn_backend(int backend) {
+  if (backend != 0 && backend != 1) return DR4SR_EINVAL;
+  g_attn_backend.store(backend);
   return DR4SR_OK;
 }
 extern "C" long long dr4sr_launch_count(void) { return g_launches.load(); }

@@ -7,7 +7,7 @@
 //
 // Structure per layer
 //   * input projection for all live tokens at once: gi = x W_ih^T  (tcgen05 / FFMA GEMM, dense.cuh)
-//   * the recurrence as ONE cluster-resident kernel: a cluster of 8 CTAs owns a tile of 64 sequences
+//   * the recurrence as ONE cluster-resident kernel: a cluster of 8 CTAs owns a tile of 32 sequences
 //     (sequences are counting-sorted by length so a tile steps in lock-step); CTA r keeps the W_hh rows
 //     of its H/8 hidden units (r-, z- and n-gate rows: 3H/8 x H fp32, ~100 KB for H = 256) in shared
 //     memory for the whole sequence, so the recurrent weights are read from HBM/L2 once per layer, not
@@ -24,7 +24,7 @@ namespace cg = cooperative_groups;
 namespace dr4sr {
 namespace {
 
-constexpr int kTile = 64;        // sequences per cluster
+constexpr int kTile = 32;        // sequences per cluster (more, smaller tiles: long tiles start first, short ones back-fill the SMs)
 constexpr int kCluster = 8;      // CTAs per cluster
 constexpr int kGruThreads = 256;
 

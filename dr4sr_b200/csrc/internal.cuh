@@ -10,6 +10,15 @@ int launch_attn_fwd(const float* qkv, const int64_t* in_ids, const int32_t* tok_
 int launch_attn_bwd(const float* qkv, const float* d_out, const int64_t* in_ids, const int32_t* tok_off, float* d_qkv,
                     int B, int L, int D, int n_head, Dropout drop, cudaStream_t st);
 
+// tcgen05 attention (head_dim 64): tiles of whole sequences with <= 128 rows  [attention_tc.cu]
+bool attn_tc_supported(int L, int D, int n_head);
+int attn_tc_num_tiles(int B, int L);
+int launch_attn_tiles(const int32_t* tok_off, int B, int L, int32_t* tile_first, cudaStream_t st);
+int launch_attn_tc_fwd(const float* qkv, const int64_t* in_ids, const int32_t* tok_off, const int32_t* row_seq,
+                       const int32_t* tile_first, float* out, int B, int L, int D, int n_head, Dropout drop, cudaStream_t st);
+int launch_attn_tc_bwd(const float* qkv, const float* d_out, const int64_t* in_ids, const int32_t* tok_off, const int32_t* row_seq,
+                       const int32_t* tile_first, float* d_qkv, int B, int L, int D, int n_head, Dropout drop, cudaStream_t st);
+
 // LayerNorm backward over packed rows + column partials  [rowops.cu]
 //   dz = LN'(dy; z, stats, gamma);  partials[blk][0..D) = sum dy*xhat, [D..2D) = sum dy,
 //   [2D..3D) = sum dz * bias_drop.factor (gradient of the bias that sits under the dropout before this LN)

@@ -47,6 +47,7 @@ struct Workspace {
   // bf16 hi/lo weight images (UMMA SW128 K-major) of every layer: forward operands W[n,k] and the
   // transposed backward-data operands W^T, rebuilt at the start of every forward
   struct LayerImg { Img in_f, out_f, w1_f, w2_f, in_b, out_b, w1_b, w2_b; } img[8];
+  int32_t* tile_first;   // attention tiles (tcgen05 path): first sequence of every <= 128-row tile
   size_t bytes;
 };
 
@@ -85,6 +86,7 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
     m.in_f = take_img(3 * D * D); m.out_f = take_img(D * D); m.w1_f = take_img(F * D); m.w2_f = take_img(D * F);
     m.in_b = take_img(3 * D * D); m.out_b = take_img(D * D); m.w1_b = take_img(F * D); m.w2_b = take_img(D * F);
   }
+  w.tile_first = reinterpret_cast<int32_t*>(take((size_t)attn_tc_num_tiles(c.B, c.L) + 2));
   w.bytes = off * sizeof(float);
   return w;
 }
@@ -225,6 +227,8 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
     (void)drop;
   }
   DR4SR_TRY(build_weight_images(*c, params, w, lo, st));
+  const bool attn_tc = attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head);
+  if (attn_tc) DR4SR_TRY(launch_attn_tiles(tok_off, c->B, c->L, w.tile_first, st));
   const float* x = w.x0;
   for (int l = 0; l < c->n_layer; ++l) {
     const float* lp = params + (size_t)c->L * D + (size_t)l * lo.total;
@@ -235,8 +239,12 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
       g.bias = lp + lo.in_b; g.tag = "gemm_qkv";
       DR4SR_TRY(gemm_nt(g, w.img[l].in_f, st));
     }
-    DR4SR_TRY(launch_attn_fwd(y.qkv, in_item_id, tok_off, y.attn, c->B, c->L, D, c->n_head,
-                              make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr), st));
+    if (attn_tc)
+      DR4SR_TRY(launch_attn_tc_fwd(y.qkv, in_item_id, tok_off, row_seq, w.tile_first, y.attn, c->B, c->L, D, c->n_head,
+                                   make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr), st));
+    else
+      DR4SR_TRY(launch_attn_fwd(y.qkv, in_item_id, tok_off, y.attn, c->B, c->L, D, c->n_head,
+                                make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr), st));
     {  // out-proj + dropout + residual + LN1
       GemmArgs g = gemm_args(y.attn, D, lp + lo.out_w, D, y.x1, D, T, D, D, counts);
       g.bias = lp + lo.out_b; g.add = x; g.ldadd = D;
@@ -267,9 +275,9 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
                                 const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
                                 const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed, float* grads,
                                 float* dx0_packed, dr4sr_stream_t stream) {
-  (void)table; (void)row_seq;
+  (void)table;
   DR4SR_TRY(check_cfg(c));
-  if (!params || !in_item_id || !tok_off || !counts || !ws || !dq_packed || !grads || !dx0_packed) return DR4SR_EINVAL;
+  if (!params || !in_item_id || !tok_off || !row_seq || !counts || !ws || !dq_packed || !grads || !dx0_packed) return DR4SR_EINVAL;
   Workspace w = carve(*c, ws);
   if (ws_bytes < w.bytes) return DR4SR_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
@@ -315,7 +323,11 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
       g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_bwd_dattn";
       DR4SR_TRY(gemm_nn(g, w.img[l].out_b, st));
     }
-    DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, s.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
+    if (attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head))   // tiles were built by the forward (same workspace)
+      DR4SR_TRY(launch_attn_tc_bwd(y.qkv, w.g2, in_item_id, tok_off, row_seq, w.tile_first, s.dqkv, c->B, c->L, D, c->n_head,
+                                   d_attn_p, st));
+    else
+      DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, s.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
     if (side.ok) {   // everything the weight gradients of this layer read is now final: fork
       if (cudaEventRecord(side.fork[l], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[l], 0) != cudaSuccess) {
         set_cuda_error(cudaGetLastError(), "backward fork");

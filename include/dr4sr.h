@@ -101,6 +101,10 @@ typedef struct {
  * fp32 accumulate) wherever the shape allows (N % 128 == 0, K % 64 == 0), 1 = exact-fp32 FFMA kernels
  * everywhere.  Process-wide; used by the parity tests to check both. */
 DR4SR_API int dr4sr_set_gemm_backend(int backend);
+/* Attention backend (head_dim 64 only): 0 (default) = register-tiled FFMA kernel, one CTA per (sequence, head);
+ * 1 = tcgen05 tiles of whole sequences (<= 128 rows) with bf16 hi/lo split operands.  Both are parity-tested; the
+ * FFMA kernel is the faster one at L = 50 today (profiles/r1_ncu_full_notes.md). */
+DR4SR_API int dr4sr_set_attn_backend(int backend);
 
 DR4SR_API size_t dr4sr_sasrec_param_count(const dr4sr_sasrec_cfg* cfg);
 DR4SR_API size_t dr4sr_sasrec_workspace_bytes(const dr4sr_sasrec_cfg* cfg);

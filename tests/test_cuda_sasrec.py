@@ -20,16 +20,19 @@ DEV = 'cuda:0'
 # per product) or on exact-fp32 FFMA kernels.  Both are held to the north-star bar (1e-4 relative on
 # losses / logits); the FFMA path is additionally held to fp32 round-off.
 TOL = {'tc': dict(fwd=1e-4, loss=1e-4, grad=1e-3, adam=1e-4), 'ffma': dict(fwd=1e-5, loss=1e-5, grad=1e-4, adam=2e-5)}
+TOL['tc_attn'] = TOL['tc']          # tcgen05 dense layers + tcgen05 attention tiles
 
 
-@pytest.fixture(params=['tc', 'ffma'], autouse=True)
+@pytest.fixture(params=['tc', 'tc_attn', 'ffma'], autouse=True)
 def backend(request):
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     from dr4sr_b200 import _lib
-    _lib.check(_lib.lib().dr4sr_set_gemm_backend(0 if request.param == 'tc' else 1), 'set_gemm_backend')
+    _lib.check(_lib.lib().dr4sr_set_gemm_backend(1 if request.param == 'ffma' else 0), 'set_gemm_backend')
+    _lib.check(_lib.lib().dr4sr_set_attn_backend(1 if request.param == 'tc_attn' else 0), 'set_attn_backend')
     yield request.param
     _lib.lib().dr4sr_set_gemm_backend(0)
+    _lib.lib().dr4sr_set_attn_backend(0)
 
 
 def _need_gpu():
