@@ -18,7 +18,7 @@ namespace dr4sr {
 namespace {
 
 enum : uint32_t { SITE_FILTER_OUT = SITE_ATTN_OUT };
-constexpr int kFilterChunks = kNumSMs;   // sequence chunks of the tap-gradient reduction
+constexpr int kFilterChunks = 4 * kNumSMs;   // sequence chunks of the tap-gradient reduction (4 CTAs of 4 warps per SM)
 
 struct FmlpOffsets {   // floats inside one layer's slice of the flat parameter buffer (state_dict order)
   size_t cw, fg, fb, w1, b1, w2, b2, ig, ib, total;
