@@ -47,6 +47,8 @@ SIGNATURES = {
     'dr4sr_neg_sample': (c_i32, [c_p, c_i64, c_i64, c_u64, c_u64, c_p]),
     'dr4sr_set_gemm_backend': (c_i32, [c_i32]),
     'dr4sr_set_attn_backend': (c_i32, [c_i32]),
+    'dr4sr_set_fused_backend': (c_i32, [c_i32]),
+    'dr4sr_debug_trace': (c_i32, [C.c_void_p]),
     'dr4sr_sasrec_param_count': (c_sz, [C.POINTER(SasrecCfg)]),
     'dr4sr_sasrec_workspace_bytes': (c_sz, [C.POINTER(SasrecCfg)]),
     'dr4sr_sasrec_fwd': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p, c_p, c_p]),

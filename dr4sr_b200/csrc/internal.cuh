@@ -19,6 +19,28 @@ int launch_attn_tc_fwd(const float* qkv, const int64_t* in_ids, const int32_t* t
 int launch_attn_tc_bwd(const float* qkv, const float* d_out, const int64_t* in_ids, const int32_t* tok_off, const int32_t* row_seq,
                        const int32_t* tile_first, float* d_qkv, int B, int L, int D, int n_head, Dropout drop, cudaStream_t st);
 
+// whole-encoder forward as one persistent tcgen05 kernel (D = F = 128, 2 heads)  [fused_fwd.cu]
+struct FusedLayerHost {
+  float *qkv, *attn, *z1, *st1, *x1, *pre, *z2, *st2, *x2;
+  const uint16_t* img[8];   // in_hi, in_lo, out_hi, out_lo, w1_hi, w1_lo, w2_hi, w2_lo (forward weight images)
+  const float *in_b, *out_b, *b1, *b2, *g1, *be1, *g2, *be2;
+  Dropout d_attn_p, d_attn_out, d_ffn_h, d_ffn_out;
+};
+struct FusedFwdHost {
+  const float* table; const float* pos;
+  const int64_t* in_ids; const int32_t* tok_off; const int32_t* row_seq; const int32_t* tiles;
+  float* x0;
+  int B, L, n_layer;
+  float ln_eps;
+  Dropout d_embed;
+  FusedLayerHost layer[8];
+};
+bool fused_fwd_supported(int L, int D, int F, int n_head);
+int fused_tiles_cap(int B, int L);
+int launch_fused_tiles(const int32_t* tok_off, int B, int32_t* tiles, cudaStream_t st);
+int launch_sasrec_fwd_fused(const FusedFwdHost& h, cudaStream_t st);
+int fused_fwd_set_trace(int* host_mapped);
+
 // LayerNorm backward over packed rows + column partials  [rowops.cu]
 //   dz = LN'(dy; z, stats, gamma);  partials[blk][0..D) = sum dy*xhat, [D..2D) = sum dy,
 //   [2D..3D) = sum dz * bias_drop.factor (gradient of the bias that sits under the dropout before this LN)

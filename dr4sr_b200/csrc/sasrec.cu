@@ -48,6 +48,7 @@ struct Workspace {
   // transposed backward-data operands W^T, rebuilt at the start of every forward
   struct LayerImg { Img in_f, out_f, w1_f, w2_f, in_b, out_b, w1_b, w2_b; } img[8];
   int32_t* tile_first;   // attention tiles (tcgen05 path): first sequence of every <= 128-row tile
+  int32_t* fused_tiles;  // fused encoder kernels: {n_tiles, first sequence of every greedy <= 128-row tile..., B}
   size_t bytes;
 };
 
@@ -87,6 +88,7 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
     m.in_b = take_img(3 * D * D); m.out_b = take_img(D * D); m.w1_b = take_img(F * D); m.w2_b = take_img(D * F);
   }
   w.tile_first = reinterpret_cast<int32_t*>(take((size_t)attn_tc_num_tiles(c.B, c.L) + 2));
+  w.fused_tiles = reinterpret_cast<int32_t*>(take((size_t)fused_tiles_cap(c.B, c.L) + 4));
   w.bytes = off * sizeof(float);
   return w;
 }
@@ -220,6 +222,37 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
   const LayerOffsets lo = layer_offsets(D, F);
   const float* pos = params;
 
+  if (fused_enabled() && fused_fwd_supported(c->L, D, F, c->n_head)) {
+    // one persistent kernel: gather + positions + dropout and every layer, per group of whole sequences
+    DR4SR_TRY(build_weight_images(*c, params, w, lo, st));
+    DR4SR_TRY(launch_fused_tiles(tok_off, c->B, w.fused_tiles, st));
+    FusedFwdHost h{};
+    h.table = table; h.pos = pos; h.in_ids = in_item_id; h.tok_off = tok_off; h.row_seq = row_seq; h.tiles = w.fused_tiles;
+    h.x0 = w.x0; h.B = c->B; h.L = c->L; h.n_layer = c->n_layer; h.ln_eps = c->ln_eps;
+    h.d_embed = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
+    for (int l = 0; l < c->n_layer; ++l) {
+      const float* lp = params + (size_t)c->L * D + (size_t)l * lo.total;
+      auto& y = w.layer[l];
+      const auto& m = w.img[l];
+      FusedLayerHost& d = h.layer[l];
+      d.qkv = y.qkv; d.attn = y.attn; d.z1 = y.z1; d.st1 = y.st1; d.x1 = y.x1; d.pre = y.pre; d.z2 = y.z2; d.st2 = y.st2;
+      d.x2 = (l == c->n_layer - 1 && q_packed) ? q_packed : y.x2;
+      d.img[0] = m.in_f.hi; d.img[1] = m.in_f.lo; d.img[2] = m.out_f.hi; d.img[3] = m.out_f.lo;
+      d.img[4] = m.w1_f.hi; d.img[5] = m.w1_f.lo; d.img[6] = m.w2_f.hi; d.img[7] = m.w2_f.lo;
+      d.in_b = lp + lo.in_b; d.out_b = lp + lo.out_b; d.b1 = lp + lo.b1; d.b2 = lp + lo.b2;
+      d.g1 = lp + lo.g1; d.be1 = lp + lo.be1; d.g2 = lp + lo.g2; d.be2 = lp + lo.be2;
+      d.d_attn_p = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr);
+      d.d_attn_out = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_OUT, l), tr);
+      d.d_ffn_h = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_H, l), tr);
+      d.d_ffn_out = make_dropout(p, c->seed, c->step, layer_site(SITE_FFN_OUT, l), tr);
+    }
+    DR4SR_TRY(launch_sasrec_fwd_fused(h, st));
+    if (attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head))   // the per-op tcgen05 attention backward needs its own tiles
+      DR4SR_TRY(launch_attn_tiles(tok_off, c->B, c->L, w.tile_first, st));
+    const float* xl = (q_packed) ? q_packed : w.layer[c->n_layer - 1].x2;
+    DR4SR_TRY(dr4sr_unpack_rows(xl, tok_off, c->B, c->L, D, q_last, q_dense, stream));
+    return DR4SR_OK;
+  }
   {  // K1: gather + positions + dropout
     const Dropout drop = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
     DR4SR_TRY(dr4sr_embed_fwd(table, pos, in_item_id, tok_off, row_seq, counts, c->B, c->L, D, tr ? p : 0.f, c->seed, c->step,

@@ -53,6 +53,10 @@ DR4SR_API const char* dr4sr_last_cuda_error(void);
 DR4SR_API long long dr4sr_launch_count(void);
 DR4SR_API int dr4sr_prof_enable(int on);
 DR4SR_API size_t dr4sr_prof_collect(char* buf, size_t cap);
+/* Debug only: install (null clears) a host-mapped buffer of 4 ints per CTA into which the persistent fused kernels
+ * record the last phase each CTA reached and, if a bounded barrier wait expires (the kernel then traps instead of
+ * hanging the device), which barrier it was: {phase, barrier tag, thread, parity}. */
+DR4SR_API int dr4sr_debug_trace(int* host_mapped);
 
 /* ------------------------------------------------------------------------------------------------
  * Batch preparation: packed-token index from `seqlen`, loss normaliser from `item_id`.
@@ -105,6 +109,10 @@ DR4SR_API int dr4sr_set_gemm_backend(int backend);
  * 1 = tcgen05 tiles of whole sequences (<= 128 rows) with bf16 hi/lo split operands.  Both are parity-tested; the
  * FFMA kernel is the faster one at L = 50 today (profiles/r1_ncu_full_notes.md). */
 DR4SR_API int dr4sr_set_attn_backend(int backend);
+/* Encoder schedule: 1 (default) = persistent fused kernels (one CTA carries a group of whole sequences, <= 128
+ * packed rows, through every layer: gather, QKV, attention, out-proj+LN, FFN+LN on tcgen05) where the shape allows
+ * (D = F = 128, 2 heads); 0 = one kernel per operator.  Both are parity-tested. */
+DR4SR_API int dr4sr_set_fused_backend(int backend);
 
 DR4SR_API size_t dr4sr_sasrec_param_count(const dr4sr_sasrec_cfg* cfg);
 DR4SR_API size_t dr4sr_sasrec_workspace_bytes(const dr4sr_sasrec_cfg* cfg);

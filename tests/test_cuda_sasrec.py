@@ -21,18 +21,21 @@ DEV = 'cuda:0'
 # losses / logits); the FFMA path is additionally held to fp32 round-off.
 TOL = {'tc': dict(fwd=1e-4, loss=1e-4, grad=1e-3, adam=1e-4), 'ffma': dict(fwd=1e-5, loss=1e-5, grad=1e-4, adam=2e-5)}
 TOL['tc_attn'] = TOL['tc']          # tcgen05 dense layers + tcgen05 attention tiles
+TOL['fused'] = TOL['tc']            # persistent fused encoder kernels (default schedule)
 
 
-@pytest.fixture(params=['tc', 'tc_attn', 'ffma'], autouse=True)
+@pytest.fixture(params=['fused', 'tc', 'tc_attn', 'ffma'], autouse=True)
 def backend(request):
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     from dr4sr_b200 import _lib
     _lib.check(_lib.lib().dr4sr_set_gemm_backend(1 if request.param == 'ffma' else 0), 'set_gemm_backend')
     _lib.check(_lib.lib().dr4sr_set_attn_backend(1 if request.param == 'tc_attn' else 0), 'set_attn_backend')
+    _lib.check(_lib.lib().dr4sr_set_fused_backend(1 if request.param == 'fused' else 0), 'set_fused_backend')
     yield request.param
     _lib.lib().dr4sr_set_gemm_backend(0)
     _lib.lib().dr4sr_set_attn_backend(0)
+    _lib.lib().dr4sr_set_fused_backend(1)
 
 
 def _need_gpu():
@@ -338,6 +341,35 @@ def test_dropout_is_deterministic_unbiased_and_consistent_with_backward():
     h = 2e-3
     numeric = (loss_at(h) - loss_at(-h)) / (2 * h)
     assert abs(analytic - numeric) <= 0.03 * max(abs(numeric), 1e-3), (analytic, numeric)
+
+
+def test_fused_schedule_matches_per_op_kernels_with_dropout(backend):
+    """Same (seed, step) => the fused persistent kernels draw exactly the per-op kernels' dropout masks: forward
+    activations, loss and every gradient agree to fp32 round-off at p = 0.5 (B chosen so tiles hold ragged groups)."""
+    _need_gpu()
+    if backend != 'fused':
+        pytest.skip('compares the two schedules once')
+    from dr4sr_b200 import _lib
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    N, D = 3000, 128
+    m = make_model(N, D, p=0.5).train()
+    batch = to_dev(synthetic_batch(97, 50, N, seed=21))
+    out = {}
+    for fused in (1, 0):
+        _lib.check(_lib.lib().dr4sr_set_fused_backend(fused), 'set_fused_backend')
+        m.engine.step = 40
+        m.optimizer.zero_grad()
+        loss = m.training_step(batch)
+        loss.backward()
+        out[fused] = (float(loss), m.engine.buffers(97).q_packed.clone(),
+                      [p.grad.clone() for p in m.query_encoder.flat_parameters()], m.item_embedding.weight.grad.clone())
+    _lib.lib().dr4sr_set_fused_backend(1)
+    n = int(m.engine.buffers(97).counts[0])
+    assert abs(out[1][0] - out[0][0]) / abs(out[0][0]) < 1e-5
+    assert rel_err(out[1][1][:n].cpu(), out[0][1][:n].cpu()) < 2e-5
+    for a, b_ in zip(out[1][2], out[0][2]):
+        assert rel_err(a.cpu(), b_.cpu()) < 2e-4
+    assert rel_err(out[1][3].cpu(), out[0][3].cpu()) < 2e-4
 
 
 def test_neg_sampling_range_uniformity_determinism():

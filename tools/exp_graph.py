@@ -52,3 +52,20 @@ g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g, stream=s):
     raw_step()
 print('graph replay      ms/step', round(timeit(g.replay), 4))
+
+# ---- attention backend comparison (raw engine calls + per-kernel profile) ----
+import ctypes
+lib = E._lib.lib()
+for backend in (0, 1):
+    lib.dr4sr_set_attn_backend(backend)
+    print(f'attn backend {backend}: raw ms/step', round(timeit(raw_step), 4))
+    lib.dr4sr_prof_enable(1)
+    for _ in range(20): raw_step()
+    torch.cuda.synchronize()
+    lib.dr4sr_prof_enable(0)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.dr4sr_prof_collect(buf, len(buf))
+    for line in buf.value.decode().strip().splitlines():
+        name, cnt, tot = line.split(',')
+        if 'attn' in name: print('   ', name, cnt, round(float(tot) / 20 * 1000, 1), 'us/step')
+lib.dr4sr_set_attn_backend(0)
