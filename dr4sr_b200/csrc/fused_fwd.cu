@@ -46,9 +46,12 @@ __device__ __forceinline__ uint64_t mn_desc16(uint32_t smem_addr) {   // MN-majo
 // A wait that would spin forever (a protocol bug) traps instead of hanging the GPU; when a host-mapped trace
 // buffer is installed (dr4sr_debug_trace), thread 0 of every CTA also records the last phase it reached.
 __device__ int* g_trace = nullptr;
-__device__ __forceinline__ void trace(int code) {
-  if (g_trace && threadIdx.x == 0) { volatile int* t = g_trace; t[blockIdx.x * 4] = code; }
-}
+#ifdef DR4SR_TRACE   // timeline of the first 8 CTAs: (code, cycles since CTA start) pairs kept in shared memory, dumped at exit
+#define TRACE(code) do { if (threadIdx.x == 0 && c.tr_n < 126) { c.tr_buf[2 * c.tr_n] = (code); \
+    c.tr_buf[2 * c.tr_n + 1] = (int)(clock64() - c.tr_t0); ++c.tr_n; } } while (0)
+#else
+#define TRACE(code) do { } while (0)
+#endif
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -111,15 +114,25 @@ __global__ void __launch_bounds__(1024) fused_tiles_kernel(const int32_t* __rest
 }
 
 // ---- shared state of one CTA -------------------------------------------------------------------------
+// TMEM (256 columns): [0,128) accumulator (GEMMs, scores S, attention output over the dead S), [128,256) the fp32
+// residual stream of the tile ("park": x0 / x1 / x2 rows, read back by the LayerNorm epilogues instead of HBM).
 struct Ctx {
   uint8_t* smem;            // 1 KB aligned dynamic smem: [0,64K) A / Q,K / P images, [64K,96K) weight ring / V images
   uint64_t *full, *empty;   // [2] weight-ring barriers
   uint64_t* acc;            // accumulator-ready barrier
-  uint32_t tmem;            // TMEM base (256 columns)
+  uint32_t tmem;            // TMEM base
   uint32_t fetched, used;   // weight-ring counters (meaningful in thread 0 only)
   uint32_t n_acc;           // completed phases of `acc` (uniform across the CTA)
   int r0, R;                // packed rows [r0, r0 + R) of the tile
+  // this thread's epilogue identity: tile row quad*32+lane, 64-column half warp>>2
+  int row, half, m;
+  bool live;
+  uint32_t trow;            // TMEM address of (row's lane group, column half*64)
+#ifdef DR4SR_TRACE
+  int tr_n; long long tr_t0; int* tr_buf;
+#endif
 };
+constexpr uint32_t kPark = 128;
 
 __device__ __forceinline__ uint8_t* a_hi(const Ctx& c, int kb) { return c.smem + (uint32_t)kb * kImg; }
 __device__ __forceinline__ uint8_t* a_lo(const Ctx& c, int kb) { return c.smem + (uint32_t)(2 + kb) * kImg; }
@@ -145,16 +158,17 @@ __device__ __forceinline__ void prefetch_chunk(Ctx& c, const uint16_t* hi, const
   ring_fetch(c, piece_src(hi, lo, N_total, n0, 1));
 }
 
-// thread 0: acc[128 x 128] (TMEM columns acc_col..+127) = A (hi/lo images in smem, K = 128) x W[n0..n0+127, :]^T.
-// The first two pieces of the chunk must already be in flight (prefetch_chunk).  `nhi/nlo != null`: the first two
+// thread 0: acc[128 x 128] (TMEM columns [0,128)) = A (hi/lo images in smem, K = 128) x W[n0..n0+127, :]^T.
+// The first two pieces of the chunk must already be in flight (prefetch_chunk).  `nhi != null`: the first two
 // pieces of the NEXT chunk are queued as soon as ring slots free up.
-__device__ __forceinline__ void issue_chunk(Ctx& c, const uint16_t* hi, const uint16_t* lo, int N_total, int n0, uint32_t acc_col,
-                                            const uint16_t* nhi, const uint16_t* nlo, int nN_total, int nn0) {
-  const uint32_t acc = c.tmem + acc_col;
+__device__ __noinline__ void issue_chunk(Ctx& c, const uint16_t* hi, const uint16_t* lo, int N_total, int n0,
+                                         const uint16_t* nhi, const uint16_t* nlo, int nN_total, int nn0) {
+  const uint32_t acc = c.tmem;
 #pragma unroll 1
   for (int p = 0; p < 4; ++p) {
     const uint32_t slot = c.used & 1u, use = c.used >> 1;
     mbar_wait_b(&c.full[slot], use & 1u, 200 + (int)slot);
+    TRACE(2000 + p);
     tc_fence_after();
     const int kb = p >> 1;
     const uint32_t b = smem_u32(ring(c, slot)), ah = smem_u32(a_hi(c, kb)), al = smem_u32(a_lo(c, kb));
@@ -174,45 +188,118 @@ __device__ __forceinline__ void issue_chunk(Ctx& c, const uint16_t* hi, const ui
     }
     umma_commit(&c.empty[slot]);
     ++c.used;
-    if (p + 2 < 4) ring_fetch(c, piece_src(hi, lo, N_total, n0, p + 2));
+    if (p + 2 < 4) { ring_fetch(c, piece_src(hi, lo, N_total, n0, p + 2)); TRACE(2010 + p); }
   }
   umma_commit(c.acc);
   if (nhi) prefetch_chunk(c, nhi, nlo, nN_total, nn0);
+  TRACE(2020);
 }
 
 // all threads: wait for the accumulator committed by the most recent issue
 __device__ __forceinline__ void wait_acc(Ctx& c) {
+  __syncwarp();                                   // lanes 1..31 of warp 0 park here while lane 0 issues (no spinning beside it)
   mbar_wait_b(c.acc, c.n_acc & 1u, 300);
   ++c.n_acc;
   tc_fence_after();
 }
 
-// 32 fp32 values of tile row `row`, columns [32 qc, 32 qc + 32) of a 128-wide operand -> hi / lo images
+// ---- TMEM 16-column accessors (thread = its own lane's row) ---------------------------------------------------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// two 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, float* va, uint32_t tb, float* vb) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(va);
+  uint32_t* q = reinterpret_cast<uint32_t*>(vb);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]),
+        "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(tb));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// ---- bf16 hi/lo split with packed conversions (bit-identical to split_bf16x8) -------------------------------------
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {   // a -> low half, b -> high half
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ha = __uint_as_float(hi << 16), hb = __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+}
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  split2(x[0], x[1], hi.x, lo.x); split2(x[2], x[3], hi.y, lo.y);
+  split2(x[4], x[5], hi.z, lo.z); split2(x[6], x[7], hi.w, lo.w);
+}
+// 16 fp32 values of tile row `row`, columns [n0, n0 + 16) (n0 % 16 == 0) of a 128-wide operand -> hi / lo images
 // laid out as [hi kb0, hi kb1, lo kb0, lo kb1] from `base`
-__device__ __forceinline__ void store_row_image(const float* v, int row, int qc, uint8_t* base) {
+__device__ __forceinline__ void store_image16(const float* v, int row, int n0, uint8_t* base) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 2; ++q) {
     uint4 h, l;
-    split_bf16x8(make_float4(v[q * 8], v[q * 8 + 1], v[q * 8 + 2], v[q * 8 + 3]),
-                 make_float4(v[q * 8 + 4], v[q * 8 + 5], v[q * 8 + 6], v[q * 8 + 7]), h, l);
-    const uint32_t off = (uint32_t)(qc >> 1) * kImg + sw128_offset((uint32_t)row, (uint32_t)((qc & 1) * 32 + q * 8));
+    split8(v + q * 8, h, l);
+    const int n = n0 + q * 8;
+    const uint32_t off = (uint32_t)(n >> 6) * kImg + sw128_offset((uint32_t)row, (uint32_t)(n & 63));
     *reinterpret_cast<uint4*>(base + off) = h;
     *reinterpret_cast<uint4*>(base + 2 * kImg + off) = l;
   }
 }
-__device__ __forceinline__ void store_row_zero(int row, int qc, uint8_t* base) {
+__device__ __forceinline__ void store_image16_zero(int row, int n0, uint8_t* base) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint32_t off = (uint32_t)(qc >> 1) * kImg + sw128_offset((uint32_t)row, (uint32_t)((qc & 1) * 32 + q * 8));
+  for (int q = 0; q < 2; ++q) {
+    const int n = n0 + q * 8;
+    const uint32_t off = (uint32_t)(n >> 6) * kImg + sw128_offset((uint32_t)row, (uint32_t)(n & 63));
     *reinterpret_cast<uint4*>(base + off) = make_uint4(0u, 0u, 0u, 0u);
     *reinterpret_cast<uint4*>(base + 2 * kImg + off) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
+// ---- dropout factors of one 128-wide row (idx = m * 128 + n): same draws as Dropout::factor4, with the row part
+// of draw32 -- mix32(key ^ (pair_index >> 7)) = mix32(key ^ (m >> 1)) -- hoisted out of the element loop ----------
+struct RowDrop {
+  uint32_t key, rk, thresh, base;   // base = pair index of the row's first element (m * 64)
+  float scale;
+  __device__ __forceinline__ void init(const Dropout& d, uint32_t m) {
+    key = d.key; thresh = d.thresh; scale = d.scale; base = m * 64u; rk = mix32(d.key ^ (m >> 1));
+  }
+  // f[j] = factor of column n0 + j, j < 16, n0 % 2 == 0
+  __device__ __forceinline__ void factors16(int n0, float* f) const {
+    if (thresh == 0u) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = scale;
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const uint32_t h = mix32((base + (uint32_t)((n0 + j) >> 1)) * 0x9E3779B1u + key) ^ rk;
+      f[j] = (h & 0xFFFFu) >= thresh ? scale : 0.f;
+      f[j + 1] = (h >> 16) >= thresh ? scale : 0.f;
+    }
+  }
+};
+
 // fp32 [R x 128] rows (row stride ld) from global -> A images (rows >= R zero)
 __device__ __forceinline__ void stage_a_global(const Ctx& c, const float* src, int ld) {
   const int chunk = threadIdx.x & 15, rsub = threadIdx.x >> 4;     // 16 chunks of 8 floats, 16 rows per pass
-#pragma unroll
+#pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     float4 v[4][2];
 #pragma unroll
@@ -229,8 +316,9 @@ __device__ __forceinline__ void stage_a_global(const Ctx& c, const float* src, i
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int row = (half * 4 + it) * 16 + rsub;
+      const float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
       uint4 h, l;
-      split_bf16x8(v[it][0], v[it][1], h, l);
+      split8(x, h, l);
       const uint32_t off = (uint32_t)(chunk >> 3) * kImg + sw128_offset((uint32_t)row, (uint32_t)((chunk & 7) * 8));
       *reinterpret_cast<uint4*>(c.smem + off) = h;
       *reinterpret_cast<uint4*>(c.smem + 2 * kImg + off) = l;
@@ -238,33 +326,40 @@ __device__ __forceinline__ void stage_a_global(const Ctx& c, const float* src, i
   }
 }
 
-// fp32 head slice [R x 64] (row stride ld) -> one hi / lo image pair (rows >= R zero)
-__device__ __forceinline__ void stage_head(const Ctx& c, const float* src, int ld, uint8_t* hi, uint8_t* lo) {
+// fp32 head slices Q, K, V [R x 64] of the packed qkv rows -> their hi / lo image pairs (rows >= R zero)
+__device__ __forceinline__ void stage_heads(const Ctx& c, const float* qkv_head) {
   const int chunk = threadIdx.x & 7, rsub = threadIdx.x >> 3;      // 32 rows per pass
-  float4 v[4][2];
+#pragma unroll 1
+  for (int which = 0; which < 3; ++which) {                        // Q, K, V
+    const float* src = qkv_head + which * 128;
+    uint8_t* hi = c.smem + (uint32_t)(2 * which) * kImg;           // q_hi, q_lo, k_hi, k_lo, v_hi, v_lo
+    uint8_t* lo = hi + kImg;
+    float4 v[4][2];
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int row = it * 32 + rsub;
-    if (row < c.R) {
-      const float* p = src + (size_t)row * ld + chunk * 8;
-      v[it][0] = *reinterpret_cast<const float4*>(p);
-      v[it][1] = *reinterpret_cast<const float4*>(p + 4);
-    } else {
-      v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 32 + rsub;
+      if (row < c.R) {
+        const float* p = src + (size_t)row * 384 + chunk * 8;
+        v[it][0] = *reinterpret_cast<const float4*>(p);
+        v[it][1] = *reinterpret_cast<const float4*>(p + 4);
+      } else {
+        v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-  }
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int row = it * 32 + rsub;
-    uint4 h, l;
-    split_bf16x8(v[it][0], v[it][1], h, l);
-    const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)(chunk * 8));
-    *reinterpret_cast<uint4*>(hi + off) = h;
-    *reinterpret_cast<uint4*>(lo + off) = l;
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 32 + rsub;
+      const float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
+      uint4 h, l;
+      split8(x, h, l);
+      const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)(chunk * 8));
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
   }
 }
 
-// make generic-proxy smem writes visible to the tensor core, order TMEM reads before later UMMAs, CTA barrier
+// make generic-proxy smem writes visible to the tensor core, order TMEM accesses before later UMMAs, CTA barrier
 __device__ __forceinline__ void sync_for_mma() {
   fence_async_smem();
   tc_fence_before();
@@ -272,119 +367,133 @@ __device__ __forceinline__ void sync_for_mma() {
   tc_fence_after();
 }
 
-// ---- epilogues (thread = tile row `quad*32+lane`, 64-column half `warp>>2`) -----------------------------
-// out[row, n] = acc + bias[n]   (optionally: next A operand = dropout(gelu(out)))
-template <bool GELU_STAGE>
-__device__ __forceinline__ void epi_linear(const Ctx& c, uint32_t acc_col, const float* bias, float* out, int ldo, const Dropout& dh) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane, m = c.r0 + row;
-  const bool live = row < c.R;
-  const uint32_t trow = c.tmem + ((uint32_t)(quad * 32) << 16) + acc_col + (uint32_t)(half * 64);
+// ---- epilogues (thread = tile row me.row, columns me.half*64 .. +63) --------------------------------------------
+struct Me { int row, half, m; bool live; uint32_t trow; uint8_t* smem; };   // passed by value: stays in registers
+__device__ __forceinline__ Me me_of(const Ctx& c) { return Me{c.row, c.half, c.m, c.live, c.trow, c.smem}; }
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// wait for every outstanding tcgen05.ld; the "+r" ties keep the consumers of v[0..16) behind the wait
+__device__ __forceinline__ void tmem_ld_fence(float* v, bool wait) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  if (wait) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+  } else {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
+  }
+}
+
+// out[row, n] = acc + bias[n]; gelu_stage: the next A operand = dropout(gelu(out)) goes straight to shared memory
+__device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, int ldo, bool gelu_stage, Dropout dh) {
+  RowDrop rd;
+  rd.init(dh, (uint32_t)me.m);
+  float* orow = out + (size_t)me.m * ldo + me.half * 64;
 #pragma unroll 1
-  for (int q = 0; q < 2; ++q) {
+  for (int g = 0; g < 2; ++g) {
+    const int n0 = me.half * 64 + g * 32;
     float v[32];
-    tmem_ld32(trow + (uint32_t)(q * 32), v);
-    const int nb = half * 64 + q * 32;
+    tmem_ld16_nowait(me.trow + (uint32_t)(g * 32), v);
+    tmem_ld16_nowait(me.trow + (uint32_t)(g * 32 + 16), v + 16);
+    tmem_ld_fence(v, true);
+    tmem_ld_fence(v + 16, false);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 bb = *reinterpret_cast<const float4*>(bias + nb + j);
+      const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + j);
       v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-      if (live) *reinterpret_cast<float4*>(out + (size_t)m * ldo + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      if (me.live) *reinterpret_cast<float4*>(orow + g * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    if (GELU_STAGE) {
+    if (gelu_stage) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 f = dh.factor4((uint32_t)m * 128u + (uint32_t)(nb + j));
-        v[j] = gelu_f(v[j]) * f.x; v[j + 1] = gelu_f(v[j + 1]) * f.y;
-        v[j + 2] = gelu_f(v[j + 2]) * f.z; v[j + 3] = gelu_f(v[j + 3]) * f.w;
+      for (int q = 0; q < 2; ++q) {
+        float f[16];
+        rd.factors16(n0 + q * 16, f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[q * 16 + j] = gelu_f(v[q * 16 + j]) * f[j];
+        store_image16(v + q * 16, me.row, n0 + q * 16, me.smem);
       }
-      if (live) store_row_image(v, row, half * 2 + q, c.smem);
-      else store_row_zero(row, half * 2 + q, c.smem);
     }
   }
 }
 
-// z = dropout(acc + bias) + res ; y = LayerNorm(z) -> Z, stats, Y (global) and, if STAGE, the next A operand
-template <bool STAGE>
-__device__ __forceinline__ void epi_ln(const Ctx& c, uint32_t acc_col, const float* bias, const float* res, const Dropout& de,
-                                       const float* gamma, const float* beta, float eps, float* Z, float* stats, float* Y,
-                                       float (*ln_part)[128]) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane, m = c.r0 + row;
-  const bool live = row < c.R;
-  const uint32_t trow = c.tmem + ((uint32_t)(quad * 32) << 16) + acc_col + (uint32_t)(half * 64);
+// z = dropout(acc + bias) + residual(park) ; y = LayerNorm(z) -> Z, stats, Y (global), park <- y and, if stage, the
+// next A operand.  The thread keeps its 64 z values in registers: one pass over TMEM.  s_b / s_g / s_be: bias, gamma,
+// beta in shared memory.
+__device__ __noinline__ void epi_ln(Me me, const float* s_b, const float* s_g, const float* s_be, Dropout de, float eps, float* Z,
+                                    float* stats, float* Y, bool stage, float (*ln_part)[128]) {
+  RowDrop rd;
+  rd.init(de, (uint32_t)me.m);
+  float z[64];
   float sum = 0.f;
-#pragma unroll 1
-  for (int q = 0; q < 2; ++q) {
-    float v[32];
-    tmem_ld32(trow + (uint32_t)(q * 32), v);
-    const int nb = half * 64 + q * 32;
+  float* zrow = Z + (size_t)me.m * 128 + me.half * 64;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const int n = nb + j;
-      const float4 bb = *reinterpret_cast<const float4*>(bias + n);
-      float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) rr = *reinterpret_cast<const float4*>(res + (size_t)m * 128 + n);
-      const float4 f = de.factor4((uint32_t)m * 128u + (uint32_t)n);
-      v[j] = (v[j] + bb.x) * f.x + rr.x;
-      v[j + 1] = (v[j + 1] + bb.y) * f.y + rr.y;
-      v[j + 2] = (v[j + 2] + bb.z) * f.z + rr.z;
-      v[j + 3] = (v[j + 3] + bb.w) * f.w + rr.w;
-      sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-      if (live) *reinterpret_cast<float4*>(Z + (size_t)m * 128 + n) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  for (int g = 0; g < 4; ++g) {
+    const int n0 = me.half * 64 + g * 16;
+    float r[16], f[16];
+    tmem_ld16_nowait(me.trow + (uint32_t)(g * 16), z + g * 16);
+    tmem_ld16_nowait(me.trow + kPark + (uint32_t)(g * 16), r);
+    rd.factors16(n0, f);
+    tmem_ld_fence(z + g * 16, true);
+    tmem_ld_fence(r, false);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      z[g * 16 + j] = (z[g * 16 + j] + s_b[n0 + j]) * f[j] + r[j];
+      sum += z[g * 16 + j];
     }
-    tmem_st32(trow + (uint32_t)(q * 32), v);
+    if (me.live) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(zrow + g * 16 + j) = make_float4(z[g * 16 + j], z[g * 16 + j + 1], z[g * 16 + j + 2], z[g * 16 + j + 3]);
+    }
   }
-  ln_part[half][row] = sum;
+  ln_part[me.half][me.row] = sum;
   __syncthreads();
-  const float mu = (ln_part[0][row] + ln_part[1][row]) * (1.0f / 128.0f);
+  const float mu = (ln_part[0][me.row] + ln_part[1][me.row]) * (1.0f / 128.0f);
   __syncthreads();
   float var = 0.f;
-#pragma unroll 1
-  for (int q = 0; q < 2; ++q) {
-    float v[32];
-    tmem_ld32(trow + (uint32_t)(q * 32), v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; var = fmaf(d, d, var); }
-  }
-  ln_part[half][row] = var;
+  for (int j = 0; j < 64; ++j) { const float d = z[j] - mu; var = fmaf(d, d, var); }
+  ln_part[me.half][me.row] = var;
   __syncthreads();
-  const float rstd = rsqrtf((ln_part[0][row] + ln_part[1][row]) * (1.0f / 128.0f) + eps);
-#pragma unroll 1
-  for (int q = 0; q < 2; ++q) {
-    float v[32];
-    tmem_ld32(trow + (uint32_t)(q * 32), v);
-    const int nb = half * 64 + q * 32;
+  const float rstd = rsqrtf((ln_part[0][me.row] + ln_part[1][me.row]) * (1.0f / 128.0f) + eps);
+  float* yrow = Y + (size_t)me.m * 128 + me.half * 64;
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const int n = nb + j;
-      const float4 gg = *reinterpret_cast<const float4*>(gamma + n);
-      const float4 be = *reinterpret_cast<const float4*>(beta + n);
-      v[j] = (v[j] - mu) * rstd * gg.x + be.x; v[j + 1] = (v[j + 1] - mu) * rstd * gg.y + be.y;
-      v[j + 2] = (v[j + 2] - mu) * rstd * gg.z + be.z; v[j + 3] = (v[j + 3] - mu) * rstd * gg.w + be.w;
-      if (live) *reinterpret_cast<float4*>(Y + (size_t)m * 128 + n) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  for (int g = 0; g < 4; ++g) {
+    const int n0 = me.half * 64 + g * 16;
+    float* v = z + g * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = (v[j] - mu) * rstd * s_g[n0 + j] + s_be[n0 + j];
+    if (me.live) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(yrow + g * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    if (STAGE) {
-      if (live) store_row_image(v, row, half * 2 + q, c.smem);
-      else store_row_zero(row, half * 2 + q, c.smem);
-    }
+    tmem_st16(me.trow + kPark + (uint32_t)(g * 16), v);
+    if (stage) store_image16(v, me.row, n0, me.smem);
   }
-  if (live && half == 0) { stats[2 * m] = mu; stats[2 * m + 1] = rstd; }
+  if (me.live && me.half == 0) { stats[2 * me.m] = mu; stats[2 * me.m + 1] = rstd; }
 }
 
 // ---- attention of one head over the tile (block-diagonal causal mask) -----------------------------------
 __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, const FusedLayer& y, int h, const int* s_start,
                                                const int* s_seq, const int* s_pad, float (*s_x)[128]) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, quad = warp & 3, half = warp >> 2;
-  const int row = quad * 32 + lane;
-  const bool live = row < c.R;
+  const int tid = threadIdx.x;
   uint8_t *q_hi = c.smem, *q_lo = c.smem + kImg, *k_hi = c.smem + 2 * kImg, *k_lo = c.smem + 3 * kImg;
   uint8_t *v_hi = c.smem + 4 * kImg, *v_lo = c.smem + 5 * kImg;
-  const float* base = y.qkv + (size_t)c.r0 * 384 + h * 64;
-  stage_head(c, base, 384, q_hi, q_lo);
-  stage_head(c, base + 128, 384, k_hi, k_lo);
-  stage_head(c, base + 256, 384, v_hi, v_lo);
+  stage_heads(c, y.qkv + (size_t)c.r0 * 384 + h * 64);
   sync_for_mma();
+  TRACE(1000 + 10 * h + 1);
   if (tid == 0) {                                             // S = Q K^T -> TMEM columns [0,128)
     const uint32_t ah = smem_u32(q_hi), al = smem_u32(q_lo), bh = smem_u32(k_hi), bl = smem_u32(k_lo);
 #pragma unroll
@@ -397,91 +506,110 @@ __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, co
     umma_commit(c.acc);
   }
   wait_acc(c);
-  const uint32_t trow = c.tmem + ((uint32_t)(quad * 32) << 16);
-  const int start = s_start[row];
-  // keys of this row: [start, row] minus pads.  Quarter qc (32 keys) is live for the row when it intersects that window.
-  bool mine[2], any[2];
+  TRACE(1000 + 10 * h + 2);
+  const int row = c.row, start = s_start[row];
+  // keys of this row: [start, row] minus pads.  A group of 16 keys is visited when it intersects the window of some
+  // row of the warp (warp-uniform, tcgen05.ld is warp-collective).
+  uint32_t live_groups = 0;
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int qc = half * 2 + q;
-    mine[q] = live && start <= qc * 32 + 31 && row >= qc * 32;
-    any[q] = __any_sync(0xffffffffu, mine[q]);
+  for (int g = 0; g < 4; ++g) {
+    const int c0 = c.half * 64 + g * 16;
+    const bool mine = c.live && start <= c0 + 15 && row >= c0;
+    if (__any_sync(0xffffffffu, mine)) live_groups |= 1u << g;
   }
   float mx = -INFINITY;
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    if (!(live_groups >> g & 1u)) continue;
+    const int c0 = c.half * 64 + g * 16;
+    float s[16];
+    tmem_ld16(c.trow + (uint32_t)(g * 16), s);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    if (!any[q]) continue;
-    const int qc = half * 2 + q;
-    float s[32];
-    tmem_ld32(trow + (uint32_t)(qc * 32), s);
-    if (mine[q]) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int key = qc * 32 + j;
-        const bool ok = key >= start && key <= row && !s_pad[key];
-        mx = fmaxf(mx, ok ? s[j] * a.scale : -INFINITY);
-      }
+    for (int j = 0; j < 16; ++j) {
+      const int key = c0 + j;
+      const bool ok = c.live && key >= start && key <= row && !s_pad[key];
+      mx = fmaxf(mx, ok ? s[j] * a.scale : -INFINITY);
     }
   }
-  s_x[half][row] = mx;
+  s_x[c.half][row] = mx;
   __syncthreads();
   mx = fmaxf(s_x[0][row], s_x[1][row]);
   __syncthreads();
   // P' = dropout(exp(s - max)) un-normalised (the 1/sum is applied to the output rows), written over the dead Q / K images
   float sum = 0.f;
+  const Dropout& dp = y.d_attn_p;
   const uint32_t dbase = (uint32_t)(s_seq[row] * 2 + h) * (uint32_t)(a.L * a.L) + (uint32_t)(row - start) * (uint32_t)a.L;
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    const int c0 = c.half * 64 + g * 16;
+    if (!(live_groups >> g & 1u)) { store_image16_zero(row, c0, c.smem); continue; }
+    float s[16];
+    tmem_ld16(c.trow + (uint32_t)(g * 16), s);
+    // dropout draws of elements idx0 .. idx0 + 15: element i uses half-word (i & 1) of draw32(key, i >> 1)
+    const uint32_t idx0 = dbase + (uint32_t)(c0 - start);
+    uint32_t e16[8];
+    if (dp.thresh != 0u) {
+      const uint32_t p0 = idx0 >> 1, odd = idx0 & 1u;
+      uint32_t d[9];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int qc = half * 2 + q;
-    if (any[q]) {
-      float s[32];
-      tmem_ld32(trow + (uint32_t)(qc * 32), s);
-      if (mine[q] && mx > -INFINITY) {
+      for (int k = 0; k < 9; ++k) d[k] = draw32(dp.key, p0 + (uint32_t)k);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = qc * 32 + j;
-          const bool ok = key >= start && key <= row && !s_pad[key];
-          const float e = ok ? expf(s[j] * a.scale - mx) : 0.f;
-          sum += e;
-          s[j] = ok ? y.d_attn_p.apply(e, dbase + (uint32_t)(key - start)) : 0.f;
-        }
-        store_row_image(s, row, qc, c.smem);
-      } else {
-        store_row_zero(row, qc, c.smem);
-      }
-    } else {
-      store_row_zero(row, qc, c.smem);
+      for (int k = 0; k < 8; ++k) e16[k] = odd ? __funnelshift_r(d[k], d[k + 1], 16) : d[k];
     }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int key = c0 + j;
+      const bool ok = c.live && key >= start && key <= row && !s_pad[key] && mx > -INFINITY;
+      const float e = ok ? expf(s[j] * a.scale - mx) : 0.f;
+      sum += e;
+      float f = dp.scale;
+      if (dp.thresh != 0u) {
+        const uint32_t hw = (j & 1) ? (e16[j >> 1] >> 16) : (e16[j >> 1] & 0xFFFFu);
+        f = hw >= dp.thresh ? dp.scale : 0.f;
+      }
+      s[j] = e * f;
+    }
+    store_image16(s, row, c0, c.smem);
   }
-  s_x[half][row] = sum;
+  s_x[c.half][row] = sum;
   sync_for_mma();
-  if (tid == 0) {                                             // O = P' V -> TMEM columns [128,192): A = P' K-major, B = V MN-major
+  TRACE(1000 + 10 * h + 3);
+  if (tid == 0) {                                             // O = P' V -> TMEM columns [0,64) (over the dead scores)
     const uint32_t ah = smem_u32(c.smem), al = smem_u32(c.smem + 2 * kImg), bh = smem_u32(v_hi), bl = smem_u32(v_lo);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {                             // 16 keys per UMMA
       const uint32_t ao = (uint32_t)(k >> 2) * kImg + (uint32_t)(k & 3) * 32u, bo = (uint32_t)k * 2048u;
-      umma_bf16(c.tmem + 128, sw128_desc(ah + ao), mn_desc16(bh + bo), kIdescN64_K_MN, k > 0 ? 1u : 0u);
-      umma_bf16(c.tmem + 128, sw128_desc(ah + ao), mn_desc16(bl + bo), kIdescN64_K_MN, 1u);
-      umma_bf16(c.tmem + 128, sw128_desc(al + ao), mn_desc16(bh + bo), kIdescN64_K_MN, 1u);
+      umma_bf16(c.tmem, sw128_desc(ah + ao), mn_desc16(bh + bo), kIdescN64_K_MN, k > 0 ? 1u : 0u);
+      umma_bf16(c.tmem, sw128_desc(ah + ao), mn_desc16(bl + bo), kIdescN64_K_MN, 1u);
+      umma_bf16(c.tmem, sw128_desc(al + ao), mn_desc16(bh + bo), kIdescN64_K_MN, 1u);
     }
     umma_commit(c.acc);
   }
   wait_acc(c);
+  TRACE(1000 + 10 * h + 4);
   {
     const float tot = s_x[0][row] + s_x[1][row];
     const float inv = tot > 0.f ? 1.0f / tot : 0.f;
-    float o[32];
-    tmem_ld32(trow + 128u + (uint32_t)(half * 32), o);
-    if (live) {
-      float* dst = y.attn + (size_t)(c.r0 + row) * 128 + h * 64 + half * 32;
+    const uint32_t to = c.trow - (uint32_t)(c.half * 64) + (uint32_t)(c.half * 32);   // this thread's 32 of the 64 output columns
+    float* dst = y.attn + (size_t)c.m * 128 + h * 64 + c.half * 32;
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+      float o[16];
+      tmem_ld16(to + (uint32_t)(g * 16), o);
+      if (c.live) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(dst + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(dst + g * 16 + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();                                            // smem images, s_x and TMEM are free again
 }
+
+// per-layer small parameters staged in shared memory (floats): in_b[384] out_b b1 b2 g1 be1 g2 be2 [128 each]
+constexpr int kParIn = 0, kParOut = 384, kParB1 = 512, kParB2 = 640, kParG1 = 768, kParBe1 = 896, kParG2 = 1024, kParBe2 = 1152,
+              kParTotal = 1280;
 
 __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_constant__ FusedFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -489,6 +617,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
   __shared__ uint32_t tmem_slot;
   __shared__ int s_start[128], s_seq[128], s_pad[128], s_id[128];
   __shared__ float s_x[2][128];
+  __shared__ __align__(16) float s_par[kParTotal];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = a.tiles[0];
   if ((int)blockIdx.x >= n_tiles) return;
@@ -497,6 +626,10 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
   c.smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   c.full = &bars[0]; c.empty = &bars[2]; c.acc = &bars[4];
   c.fetched = 0; c.used = 0; c.n_acc = 0;
+#ifdef DR4SR_TRACE
+  __shared__ int s_trace[256];
+  c.tr_n = 0; c.tr_t0 = clock64(); c.tr_buf = s_trace;
+#endif
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
@@ -506,12 +639,18 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   c.tmem = tmem_slot;
+  c.row = (warp & 3) * 32 + lane;
+  c.half = warp >> 2;
+  c.trow = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c.half * 64);
 
+#pragma unroll 1
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int b0 = a.tiles[1 + tile], b1 = a.tiles[2 + tile];
     c.r0 = a.tok_off[b0];
     c.R = a.tok_off[b1] - c.r0;
     if (c.R <= 0) continue;                                   // CTA-uniform
+    c.live = c.row < c.R;
+    c.m = c.r0 + c.row;
     // ---- row metadata (same for every layer and head) ----
     if (tid < 128) {
       int st = 0, sq = 0, pd = 1, id = 0;
@@ -524,95 +663,119 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       }
       s_start[tid] = st; s_seq[tid] = sq; s_pad[tid] = pd; s_id[tid] = id;
     }
-    trace(1);
+    TRACE(1);
     if (tid == 0) prefetch_chunk(c, a.layer[0].in_hi, a.layer[0].in_lo, 384, 0);
     __syncthreads();
-    trace(2);
-    // ---- x0 = dropout(E[id] + P[t]) -> global (backward needs it) and the first A operand ----
+    // ---- x0 = dropout(E[id] + P[t]) -> global (the backward needs it), park (residual) and the first A operand ----
     {
-      const int chunk = tid & 15, rsub = tid >> 4;
-#pragma unroll 2
-      for (int it = 0; it < 8; ++it) {
-        const int row = it * 16 + rsub;
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (row < c.R) {
-          const int m = c.r0 + row;
-          const float* e = a.table + (size_t)s_id[row] * 128 + chunk * 8;
-          const float* p = a.pos + (size_t)(row - s_start[row]) * 128 + chunk * 8;
-          v0 = *reinterpret_cast<const float4*>(e); v1 = *reinterpret_cast<const float4*>(e + 4);
-          const float4 p0 = *reinterpret_cast<const float4*>(p), p1 = *reinterpret_cast<const float4*>(p + 4);
-          const uint32_t idx = (uint32_t)m * 128u + (uint32_t)(chunk * 8);
-          const float4 f0 = a.d_embed.factor4(idx), f1 = a.d_embed.factor4(idx + 4);
-          v0.x = (v0.x + p0.x) * f0.x; v0.y = (v0.y + p0.y) * f0.y; v0.z = (v0.z + p0.z) * f0.z; v0.w = (v0.w + p0.w) * f0.w;
-          v1.x = (v1.x + p1.x) * f1.x; v1.y = (v1.y + p1.y) * f1.y; v1.z = (v1.z + p1.z) * f1.z; v1.w = (v1.w + p1.w) * f1.w;
-          float* dst = a.x0 + (size_t)m * 128 + chunk * 8;
-          *reinterpret_cast<float4*>(dst) = v0; *reinterpret_cast<float4*>(dst + 4) = v1;
+      RowDrop rd;
+      rd.init(a.d_embed, (uint32_t)c.m);
+      const float* e = a.table + (size_t)s_id[c.row] * 128 + c.half * 64;
+      const float* p = a.pos + (size_t)(c.row - s_start[c.row]) * 128 + c.half * 64;
+      float4 ev[16];                                            // the thread's 64 table floats: every load in flight at once
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ev[j] = c.live ? *reinterpret_cast<const float4*>(e + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n0 = c.half * 64 + g * 16;
+        float v[16], f[16];
+        if (c.live) {
+          rd.factors16(n0, f);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 pv = *reinterpret_cast<const float4*>(p + g * 16 + j);
+            const float4 x = ev[g * 4 + j / 4];
+            v[j] = (x.x + pv.x) * f[j]; v[j + 1] = (x.y + pv.y) * f[j + 1];
+            v[j + 2] = (x.z + pv.z) * f[j + 2]; v[j + 3] = (x.w + pv.w) * f[j + 3];
+            *reinterpret_cast<float4*>(a.x0 + (size_t)c.m * 128 + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
         }
-        uint4 hh, ll;
-        split_bf16x8(v0, v1, hh, ll);
-        const uint32_t off = (uint32_t)(chunk >> 3) * kImg + sw128_offset((uint32_t)row, (uint32_t)((chunk & 7) * 8));
-        *reinterpret_cast<uint4*>(c.smem + off) = hh;
-        *reinterpret_cast<uint4*>(c.smem + 2 * kImg + off) = ll;
+        tmem_st16(c.trow + kPark + (uint32_t)(g * 16), v);
+        store_image16(v, c.row, n0, c.smem);
       }
     }
-    const float* xin = a.x0;
+#pragma unroll 1
     for (int l = 0; l < a.n_layer; ++l) {
       const FusedLayer& y = a.layer[l];
+      // small parameters of the layer -> shared memory (the previous layer's epilogues are done: barrier at its end)
+      for (int i = tid; i < kParTotal; i += kFT) {
+        const float* src = i < kParOut ? y.in_b + i
+                         : i < kParB1 ? y.out_b + (i - kParOut)
+                         : i < kParB2 ? y.b1 + (i - kParB1)
+                         : i < kParG1 ? y.b2 + (i - kParB2)
+                         : i < kParBe1 ? y.g1 + (i - kParG1)
+                         : i < kParG2 ? y.be1 + (i - kParBe1)
+                         : i < kParBe2 ? y.g2 + (i - kParG2) : y.be2 + (i - kParBe2);
+        s_par[i] = *src;
+      }
       // ---- QKV projection: A operand already staged (embedding stage or the previous layer's LN2 epilogue) ----
       sync_for_mma();
 #pragma unroll 1
       for (int ch = 0; ch < 3; ++ch) {
-        trace(100 * l + 10 + ch);
+        TRACE(100 * l + 10 + ch);
         if (tid == 0) {
-          if (ch < 2) issue_chunk(c, y.in_hi, y.in_lo, 384, ch * 128, 0, y.in_hi, y.in_lo, 384, (ch + 1) * 128);
-          else issue_chunk(c, y.in_hi, y.in_lo, 384, ch * 128, 0, nullptr, nullptr, 0, 0);
+          const bool nx = ch < 2;
+          issue_chunk(c, y.in_hi, y.in_lo, 384, ch * 128, nx ? y.in_hi : nullptr, y.in_lo, 384, (ch + 1) * 128);
         }
+        TRACE(100 * l + 13 + ch);
         wait_acc(c);
-        epi_linear<false>(c, 0, y.in_b + ch * 128, y.qkv + ch * 128, 384, y.d_ffn_h);
+        TRACE(100 * l + 16 + ch);
+        epi_linear(me_of(c), s_par + kParIn + ch * 128, y.qkv + ch * 128, 384, false, y.d_ffn_h);
         tc_fence_before();
         __syncthreads();                                      // accumulator free; qkv rows visible to the whole CTA
         tc_fence_after();
       }
       // ---- attention (per head; Q/K/V slices re-read from the rows this CTA just wrote) ----
-      trace(100 * l + 20);
-      attention_head(c, a, y, 0, s_start, s_seq, s_pad, s_x);
-      trace(100 * l + 21);
-      attention_head(c, a, y, 1, s_start, s_seq, s_pad, s_x);
-      trace(100 * l + 30);
-      // ---- out-proj + dropout + residual + LN1 (stages x1 as the FFN-up operand) ----
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        TRACE(100 * l + 20 + h);
+        attention_head(c, a, y, h, s_start, s_seq, s_pad, s_x);
+      }
+      TRACE(100 * l + 30);
+      // ---- out-proj + dropout + residual + LN1 (x1 -> park and the FFN-up operand) ----
       if (tid == 0) prefetch_chunk(c, y.out_hi, y.out_lo, 128, 0);
       stage_a_global(c, y.attn, 128);
       sync_for_mma();
-      if (tid == 0) issue_chunk(c, y.out_hi, y.out_lo, 128, 0, 0, y.w1_hi, y.w1_lo, 128, 0);
+      TRACE(100 * l + 31);
+      if (tid == 0) issue_chunk(c, y.out_hi, y.out_lo, 128, 0, y.w1_hi, y.w1_lo, 128, 0);
+      TRACE(100 * l + 32);
       wait_acc(c);
-      epi_ln<true>(c, 0, y.out_b, xin, y.d_attn_out, y.g1, y.be1, a.ln_eps, y.z1, y.st1, y.x1, s_x);
+      TRACE(100 * l + 33);
+      epi_ln(me_of(c), s_par + kParOut, s_par + kParG1, s_par + kParBe1, y.d_attn_out, a.ln_eps, y.z1, y.st1, y.x1, true, s_x);
       sync_for_mma();
-      trace(100 * l + 40);
-      // ---- FFN up (+bias -> pre) ; stages dropout(gelu(pre)) as the FFN-down operand ----
-      if (tid == 0) issue_chunk(c, y.w1_hi, y.w1_lo, 128, 0, 128, y.w2_hi, y.w2_lo, 128, 0);
+      TRACE(100 * l + 40);
+      // ---- FFN up (+bias -> pre) ; dropout(gelu(pre)) -> the FFN-down operand ----
+      if (tid == 0) issue_chunk(c, y.w1_hi, y.w1_lo, 128, 0, y.w2_hi, y.w2_lo, 128, 0);
+      TRACE(100 * l + 41);
       wait_acc(c);
-      epi_linear<true>(c, 128, y.b1, y.pre, 128, y.d_ffn_h);
+      TRACE(100 * l + 42);
+      epi_linear(me_of(c), s_par + kParB1, y.pre, 128, true, y.d_ffn_h);
       sync_for_mma();
-      trace(100 * l + 50);
-      // ---- FFN down + dropout + residual + LN2 (stages x2 as the next layer's QKV operand) ----
+      TRACE(100 * l + 50);
+      // ---- FFN down + dropout + residual + LN2 (x2 -> park and the next layer's QKV operand) ----
       const bool more = l + 1 < a.n_layer;
-      if (tid == 0) {
-        if (more) issue_chunk(c, y.w2_hi, y.w2_lo, 128, 0, 0, a.layer[l + 1].in_hi, a.layer[l + 1].in_lo, 384, 0);
-        else issue_chunk(c, y.w2_hi, y.w2_lo, 128, 0, 0, nullptr, nullptr, 0, 0);
-      }
+      if (tid == 0)
+        issue_chunk(c, y.w2_hi, y.w2_lo, 128, 0, more ? a.layer[more ? l + 1 : l].in_hi : nullptr, a.layer[more ? l + 1 : l].in_lo, 384, 0);
+      TRACE(100 * l + 51);
       wait_acc(c);
-      if (more) epi_ln<true>(c, 0, y.b2, y.x1, y.d_ffn_out, y.g2, y.be2, a.ln_eps, y.z2, y.st2, y.x2, s_x);
-      else epi_ln<false>(c, 0, y.b2, y.x1, y.d_ffn_out, y.g2, y.be2, a.ln_eps, y.z2, y.st2, y.x2, s_x);
-      xin = y.x2;
+      TRACE(100 * l + 52);
+      epi_ln(me_of(c), s_par + kParB2, s_par + kParG2, s_par + kParBe2, y.d_ffn_out, a.ln_eps, y.z2, y.st2, y.x2, more, s_x);
+      tc_fence_before();
+      __syncthreads();                                        // s_par / images / TMEM handed to the next layer (or tile)
+      tc_fence_after();
     }
-    trace(9000);
-    tc_fence_before();
-    __syncthreads();                                          // before the next tile reuses smem / TMEM / metadata
-    tc_fence_after();
+    TRACE(9000);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(c.tmem, 256);
+#ifdef DR4SR_TRACE
+  if (tid == 0 && g_trace && blockIdx.x < 8)
+    for (int i = 0; i < 2 * c.tr_n; ++i) g_trace[blockIdx.x * 256 + i] = c.tr_buf[i];
+#endif
 }
 
 }  // namespace

@@ -131,7 +131,7 @@ int build_weight_images(const dr4sr_sasrec_cfg& c, const float* params, const Wo
 }
 // Side stream for the weight-gradient work of the backward (fork/join with events; also legal inside a
 // CUDA-graph capture of the main stream).  One per device, created on first use, never destroyed.
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork[8] = {}, join = nullptr; bool ok = false; };
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork[16] = {}, join = nullptr; bool ok = false; };
 SideStream& side_stream() {
   static SideStream per_dev[64];
   int dev = 0;
@@ -139,7 +139,7 @@ SideStream& side_stream() {
   SideStream& x = per_dev[dev & 63];
   if (!x.ok) {
     bool good = cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 8 && good; ++i) good = cudaEventCreateWithFlags(&x.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 16 && good; ++i) good = cudaEventCreateWithFlags(&x.fork[i], cudaEventDisableTiming) == cudaSuccess;
     good = good && cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
     x.ok = good;
   }
@@ -351,6 +351,26 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
     }
     // LN1 backward: g1 = dz1 ; partials -> dgamma1, dbeta1, db_out
     DR4SR_TRY(launch_ln_bwd(w.g0, y.z1, y.st1, lp + lo.g1, s.g1, s.part_ln1, D, T, counts, d_attn_out, st));
+    const bool wg_tc = tc_enabled() && tc::wgrad_supported(D, F) && tc::wgrad_supported(F, D) && tc::wgrad_supported(D, D) &&
+                       tc::wgrad_supported(3 * D, D);
+    const Dropout none = no_dropout();
+    if (side.ok) {   // dz2, dpre, dz1 are final: the weight gradients that do not need dqkv start now (side stream)
+      if (cudaEventRecord(side.fork[2 * l], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[2 * l], 0) != cudaSuccess) {
+        set_cuda_error(cudaGetLastError(), "backward fork");
+        return DR4SR_ECUDA;
+      }
+    }
+    DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
+    //   dW2[d,f]  = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]      dW1[f,d]  = sum_m dpre[m,f] * x1[m,d]
+    //   dWo[n,k]  = sum_m (dz1*mask)[m,n] * attn[m,k]                     dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
+    if (wg_tc) {
+      tc::WgradTable tab{};
+      tab.job[0] = tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
+      tab.job[1] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
+      tab.job[2] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
+      tab.count = 3; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
+      DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
+    }
     {  // d(attn) = (dz1 * mask) Wo -> g2
       GemmArgs g = gemm_args(s.g1, D, lp + lo.out_w, D, w.g2, D, T, D, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_bwd_dattn";
@@ -362,7 +382,7 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
     else
       DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, s.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
     if (side.ok) {   // everything the weight gradients of this layer read is now final: fork
-      if (cudaEventRecord(side.fork[l], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[l], 0) != cudaSuccess) {
+      if (cudaEventRecord(side.fork[2 * l + 1], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[2 * l + 1], 0) != cudaSuccess) {
         set_cuda_error(cudaGetLastError(), "backward fork");
         return DR4SR_ECUDA;
       }
@@ -376,20 +396,12 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
       DR4SR_TRY(gemm_nn(g, w.img[l].in_b, st));
     }
 
-    // ---- weight / bias gradients of this layer (side stream; overlaps the next layer's chain) ----
-    DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
+    // ---- remaining weight / bias gradients of this layer (side stream; overlaps the next layer's chain) ----
     DR4SR_TRY(launch_colsum(s.dqkv, 3 * D, T, counts, s.part_cs_in, sw));
-    //   dW2[d,f]  = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]      dW1[f,d]  = sum_m dpre[m,f] * x1[m,d]
-    //   dWo[n,k]  = sum_m (dz1*mask)[m,n] * attn[m,k]                     dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
-    if (tc_enabled() && tc::wgrad_supported(D, F) && tc::wgrad_supported(F, D) &&
-        tc::wgrad_supported(D, D) && tc::wgrad_supported(3 * D, D)) {
+    if (wg_tc) {
       tc::WgradTable tab{};
-      const Dropout none = no_dropout();
       tab.job[0] = tc::WgradJob{s.dqkv, 3 * D, PRO_NONE, none, xin, D, PRO_NONE, none, 3 * D, D, s.part_w + pw_in, 0};
-      tab.job[1] = tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
-      tab.job[2] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
-      tab.job[3] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
-      tab.count = 4; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
+      tab.count = 1; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
       DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
     } else {
       {
