@@ -25,6 +25,11 @@ lib.dr4sr_debug_trace(None)
 import collections
 for cta in (0, 5):
     t = tr.view(8, 128, 2)[cta]
+    if len(sys.argv) > 2:
+        pv = 0
+        for code, cyc in t.tolist()[:int(sys.argv[2])]:
+            print(f'  {code:5d} t={cyc:8d} (+{cyc - pv})'); pv = cyc
+        continue
     prev, prevc = 0, 0
     agg = collections.OrderedDict()
     last = 0
