@@ -42,22 +42,6 @@ __device__ __forceinline__ uint64_t mn_desc16(uint32_t smem_addr) {   // MN-majo
   return d;
 }
 
-constexpr uint32_t kAHi = 128, kALo = 192;   // TMEM columns of the bf16 hi / lo A operand
-// tcgen05.mma with the A operand in tensor memory (row per lane, two bf16 k-elements per 32-bit column), B from smem
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}" ::"r"(tmem_c), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t* r) {   // 8 columns, no wait
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
-               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 // ---- bounded mbarrier waits + optional progress trace ------------------------------------------------------
 // A wait that would spin forever (a protocol bug) traps instead of hanging the GPU; when a host-mapped trace
 // buffer is installed (dr4sr_debug_trace), thread 0 of every CTA also records the last phase it reached.
@@ -73,14 +57,13 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int tag) {
   for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins) {
-    if (threadIdx.x != 0) __nanosleep(64);          // pollers other than the issuing thread back off
     if (spins > (1u << 22)) {
       if (g_trace) {
         volatile int* t = g_trace;
@@ -131,18 +114,14 @@ __global__ void __launch_bounds__(1024) fused_tiles_kernel(const int32_t* __rest
 }
 
 // ---- shared state of one CTA -------------------------------------------------------------------------
-// TMEM (256 columns): [0,128) fp32 accumulator (GEMMs, scores S, attention output over the dead S);
-// [128,192) / [192,256) the bf16 hi / lo A operand of the next product (activations or P'), written by the epilogues
-// with tcgen05.st: row per lane, two consecutive k per 32-bit column.  Shared memory (96 KB) is therefore free for
-// the operands that must be there: a 6-slot ring of 16 KB weight pieces, or the Q / K / V images during attention.
-constexpr int kSlots = 6;
+// TMEM (256 columns): [0,128) accumulator (GEMMs, scores S, attention output over the dead S), [128,256) the fp32
+// residual stream of the tile ("park": x0 / x1 / x2 rows, read back by the LayerNorm epilogues instead of HBM).
 struct Ctx {
-  uint8_t* smem;            // 1 KB aligned dynamic smem: kSlots x 16 KB
-  uint64_t *full, *empty;   // [kSlots] weight-ring barriers
+  uint8_t* smem;            // 1 KB aligned dynamic smem: [0,64K) A / Q,K / P images, [64K,96K) weight ring / V images
+  uint64_t *full, *empty;   // [2] weight-ring barriers
   uint64_t* acc;            // accumulator-ready barrier
   uint32_t tmem;            // TMEM base
   uint32_t fetched, used;   // weight-ring counters (meaningful in thread 0 only)
-  uint32_t pf, pf_limit;    // next weight piece of the tile's stream to fetch / first piece that may not be fetched yet
   uint32_t n_acc;           // completed phases of `acc` (uniform across the CTA)
   int r0, R;                // packed rows [r0, r0 + R) of the tile
   // this thread's epilogue identity: tile row quad*32+lane, 64-column half warp>>2
@@ -153,66 +132,67 @@ struct Ctx {
   int tr_n; long long tr_t0; int* tr_buf;
 #endif
 };
+constexpr uint32_t kPark = 128;
 
-__device__ __forceinline__ uint8_t* ring(const Ctx& c, uint32_t slot) { return c.smem + slot * kImg; }
+__device__ __forceinline__ uint8_t* a_hi(const Ctx& c, int kb) { return c.smem + (uint32_t)kb * kImg; }
+__device__ __forceinline__ uint8_t* a_lo(const Ctx& c, int kb) { return c.smem + (uint32_t)(2 + kb) * kImg; }
+__device__ __forceinline__ uint8_t* ring(const Ctx& c, uint32_t slot) { return c.smem + (4 + slot) * kImg; }
 
-// The tile's weight stream: 24 pieces per layer in consumption order -- in_proj chunks 0..2, out_proj, linear1,
-// linear2, each as 4 pieces {k-block 0 hi, k-block 0 lo, k-block 1 hi, k-block 1 lo} of 16 KB (rows n0..n0+127 of a
-// k-block of the SW128 K-major image are contiguous).
-__device__ __forceinline__ const uint8_t* piece_addr(const FusedFwdArgs& a, uint32_t g) {
-  const FusedLayer& y = a.layer[g / 24u];
-  const uint32_t q = g % 24u, chunk = q >> 2, p = q & 3u;
-  const uint16_t *hi, *lo;
-  uint32_t n_total = 128, n0 = 0;
-  if (chunk < 3) { hi = y.in_hi; lo = y.in_lo; n_total = 384; n0 = chunk * 128; }
-  else if (chunk == 3) { hi = y.out_hi; lo = y.out_lo; }
-  else if (chunk == 4) { hi = y.w1_hi; lo = y.w1_lo; }
-  else { hi = y.w2_hi; lo = y.w2_lo; }
-  const uint8_t* base = reinterpret_cast<const uint8_t*>((p & 1u) ? lo : hi);
-  return base + ((size_t)(p >> 1) * n_total + n0) * 128;
-}
-// thread 0: queue bulk copies of the next pieces while ring slots are free (blocks only on slots whose UMMAs are still
-// running, i.e. on work the whole CTA is waiting for anyway)
-__device__ __noinline__ void ring_fill(Ctx& c, const FusedFwdArgs& a) {
-  while (c.pf < c.pf_limit && c.fetched - c.used < (uint32_t)kSlots) {
-    const uint32_t slot = c.fetched % kSlots, use = c.fetched / kSlots;
-    if (use >= 1) mbar_wait_b(&c.empty[slot], (use - 1) & 1u, 100 + (int)slot);
-    TRACE(3040);
-    mbar_expect_tx(&c.full[slot], kImg);
-    bulk_g2s(ring(c, slot), piece_addr(a, c.pf), kImg, &c.full[slot]);
-    ++c.fetched;
-    ++c.pf;
+// thread 0: queue the bulk copy of one 16 KB weight piece into the next ring slot
+__device__ __forceinline__ void ring_fetch(Ctx& c, const uint8_t* src) {
+  const uint32_t slot = c.fetched & 1u, use = c.fetched >> 1;
+  if (use >= 1) {                                   // the UMMAs that read the slot's previous piece are done
+    mbar_wait_b(&c.empty[slot], (use - 1) & 1u, 100 + (int)slot);
   }
+  mbar_expect_tx(&c.full[slot], kImg);
+  bulk_g2s(ring(c, slot), src, kImg, &c.full[slot]);
+  ++c.fetched;
+}
+// piece p of a 128-column chunk n0 of a logical [N_total, 128] weight: p = 2 * kb + (lo ? 1 : 0)
+__device__ __forceinline__ const uint8_t* piece_src(const uint16_t* hi, const uint16_t* lo, int N_total, int n0, int p) {
+  const uint8_t* base = reinterpret_cast<const uint8_t*>((p & 1) ? lo : hi);
+  return base + ((size_t)(p >> 1) * N_total + n0) * 128;
+}
+__device__ __forceinline__ void prefetch_chunk(Ctx& c, const uint16_t* hi, const uint16_t* lo, int N_total, int n0) {
+  ring_fetch(c, piece_src(hi, lo, N_total, n0, 0));
+  ring_fetch(c, piece_src(hi, lo, N_total, n0, 1));
 }
 
-// thread 0: acc[128 x 128] (TMEM columns [0,128)) = A (bf16 hi/lo in TMEM, K = 128) x the next 4 pieces of the stream
-__device__ __noinline__ void issue_chunk(Ctx& c) {
+// thread 0: acc[128 x 128] (TMEM columns [0,128)) = A (hi/lo images in smem, K = 128) x W[n0..n0+127, :]^T.
+// The first two pieces of the chunk must already be in flight (prefetch_chunk).  `nhi != null`: the first two
+// pieces of the NEXT chunk are queued as soon as ring slots free up.
+__device__ __noinline__ void issue_chunk(Ctx& c, const uint16_t* hi, const uint16_t* lo, int N_total, int n0,
+                                         const uint16_t* nhi, const uint16_t* nlo, int nN_total, int nn0) {
   const uint32_t acc = c.tmem;
 #pragma unroll 1
   for (int p = 0; p < 4; ++p) {
-    const uint32_t slot = c.used % kSlots, use = c.used / kSlots;
-    TRACE(3000 + p);
+    const uint32_t slot = c.used & 1u, use = c.used >> 1;
     mbar_wait_b(&c.full[slot], use & 1u, 200 + (int)slot);
-    TRACE(3010 + p);
+    TRACE(2000 + p);
     tc_fence_after();
-    const uint32_t b = smem_u32(ring(c, slot));
-    const uint32_t ah = c.tmem + kAHi + (uint32_t)((p >> 1) * 32), al = c.tmem + kALo + (uint32_t)((p >> 1) * 32);
+    const int kb = p >> 1;
+    const uint32_t b = smem_u32(ring(c, slot)), ah = smem_u32(a_hi(c, kb)), al = smem_u32(a_lo(c, kb));
     if ((p & 1) == 0) {                               // W_hi piece: A_hi W_hi + A_lo W_hi
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        umma_bf16_ts(acc, ah + (uint32_t)(k * 8), sw128_desc(b + (uint32_t)k * 32u), kIdesc, (p > 0 || k > 0) ? 1u : 0u);
-        umma_bf16_ts(acc, al + (uint32_t)(k * 8), sw128_desc(b + (uint32_t)k * 32u), kIdesc, 1u);
+        const uint32_t ko = (uint32_t)k * 32u;
+        umma_bf16(acc, sw128_desc(ah + ko), sw128_desc(b + ko), kIdesc, (p > 0 || k > 0) ? 1u : 0u);
+        umma_bf16(acc, sw128_desc(al + ko), sw128_desc(b + ko), kIdesc, 1u);
       }
     } else {                                          // W_lo piece: A_hi W_lo
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_ts(acc, ah + (uint32_t)(k * 8), sw128_desc(b + (uint32_t)k * 32u), kIdesc, 1u);
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t ko = (uint32_t)k * 32u;
+        umma_bf16(acc, sw128_desc(ah + ko), sw128_desc(b + ko), kIdesc, 1u);
+      }
     }
-    TRACE(3020 + p);
     umma_commit(&c.empty[slot]);
     ++c.used;
+    if (p + 2 < 4) { ring_fetch(c, piece_src(hi, lo, N_total, n0, p + 2)); TRACE(2010 + p); }
   }
   umma_commit(c.acc);
-  TRACE(3030);
+  if (nhi) prefetch_chunk(c, nhi, nlo, nN_total, nn0);
+  TRACE(2020);
 }
 
 // all threads: wait for the accumulator committed by the most recent issue
@@ -282,19 +262,6 @@ __device__ __forceinline__ void store_image16(const float* v, int row, int n0, u
     *reinterpret_cast<uint4*>(base + 2 * kImg + off) = l;
   }
 }
-// the same 16 values as a TMEM A operand: this thread's lane, k = n0 .. n0+15 -> columns n0/2 .. n0/2+7 of the hi and lo halves
-__device__ __forceinline__ void store_tmemA16(const float* v, uint32_t lane_base, int n0) {
-  uint32_t h[8], l[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) split2(v[2 * q], v[2 * q + 1], h[q], l[q]);
-  tmem_st8u(lane_base + kAHi + (uint32_t)(n0 >> 1), h);
-  tmem_st8u(lane_base + kALo + (uint32_t)(n0 >> 1), l);
-}
-__device__ __forceinline__ void store_tmemA16_zero(uint32_t lane_base, int n0) {
-  const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-  tmem_st8u(lane_base + kAHi + (uint32_t)(n0 >> 1), z);
-  tmem_st8u(lane_base + kALo + (uint32_t)(n0 >> 1), z);
-}
 __device__ __forceinline__ void store_image16_zero(int row, int n0, uint8_t* base) {
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -329,19 +296,34 @@ struct RowDrop {
   }
 };
 
-// fp32 [R x 128] rows from global -> the TMEM A operand (thread = its row, 64 columns; rows >= R zero)
-__device__ __forceinline__ void stage_a_global(const Ctx& c, const float* src) {
-  const float* rowp = src + (size_t)c.m * 128 + c.half * 64;
-  float4 x[16];
+// fp32 [R x 128] rows (row stride ld) from global -> A images (rows >= R zero)
+__device__ __forceinline__ void stage_a_global(const Ctx& c, const float* src, int ld) {
+  const int chunk = threadIdx.x & 15, rsub = threadIdx.x >> 4;     // 16 chunks of 8 floats, 16 rows per pass
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float4 v[4][2];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = c.live ? *reinterpret_cast<const float4*>(rowp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < 4; ++it) {
+      const int row = (half * 4 + it) * 16 + rsub;
+      if (row < c.R) {
+        const float* p = src + (size_t)(c.r0 + row) * ld + chunk * 8;
+        v[it][0] = *reinterpret_cast<const float4*>(p);
+        v[it][1] = *reinterpret_cast<const float4*>(p + 4);
+      } else {
+        v[it][0] = v[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const float v[16] = {x[4 * g].x, x[4 * g].y, x[4 * g].z, x[4 * g].w, x[4 * g + 1].x, x[4 * g + 1].y, x[4 * g + 1].z, x[4 * g + 1].w,
-                         x[4 * g + 2].x, x[4 * g + 2].y, x[4 * g + 2].z, x[4 * g + 2].w, x[4 * g + 3].x, x[4 * g + 3].y, x[4 * g + 3].z, x[4 * g + 3].w};
-    store_tmemA16(v, c.trow - (uint32_t)(c.half * 64), c.half * 64 + g * 16);
+    for (int it = 0; it < 4; ++it) {
+      const int row = (half * 4 + it) * 16 + rsub;
+      const float x[8] = {v[it][0].x, v[it][0].y, v[it][0].z, v[it][0].w, v[it][1].x, v[it][1].y, v[it][1].z, v[it][1].w};
+      uint4 h, l;
+      split8(x, h, l);
+      const uint32_t off = (uint32_t)(chunk >> 3) * kImg + sw128_offset((uint32_t)row, (uint32_t)((chunk & 7) * 8));
+      *reinterpret_cast<uint4*>(c.smem + off) = h;
+      *reinterpret_cast<uint4*>(c.smem + 2 * kImg + off) = l;
+    }
   }
-  tmem_st_wait();
 }
 
 // fp32 head slices Q, K, V [R x 64] of the packed qkv rows -> their hi / lo image pairs (rows >= R zero)
@@ -439,42 +421,35 @@ __device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, 
         rd.factors16(n0 + q * 16, f);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[q * 16 + j] = gelu_f(v[q * 16 + j]) * f[j];
-        store_tmemA16(v + q * 16, me.trow - (uint32_t)(me.half * 64), n0 + q * 16);
+        store_image16(v + q * 16, me.row, n0 + q * 16, me.smem);
       }
     }
   }
-  if (gelu_stage) tmem_st_wait();
 }
 
 // z = dropout(acc + bias) + residual(park) ; y = LayerNorm(z) -> Z, stats, Y (global), park <- y and, if stage, the
 // next A operand.  The thread keeps its 64 z values in registers: one pass over TMEM.  s_b / s_g / s_be: bias, gamma,
 // beta in shared memory.
-__device__ __noinline__ void epi_ln(Me me, const float* s_b, const float* s_g, const float* s_be, Dropout de, float eps, const float* res,
-                                    float* Z, float* stats, float* Y, bool stage, float (*ln_part)[128]) {
+__device__ __noinline__ void epi_ln(Me me, const float* s_b, const float* s_g, const float* s_be, Dropout de, float eps, float* Z,
+                                    float* stats, float* Y, bool stage, float (*ln_part)[128]) {
   RowDrop rd;
   rd.init(de, (uint32_t)me.m);
   float z[64];
   float sum = 0.f;
   float* zrow = Z + (size_t)me.m * 128 + me.half * 64;
-  const float* rrow = res + (size_t)me.m * 128 + me.half * 64;
-  float4 rr[16];                                               // the row's residual (L2-resident: this CTA wrote it), all loads in flight
-#pragma unroll
-  for (int j = 0; j < 16; ++j) rr[j] = me.live ? *reinterpret_cast<const float4*>(rrow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int n0 = me.half * 64 + g * 16;
-    float f[16];
+    float r[16], f[16];
     tmem_ld16_nowait(me.trow + (uint32_t)(g * 16), z + g * 16);
+    tmem_ld16_nowait(me.trow + kPark + (uint32_t)(g * 16), r);
     rd.factors16(n0, f);
     tmem_ld_fence(z + g * 16, true);
+    tmem_ld_fence(r, false);
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 r4 = rr[g * 4 + j / 4];
-      z[g * 16 + j] = (z[g * 16 + j] + s_b[n0 + j]) * f[j] + r4.x;
-      z[g * 16 + j + 1] = (z[g * 16 + j + 1] + s_b[n0 + j + 1]) * f[j + 1] + r4.y;
-      z[g * 16 + j + 2] = (z[g * 16 + j + 2] + s_b[n0 + j + 2]) * f[j + 2] + r4.z;
-      z[g * 16 + j + 3] = (z[g * 16 + j + 3] + s_b[n0 + j + 3]) * f[j + 3] + r4.w;
-      sum += (z[g * 16 + j] + z[g * 16 + j + 1]) + (z[g * 16 + j + 2] + z[g * 16 + j + 3]);
+    for (int j = 0; j < 16; ++j) {
+      z[g * 16 + j] = (z[g * 16 + j] + s_b[n0 + j]) * f[j] + r[j];
+      sum += z[g * 16 + j];
     }
     if (me.live) {
 #pragma unroll
@@ -504,9 +479,9 @@ __device__ __noinline__ void epi_ln(Me me, const float* s_b, const float* s_g, c
       for (int j = 0; j < 16; j += 4)
         *reinterpret_cast<float4*>(yrow + g * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    if (stage) store_tmemA16(v, me.trow - (uint32_t)(me.half * 64), n0);
+    tmem_st16(me.trow + kPark + (uint32_t)(g * 16), v);
+    if (stage) store_image16(v, me.row, n0, me.smem);
   }
-  if (stage) tmem_st_wait();
   if (me.live && me.half == 0) { stats[2 * me.m] = mu; stats[2 * me.m + 1] = rstd; }
 }
 
@@ -560,14 +535,14 @@ __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, co
   __syncthreads();
   mx = fmaxf(s_x[0][row], s_x[1][row]);
   __syncthreads();
-  // P' = dropout(exp(s - max)) un-normalised (the 1/sum is applied to the output rows) -> TMEM A operand (bf16 hi / lo)
+  // P' = dropout(exp(s - max)) un-normalised (the 1/sum is applied to the output rows), written over the dead Q / K images
   float sum = 0.f;
   const Dropout& dp = y.d_attn_p;
   const uint32_t dbase = (uint32_t)(s_seq[row] * 2 + h) * (uint32_t)(a.L * a.L) + (uint32_t)(row - start) * (uint32_t)a.L;
 #pragma unroll 1
   for (int g = 0; g < 4; ++g) {
     const int c0 = c.half * 64 + g * 16;
-    if (!(live_groups >> g & 1u)) { store_tmemA16_zero(c.trow - (uint32_t)(c.half * 64), c0); continue; }
+    if (!(live_groups >> g & 1u)) { store_image16_zero(row, c0, c.smem); continue; }
     float s[16];
     tmem_ld16(c.trow + (uint32_t)(g * 16), s);
     // dropout draws of elements idx0 .. idx0 + 15: element i uses half-word (i & 1) of draw32(key, i >> 1)
@@ -594,20 +569,19 @@ __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, co
       }
       s[j] = e * f;
     }
-    store_tmemA16(s, c.trow - (uint32_t)(c.half * 64), c0);
+    store_image16(s, row, c0, c.smem);
   }
-  tmem_st_wait();
   s_x[c.half][row] = sum;
   sync_for_mma();
   TRACE(1000 + 10 * h + 3);
-  if (tid == 0) {                                             // O = P' V -> TMEM columns [0,64) (over the dead scores); A = P' in TMEM
-    const uint32_t bh = smem_u32(v_hi), bl = smem_u32(v_lo);
+  if (tid == 0) {                                             // O = P' V -> TMEM columns [0,64) (over the dead scores)
+    const uint32_t ah = smem_u32(c.smem), al = smem_u32(c.smem + 2 * kImg), bh = smem_u32(v_hi), bl = smem_u32(v_lo);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {                             // 16 keys per UMMA = 8 TMEM columns of A, 2048 B of V
-      const uint32_t ah = c.tmem + kAHi + (uint32_t)(k * 8), al = c.tmem + kALo + (uint32_t)(k * 8), bo = (uint32_t)k * 2048u;
-      umma_bf16_ts(c.tmem, ah, mn_desc16(bh + bo), kIdescN64_K_MN, k > 0 ? 1u : 0u);
-      umma_bf16_ts(c.tmem, ah, mn_desc16(bl + bo), kIdescN64_K_MN, 1u);
-      umma_bf16_ts(c.tmem, al, mn_desc16(bh + bo), kIdescN64_K_MN, 1u);
+    for (int k = 0; k < 8; ++k) {                             // 16 keys per UMMA
+      const uint32_t ao = (uint32_t)(k >> 2) * kImg + (uint32_t)(k & 3) * 32u, bo = (uint32_t)k * 2048u;
+      umma_bf16(c.tmem, sw128_desc(ah + ao), mn_desc16(bh + bo), kIdescN64_K_MN, k > 0 ? 1u : 0u);
+      umma_bf16(c.tmem, sw128_desc(ah + ao), mn_desc16(bl + bo), kIdescN64_K_MN, 1u);
+      umma_bf16(c.tmem, sw128_desc(al + ao), mn_desc16(bh + bo), kIdescN64_K_MN, 1u);
     }
     umma_commit(c.acc);
   }
@@ -639,7 +613,7 @@ constexpr int kParIn = 0, kParOut = 384, kParB1 = 512, kParB2 = 640, kParG1 = 76
 
 __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_constant__ FusedFwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * kSlots + 1];
+  __shared__ __align__(8) uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_start[128], s_seq[128], s_pad[128], s_id[128];
   __shared__ float s_x[2][128];
@@ -650,14 +624,14 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
 
   Ctx c;
   c.smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  c.full = &bars[0]; c.empty = &bars[kSlots]; c.acc = &bars[2 * kSlots];
-  c.fetched = 0; c.used = 0; c.n_acc = 0; c.pf = 0; c.pf_limit = 0;
+  c.full = &bars[0]; c.empty = &bars[2]; c.acc = &bars[4];
+  c.fetched = 0; c.used = 0; c.n_acc = 0;
 #ifdef DR4SR_TRACE
   __shared__ int s_trace[256];
   c.tr_n = 0; c.tr_t0 = clock64(); c.tr_buf = s_trace;
 #endif
   if (tid == 0) {
-    for (int i = 0; i < 2 * kSlots + 1; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
@@ -690,7 +664,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       s_start[tid] = st; s_seq[tid] = sq; s_pad[tid] = pd; s_id[tid] = id;
     }
     TRACE(1);
-    if (tid == 0) { c.pf = 0; c.pf_limit = 12; ring_fill(c, a); }     // the first layer's in_proj pieces
+    if (tid == 0) prefetch_chunk(c, a.layer[0].in_hi, a.layer[0].in_lo, 384, 0);
     __syncthreads();
     // ---- x0 = dropout(E[id] + P[t]) -> global (the backward needs it), park (residual) and the first A operand ----
     {
@@ -719,11 +693,10 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
         }
-        store_tmemA16(v, c.trow - (uint32_t)(c.half * 64), n0);
+        tmem_st16(c.trow + kPark + (uint32_t)(g * 16), v);
+        store_image16(v, c.row, n0, c.smem);
       }
-      tmem_st_wait();
     }
-    const float* xin = a.x0;
 #pragma unroll 1
     for (int l = 0; l < a.n_layer; ++l) {
       const FusedLayer& y = a.layer[l];
@@ -743,7 +716,10 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
 #pragma unroll 1
       for (int ch = 0; ch < 3; ++ch) {
         TRACE(100 * l + 10 + ch);
-        if (tid == 0) { issue_chunk(c); ring_fill(c, a); }
+        if (tid == 0) {
+          const bool nx = ch < 2;
+          issue_chunk(c, y.in_hi, y.in_lo, 384, ch * 128, nx ? y.in_hi : nullptr, y.in_lo, 384, (ch + 1) * 128);
+        }
         TRACE(100 * l + 13 + ch);
         wait_acc(c);
         TRACE(100 * l + 16 + ch);
@@ -760,20 +736,19 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       }
       TRACE(100 * l + 30);
       // ---- out-proj + dropout + residual + LN1 (x1 -> park and the FFN-up operand) ----
-      const bool more = l + 1 < a.n_layer;
-      if (tid == 0) { c.pf_limit = 24u * (uint32_t)(l + 1) + (more ? 12u : 0u); ring_fill(c, a); }   // through the next layer's in_proj
-      stage_a_global(c, y.attn);
+      if (tid == 0) prefetch_chunk(c, y.out_hi, y.out_lo, 128, 0);
+      stage_a_global(c, y.attn, 128);
       sync_for_mma();
       TRACE(100 * l + 31);
-      if (tid == 0) { issue_chunk(c); ring_fill(c, a); }
+      if (tid == 0) issue_chunk(c, y.out_hi, y.out_lo, 128, 0, y.w1_hi, y.w1_lo, 128, 0);
       TRACE(100 * l + 32);
       wait_acc(c);
       TRACE(100 * l + 33);
-      epi_ln(me_of(c), s_par + kParOut, s_par + kParG1, s_par + kParBe1, y.d_attn_out, a.ln_eps, xin, y.z1, y.st1, y.x1, true, s_x);
+      epi_ln(me_of(c), s_par + kParOut, s_par + kParG1, s_par + kParBe1, y.d_attn_out, a.ln_eps, y.z1, y.st1, y.x1, true, s_x);
       sync_for_mma();
       TRACE(100 * l + 40);
       // ---- FFN up (+bias -> pre) ; dropout(gelu(pre)) -> the FFN-down operand ----
-      if (tid == 0) { issue_chunk(c); ring_fill(c, a); }
+      if (tid == 0) issue_chunk(c, y.w1_hi, y.w1_lo, 128, 0, y.w2_hi, y.w2_lo, 128, 0);
       TRACE(100 * l + 41);
       wait_acc(c);
       TRACE(100 * l + 42);
@@ -781,15 +756,16 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       sync_for_mma();
       TRACE(100 * l + 50);
       // ---- FFN down + dropout + residual + LN2 (x2 -> park and the next layer's QKV operand) ----
-      if (tid == 0) { issue_chunk(c); ring_fill(c, a); }
+      const bool more = l + 1 < a.n_layer;
+      if (tid == 0)
+        issue_chunk(c, y.w2_hi, y.w2_lo, 128, 0, more ? a.layer[more ? l + 1 : l].in_hi : nullptr, a.layer[more ? l + 1 : l].in_lo, 384, 0);
       TRACE(100 * l + 51);
       wait_acc(c);
       TRACE(100 * l + 52);
-      epi_ln(me_of(c), s_par + kParB2, s_par + kParG2, s_par + kParBe2, y.d_ffn_out, a.ln_eps, y.x1, y.z2, y.st2, y.x2, more, s_x);
+      epi_ln(me_of(c), s_par + kParB2, s_par + kParG2, s_par + kParBe2, y.d_ffn_out, a.ln_eps, y.z2, y.st2, y.x2, more, s_x);
       tc_fence_before();
       __syncthreads();                                        // s_par / images / TMEM handed to the next layer (or tile)
       tc_fence_after();
-      xin = y.x2;
     }
     TRACE(9000);
   }
