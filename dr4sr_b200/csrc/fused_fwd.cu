@@ -367,6 +367,12 @@ __device__ __forceinline__ void sync_for_mma() {
   tc_fence_after();
 }
 
+// 8 consecutive floats (32-byte aligned) as one 256-bit store: a full 32 B sector per thread per instruction
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 // ---- epilogues (thread = tile row me.row, columns me.half*64 .. +63) --------------------------------------------
 struct Me { int row, half, m; bool live; uint32_t trow; uint8_t* smem; };   // passed by value: stays in registers
 __device__ __forceinline__ Me me_of(const Ctx& c) { return Me{c.row, c.half, c.m, c.live, c.trow, c.smem}; }
@@ -412,7 +418,10 @@ __device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, 
     for (int j = 0; j < 32; j += 4) {
       const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + j);
       v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-      if (me.live) *reinterpret_cast<float4*>(orow + g * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    if (me.live) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st_global_v8(orow + g * 32 + j, v + j);
     }
     if (gelu_stage) {
 #pragma unroll
@@ -452,9 +461,8 @@ __device__ __noinline__ void epi_ln(Me me, const float* s_b, const float* s_g, c
       sum += z[g * 16 + j];
     }
     if (me.live) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(zrow + g * 16 + j) = make_float4(z[g * 16 + j], z[g * 16 + j + 1], z[g * 16 + j + 2], z[g * 16 + j + 3]);
+      st_global_v8(zrow + g * 16, z + g * 16);
+      st_global_v8(zrow + g * 16 + 8, z + g * 16 + 8);
     }
   }
   ln_part[me.half][me.row] = sum;
@@ -475,9 +483,8 @@ __device__ __noinline__ void epi_ln(Me me, const float* s_b, const float* s_g, c
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = (v[j] - mu) * rstd * s_g[n0 + j] + s_be[n0 + j];
     if (me.live) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(yrow + g * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      st_global_v8(yrow + g * 16, v);
+      st_global_v8(yrow + g * 16 + 8, v + 8);
     }
     tmem_st16(me.trow + kPark + (uint32_t)(g * 16), v);
     if (stage) store_image16(v, me.row, n0, me.smem);
