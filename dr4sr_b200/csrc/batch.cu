@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(1024) prep_scan_kernel(const int64_t* __restri
                                                          int32_t* __restrict__ counts) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
+  __shared__ int s_before[1024], s_len[1024];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry = 0;
   __syncthreads();
@@ -39,9 +40,13 @@ __global__ void __launch_bounds__(1024) prep_scan_kernel(const int64_t* __restri
     }
     __syncthreads();
     const int before = carry + (warp ? warp_tot[warp - 1] : 0) + incl - len;
-    if (b < B) {
-      tok_off[b] = before;
-      for (int t = 0; t < len; ++t) row_seq[before + t] = b;
+    if (b < B) tok_off[b] = before;
+    s_before[tid] = before; s_len[tid] = len;
+    __syncthreads();
+    // row_seq: one warp per sequence, lanes = positions (coalesced stores instead of a serial loop per thread)
+    for (int i = warp; i < (int)blockDim.x && base + i < B; i += (int)(blockDim.x >> 5)) {
+      const int o = s_before[i], n = s_len[i];
+      for (int t = lane; t < n; t += 32) row_seq[o + t] = base + i;
     }
     __syncthreads();
     if (tid == blockDim.x - 1) carry = before + len;

@@ -304,10 +304,10 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
   return DR4SR_OK;
 }
 
-extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, const float* params,
-                                const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
-                                const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed, float* grads,
-                                float* dx0_packed, dr4sr_stream_t stream) {
+static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const float* params,
+                           const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                           const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed, float* grads,
+                           float* dx0_packed, dr4sr_stream_t stream, bool join) {
   (void)table;
   DR4SR_TRY(check_cfg(c));
   if (!params || !in_item_id || !tok_off || !row_seq || !counts || !ws || !dq_packed || !grads || !dx0_packed) return DR4SR_EINVAL;
@@ -446,13 +446,33 @@ extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, c
     }
     gin = w.g0;
   }
-  if (side.ok) {   // join: the caller's stream sees every gradient
-    if (cudaEventRecord(side.join, sw) != cudaSuccess || cudaStreamWaitEvent(st, side.join, 0) != cudaSuccess) {
+  if (join) return dr4sr_sasrec_bwd_join(stream);
+  return DR4SR_OK;
+}
+
+extern "C" int dr4sr_sasrec_bwd_join(dr4sr_stream_t stream) {
+  SideStream& side = side_stream();
+  if (side.ok) {   // the caller's stream sees every weight gradient after this point
+    if (cudaEventRecord(side.join, side.s) != cudaSuccess || cudaStreamWaitEvent(as_stream(stream), side.join, 0) != cudaSuccess) {
       set_cuda_error(cudaGetLastError(), "backward join");
       return DR4SR_ECUDA;
     }
   }
   return DR4SR_OK;
+}
+
+extern "C" int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* c, const float* table, const float* params,
+                                const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                                const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed, float* grads,
+                                float* dx0_packed, dr4sr_stream_t stream) {
+  return sasrec_bwd_impl(c, table, params, in_item_id, tok_off, row_seq, counts, ws, ws_bytes, dq_packed, grads, dx0_packed, stream, true);
+}
+
+extern "C" int dr4sr_sasrec_bwd_async(const dr4sr_sasrec_cfg* c, const float* table, const float* params,
+                                      const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                                      const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed, float* grads,
+                                      float* dx0_packed, dr4sr_stream_t stream) {
+  return sasrec_bwd_impl(c, table, params, in_item_id, tok_off, row_seq, counts, ws, ws_bytes, dq_packed, grads, dx0_packed, stream, false);
 }
 
 extern "C" int dr4sr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int32_t M, int32_t N, int32_t K,

@@ -62,6 +62,7 @@ class SASRecEngine:
         self._bufs: Dict[int, _Buffers] = {}
         self._fn_count, self._fn_ws = self.lib.dr4sr_sasrec_param_count, self.lib.dr4sr_sasrec_workspace_bytes
         self._fn_fwd, self._fn_bwd, self._name = self.lib.dr4sr_sasrec_fwd, self.lib.dr4sr_sasrec_bwd, 'dr4sr_sasrec'
+        self._fn_bwd_async = self.lib.dr4sr_sasrec_bwd_async
         self._finish_init(f'unsupported SASRec shape D={self.D} F={self.F} L={self.L} heads={self.H} layers={self.n_layer} '
                           f'(D in {{64,128}}, F % 64 == 0, L <= 64)')
 
@@ -135,14 +136,21 @@ class SASRecEngine:
         return b.loss
 
     def encode_bwd(self, b: _Buffers, table: torch.Tensor, flat: torch.Tensor, in_ids: torch.Tensor, grads_flat: torch.Tensor,
-                   dq: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   dq: Optional[torch.Tensor] = None, defer_join: bool = False) -> torch.Tensor:
+        """defer_join: (SASRec only) return with the weight gradients still in flight on the library's side stream;
+        the caller must call join_bwd() before anything reads `grads_flat` (dx0 is already ordered)."""
         in_ids = _req(in_ids, torch.int64, 'in_item_id')
         B = in_ids.size(0)
         cfg = self.cfg(B)
         dq = b.dq if dq is None else dq
-        check(self._fn_bwd(C.byref(cfg), _p(table), _p(flat), _p(in_ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
+        fn = self._fn_bwd_async if (defer_join and getattr(self, '_fn_bwd_async', None) is not None) else self._fn_bwd
+        check(fn(C.byref(cfg), _p(table), _p(flat), _p(in_ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
                                         _p(b.ws), b.ws.numel(), _p(dq), _p(grads_flat), _p(b.dx0), _stream()), self._name + '_bwd')
         return b.dx0
+
+    def join_bwd(self) -> None:
+        if getattr(self, '_fn_bwd_async', None) is not None:
+            check(self.lib.dr4sr_sasrec_bwd_join(_stream()), 'dr4sr_sasrec_bwd_join')
 
     def table_grad(self, b: _Buffers, in_ids: torch.Tensor, item_id: Optional[torch.Tensor], neg_item: Optional[torch.Tensor],
                    table_grad: torch.Tensor, pos_grad: Optional[torch.Tensor], with_dx0: bool = True) -> None:
@@ -168,6 +176,7 @@ class GRUEngine(SASRecEngine):
         self._bufs = {}
         self._fn_count, self._fn_ws = self.lib.dr4sr_gru_param_count, self.lib.dr4sr_gru_workspace_bytes
         self._fn_fwd, self._fn_bwd, self._name = self.lib.dr4sr_gru_fwd, self.lib.dr4sr_gru_bwd, 'dr4sr_gru'
+        self._fn_bwd_async = None
         self._finish_init(f'unsupported GRU4Rec shape D={self.D} H={self.Hh} layers={self.n_layer} '
                           f'(D in {{64,128}}, H in {{64,128,256}}, layers <= 4)')
         self._tg_ws = torch.empty(self.lib.dr4sr_table_grad_workspace_bytes(self.L, self.D), dtype=torch.uint8, device=self.device)

@@ -113,9 +113,11 @@ class SASRec(BaseModel):
         if dquery is not None:
             valid = torch.arange(eng.L, device=dquery.device).view(1, -1) < batch_len(b)
             b.dq[: int(b.counts[0])] += dquery[valid]
-        eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad)
+        # the weight gradients finish on the library's side stream while the embedding scatter-add runs here
+        eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad, defer_join=True)
         tg = self._scatter_target()
         eng.table_grad(b, in_ids, item_id, neg, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
+        eng.join_bwd()
         self._dp_sum(self._flat_grad)
         self._finish_table_grad(tg)
 

@@ -134,6 +134,15 @@ DR4SR_API int dr4sr_sasrec_bwd(const dr4sr_sasrec_cfg* cfg, const float* table, 
                      const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
                      const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed,
                      float* grads, float* dx0_packed, dr4sr_stream_t stream);
+/* The weight gradients of the backward run on an internal side stream that overlaps the data-gradient chain.
+ * dr4sr_sasrec_bwd joins it before returning (every gradient is ordered on `stream`).  dr4sr_sasrec_bwd_async leaves
+ * the join to the caller: dx0_packed is ordered on `stream`, `grads` only after dr4sr_sasrec_bwd_join(stream) -- the
+ * Python model enqueues the embedding scatter-add (dr4sr_table_grad) in between, under the tail of the side stream. */
+DR4SR_API int dr4sr_sasrec_bwd_async(const dr4sr_sasrec_cfg* cfg, const float* table, const float* params,
+                     const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                     const int32_t* counts, void* ws, size_t ws_bytes, float* dq_packed,
+                     float* grads, float* dx0_packed, dr4sr_stream_t stream);
+DR4SR_API int dr4sr_sasrec_bwd_join(dr4sr_stream_t stream);
 
 /* Packed rows -> the reference's layouts: q_last [B,D] = row seqlen-1 of every sequence ('last' pooling,
  * module/layers.py:69-73), q_dense [B,L,D] = rows scattered back with zeros at t >= seqlen ('origin'
