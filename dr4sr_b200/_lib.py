@@ -55,6 +55,7 @@ SIGNATURES = {
     'dr4sr_sasrec_bwd': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
     'dr4sr_sasrec_bwd_async': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
     'dr4sr_sasrec_bwd_join': (c_i32, [c_p]),
+    'dr4sr_scale_grads': (c_i32, [c_p, c_p, c_i32, c_p, c_p, c_p]),
     'dr4sr_unpack_rows': (c_i32, [c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p]),
     'dr4sr_gru_param_count': (c_sz, [C.POINTER(GruCfg)]),
     'dr4sr_gru_workspace_bytes': (c_sz, [C.POINTER(GruCfg)]),

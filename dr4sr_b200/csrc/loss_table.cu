@@ -188,10 +188,34 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   }
 }
 
+// dq, dscore *= *upstream over the live rows; leaves immediately when the factor is 1 (the usual loss.backward())
+__global__ void __launch_bounds__(256) scale_grads_kernel(const float* __restrict__ upstream, const int32_t* __restrict__ counts,
+                                                          int D, float* __restrict__ dq, float* __restrict__ dscore) {
+  const float up = *upstream;
+  if (up == 1.0f) return;
+  const int T = counts[0];
+  const int64_t nq = (int64_t)T * D / 4, ns = (int64_t)T * 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<float4*>(dq)[i];
+    v.x *= up; v.y *= up; v.z *= up; v.w *= up;
+    reinterpret_cast<float4*>(dq)[i] = v;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += (int64_t)gridDim.x * blockDim.x) dscore[i] *= up;
+}
+
 }  // namespace
 }  // namespace dr4sr
 
 using namespace dr4sr;
+
+extern "C" int dr4sr_scale_grads(const float* upstream, const int32_t* counts, int32_t D, float* dq_packed, float* dscore,
+                                 dr4sr_stream_t stream) {
+  if (!upstream || !counts || !dq_packed || !dscore || D % 4) return DR4SR_EINVAL;
+  ProfScope prof("scale_grads", as_stream(stream));
+  scale_grads_kernel<<<2 * kNumSMs, 256, 0, as_stream(stream)>>>(upstream, counts, D, dq_packed, dscore);
+  DR4SR_LAUNCH_CHECK("scale_grads_kernel");
+  return DR4SR_OK;
+}
 
 extern "C" int dr4sr_score_bce(const float* q_packed, const float* table, const int64_t* item_id, const int64_t* neg_item,
                                const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,

@@ -128,7 +128,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rl < lanes_r) {
-    for (int row = blockIdx.x * lanes_r + rl; row < T; row += gridDim.x * lanes_r) {
+    const int step = gridDim.x * lanes_r;
+    int row = blockIdx.x * lanes_r + rl;
+    for (; row + 3 * step < T; row += 4 * step) {          // four independent loads in flight; fixed summation order
+      const float4 v0 = *reinterpret_cast<const float4*>(x + (size_t)row * N + cg * 4);
+      const float4 v1 = *reinterpret_cast<const float4*>(x + (size_t)(row + step) * N + cg * 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(x + (size_t)(row + 2 * step) * N + cg * 4);
+      const float4 v3 = *reinterpret_cast<const float4*>(x + (size_t)(row + 3 * step) * N + cg * 4);
+      acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+      acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; row < T; row += step) {
       const float4 v = *reinterpret_cast<const float4*>(x + (size_t)row * N + cg * 4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }

@@ -135,6 +135,11 @@ class SASRecEngine:
         check(self.lib.dr4sr_sum(_p(b.loss_pos), b.loss_pos.numel(), _p(b.loss), _stream()), 'dr4sr_sum')
         return b.loss
 
+    def scale_grads(self, b: _Buffers, upstream: torch.Tensor) -> None:
+        """dq, dscore (computed in the forward sweep with upstream = 1) *= upstream; a no-op kernel when it is 1."""
+        check(self.lib.dr4sr_scale_grads(_p(_req(upstream, torch.float32, 'upstream')), _p(b.counts), self.D, _p(b.dq), _p(b.dscore),
+                                         _stream()), 'dr4sr_scale_grads')
+
     def encode_bwd(self, b: _Buffers, table: torch.Tensor, flat: torch.Tensor, in_ids: torch.Tensor, grads_flat: torch.Tensor,
                    dq: Optional[torch.Tensor] = None, defer_join: bool = False) -> torch.Tensor:
         """defer_join: (SASRec only) return with the weight gradients still in flight on the library's side stream;

@@ -44,8 +44,10 @@ class GRU4Rec(BaseModel):
 
     def _step_backward(self, state, reduce, dloss, dquery) -> None:
         eng = self.engine
-        b, table, in_ids, item_id, neg = state
-        if reduce:
+        b, table, in_ids, item_id, neg, fused_grad = state
+        if fused_grad:
+            eng.scale_grads(b, dloss)
+        elif reduce:
             eng.score_bce(b, table, item_id, neg, want_grad=True, upstream=dloss)
         else:
             eng.score_bce(b, table, item_id, neg, want_grad=True, loss_weight=dloss)

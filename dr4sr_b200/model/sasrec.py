@@ -97,16 +97,21 @@ class SASRec(BaseModel):
             q_dense = torch.empty(in_ids.size(0), eng.L, eng.D, dtype=torch.float32, device=in_ids.device)
         table, in_ids, item_id, neg = self._rows_for(b, in_ids, item_id, neg)     # sharded table: staged rows + remapped ids
         eng.encode(b, table, self._flat, in_ids, train=self.training, q_dense=q_dense)
-        eng.score_bce(b, table, item_id, neg, want_grad=False)
+        # training with the mean loss: ds, dq come out of the same sweep as the loss (scaled by autograd's grad_output
+        # in the backward); the weighted / per-position variants recompute them there
+        fused_grad = bool(reduce and self.training)
+        eng.score_bce(b, table, item_id, neg, want_grad=fused_grad)
         loss = eng.reduce_loss(b).clone() if reduce else b.loss_pos.clone()
         if reduce:
             self._dp_sum(loss)
-        return loss, q_dense, (b, table, in_ids, item_id, neg)
+        return loss, q_dense, (b, table, in_ids, item_id, neg, fused_grad)
 
     def _step_backward(self, state, reduce, dloss, dquery) -> None:
         eng = self.engine
-        b, table, in_ids, item_id, neg = state
-        if reduce:
+        b, table, in_ids, item_id, neg, fused_grad = state
+        if fused_grad:
+            eng.scale_grads(b, dloss)
+        elif reduce:
             eng.score_bce(b, table, item_id, neg, want_grad=True, upstream=dloss)
         else:
             eng.score_bce(b, table, item_id, neg, want_grad=True, loss_weight=dloss)

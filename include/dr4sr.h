@@ -216,6 +216,11 @@ DR4SR_API int dr4sr_score_bce(const float* q_packed, const float* table, const i
                     const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
                     int32_t D, const float* loss_weight, const float* upstream, float* loss_pos, float* dscore,
                     float* dq_packed, dr4sr_stream_t stream);
+/* dq_packed and dscore of a dr4sr_score_bce call made with upstream = NULL, multiplied afterwards by the device scalar
+ * `upstream` (autograd's grad_output arrives only at backward time): lets the forward pass compute the gradients in
+ * the same sweep as the loss; the kernel exits at once when *upstream == 1. */
+DR4SR_API int dr4sr_scale_grads(const float* upstream, const int32_t* counts, int32_t D, float* dq_packed, float* dscore,
+                      dr4sr_stream_t stream);
 
 /* Deterministic sum of loss_pos [n] into loss[0] (reduce=True path). */
 DR4SR_API int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t stream);
