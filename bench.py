@@ -37,6 +37,15 @@ CFG2 = dict(model='SASRec', num_items=100_000, embed_dim=128, max_seq_len=50, ba
             layer_num=2, head_num=2, dropout_rate=0.5)
 
 
+def ncu_traffic():
+    """dram read+write bytes per launch of the top kernels from the committed `ncu --set full` capture (cold cache)."""
+    path = os.path.join(REPO, 'profiles', 'r1_ncu_traffic.json')
+    try:
+        return json.load(open(path))['bytes_per_launch']
+    except Exception:
+        return {}
+
+
 def peaks():
     path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -210,7 +219,9 @@ def kernel_work(name: str, T: int, B: int, c: dict):
     gemm['wgrad_tc'] = 2 * T * (3 * D * D + D * D + 2 * D * F)
     if name in gemm:
         return dict(bound='tensor', work=gemm[name], unit='TFLOP/s')
-    byts = {'adam_table': 24 * c.get('adam_rows', N) * D, 'embed_fwd': 2 * U, 'score_bce': 4 * U, 'table_grad_scatter': 5 * U, 'ln_bwd': 3 * U,
+    nl = c.get('layer_num', 2)
+    byts = {'sasrec_fwd_fused': (2 + 9 * nl) * U,      # gather in + x0 out, per layer qkv 3U + attn, z1, x1, pre, z2, x2 kept for the backward
+            'adam_table': 24 * c.get('adam_rows', N) * D, 'embed_fwd': 2 * U, 'score_bce': 4 * U, 'table_grad_scatter': 5 * U, 'ln_bwd': 3 * U,
             'attn_fwd': 4 * U, 'attn_bwd': 7 * U, 'colsum': 2 * U, 'pos_grad': U}
     if name in byts:
         return dict(bound='hbm', work=byts[name], unit='GB/s')
@@ -375,7 +386,7 @@ def main():
             ach = w['work'] / (per_launch_ms * 1e-3) / (1e12 if w['bound'] == 'tensor' else 1e9)
             peak = pk['tensor'] if w['bound'] == 'tensor' else pk['hbm']
             roof = {'kernel': name, 'bound': w['bound'], 'achieved': ach, 'peak': peak, 'unit': w['unit'], 'frac': ach / peak,
-                    'traffic': None, 'peak_source': pk['source'], 'us_per_launch': per_launch_ms * 1e3,
+                    'traffic': ncu_traffic().get(name), 'peak_source': pk['source'], 'us_per_launch': per_launch_ms * 1e3,
                     'share_of_step': tot / total_kernel_ms,
                     'note': 'algorithmic work uses live (non-pad) tokens; fp32-exact FFMA GEMM measured against the bf16 '
                             'tensor peak' if w['bound'] == 'tensor' else 'algorithmic bytes on live (non-pad) tokens'}

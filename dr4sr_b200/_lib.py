@@ -48,6 +48,7 @@ SIGNATURES = {
     'dr4sr_set_gemm_backend': (c_i32, [c_i32]),
     'dr4sr_set_attn_backend': (c_i32, [c_i32]),
     'dr4sr_set_fused_backend': (c_i32, [c_i32]),
+    'dr4sr_fused_tiles': (c_i32, [c_p, c_i32, c_i32, c_p, c_sz, c_p]),
     'dr4sr_debug_trace': (c_i32, [C.c_void_p]),
     'dr4sr_sasrec_param_count': (c_sz, [C.POINTER(SasrecCfg)]),
     'dr4sr_sasrec_workspace_bytes': (c_sz, [C.POINTER(SasrecCfg)]),

@@ -813,6 +813,16 @@ int launch_fused_tiles(const int32_t* tok_off, int B, int32_t* tiles, cudaStream
   return DR4SR_OK;
 }
 
+}  // namespace dr4sr
+
+extern "C" int dr4sr_fused_tiles(const int32_t* tok_off, int32_t B, int32_t L, int32_t* tiles, size_t tiles_len, dr4sr_stream_t stream) {
+  if (!tok_off || !tiles || B <= 0 || L <= 0 || L > 128) return DR4SR_EINVAL;
+  if (tiles_len < (size_t)dr4sr::fused_tiles_cap(B, L) + 2) return DR4SR_EWORKSPACE;
+  return dr4sr::launch_fused_tiles(tok_off, B, tiles, dr4sr::as_stream(stream));
+}
+
+namespace dr4sr {
+
 int launch_sasrec_fwd_fused(const FusedFwdHost& h, cudaStream_t st) {
   if (!fused_fwd_supported(h.L, 128, 128, 2) || h.n_layer < 1 || h.n_layer > 8) return DR4SR_EINVAL;
   FusedFwdArgs a{};

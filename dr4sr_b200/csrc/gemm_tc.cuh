@@ -41,16 +41,20 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a protocol bug traps (a failed launch the caller sees) instead of spinning forever on the device.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n\t"
-      ".reg .pred P1;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -429,23 +433,32 @@ struct WgradTable { WgradJob job[kMaxWgradJobs]; int count; int total_tiles; int
 
 // instruction descriptor with both operands MN-major
 constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);
-// MN-major SW128 stage [64 tokens x 128 features]: atom(ib, mb) at ib * 8192 + mb * 1024
+// A weight-gradient stage holds kWTok tokens x 128 features per operand in the MN-major SW128 layout: atoms of 64 features x
+// 8 tokens (1 KB); atom(feature block ib, token group mb) at ib * kWFeatStride + mb * 1024.
+constexpr int kWTok = 32;                                   // tokens per stage (two UMMA k-steps)
+constexpr uint32_t kWFeatStride = (kWTok / 8) * 1024;       // 4 KB between the two 64-feature blocks
+constexpr uint32_t kWImg = 2 * kWFeatStride;                // one operand image of a stage = 8 KB
+constexpr uint32_t kWBuf = 4 * kWImg;                       // a_hi, a_lo, b_hi, b_lo = 32 KB; two buffers = kSmemBytes - 1 KB
+static_assert(2 * kWBuf + 1024 == kSmemBytes, "two weight-gradient stage buffers fill the GEMM shared-memory budget");
 __device__ __forceinline__ uint64_t sw128_desc_mn(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(8192 >> 4) << 16;                  // leading byte offset: next 64-feature block
+  d |= (uint64_t)(kWFeatStride >> 4) << 16;          // leading byte offset: next 64-feature block
   d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next 8-token group
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ uint32_t sw128_offset_mn(uint32_t tok, uint32_t feat) {   // tok < 64, feat < 128, feat % 8 == 0
-  return (feat >> 6) * 8192u + (tok >> 3) * 1024u + (tok & 7u) * 128u + (((((feat & 63u) >> 3) ^ (tok & 7u)) & 7u) << 4);
+__device__ __forceinline__ uint32_t sw128_offset_mn(uint32_t tok, uint32_t feat) {   // tok < kWTok, feat < 128, feat % 8 == 0
+  return (feat >> 6) * kWFeatStride + (tok >> 3) * 1024u + (tok & 7u) * 128u + (((((feat & 63u) >> 3) ^ (tok & 7u)) & 7u) << 4);
 }
 
+// One CTA = one 128 x 128 output tile of one job x one token split.  Stages of kWTok tokens are software-pipelined:
+// the fp32 rows of stage s+1 are in flight in registers while stage s is converted (prologue, bf16 hi/lo split) into one
+// of two shared-memory buffers, and the UMMAs of a buffer run asynchronously while the other one is being filled.
 static __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable tab) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ __align__(8) uint64_t bar_buf[2], bar_done;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   int ji = 0;
@@ -456,9 +469,9 @@ static __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable ta
 
   const int R = min(tab.T_cap, tab.tok_dev ? *tab.tok_dev : tab.T_cap);
   int len = (R + tab.n_split - 1) / tab.n_split;
-  len = (len + kBK - 1) / kBK * kBK;
+  len = (len + kWTok - 1) / kWTok * kWTok;
   const int kbeg = min(R, (int)blockIdx.y * len), kend = min(R, kbeg + len);
-  const int nstage = (kend - kbeg + kBK - 1) / kBK;
+  const int nstage = (kend - kbeg + kWTok - 1) / kWTok;
   float* out = job.partial + (size_t)blockIdx.y * job.M_out * job.N_out;
 
   if (nstage == 0) {                                   // no tokens in this split: the partial is zero
@@ -469,12 +482,10 @@ static __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable ta
     return;
   }
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_hi = smem;
-  uint8_t* a_lo = smem + kStageBytes;
-  uint8_t* b_hi = smem + 2 * kStageBytes;
-  uint8_t* b_lo = smem + 3 * kStageBytes;
   if (tid == 0) {
-    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_buf[0], 1);
+    mbar_init(&bar_buf[1], 1);
+    mbar_init(&bar_done, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, kBN);
@@ -483,30 +494,36 @@ static __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable ta
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  // a stage = 64 tokens x 128 features per operand = 1024 16-byte chunks -> 4 per thread per operand;
+  // a stage = kWTok tokens x 128 features per operand = 512 16-byte chunks -> 2 per thread per operand;
   // 16 consecutive lanes read one token's 512 contiguous bytes
   const int fchunk = tid & 15, tsub = tid >> 4;        // feature chunk (8 floats), token within a group of 16
-  for (int s = 0; s < nstage; ++s) {
-    float4 ra[4][2], rb[4][2];
+  float4 ra[2][2], rb[2][2], na[2][2], nb[2][2];
+  auto load_stage = [&](int s, float4 (&xa)[2][2], float4 (&xb)[2][2]) {
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int tok = it * 16 + tsub, gm = kbeg + s * kBK + tok;
+    for (int it = 0; it < 2; ++it) {
+      const int gm = kbeg + s * kWTok + it * 16 + tsub;
       if (gm < kend) {
         const float* pa = job.A + (size_t)gm * job.lda + i0 + fchunk * 8;
         const float* pb = job.B + (size_t)gm * job.ldb + j0 + fchunk * 8;
-        ra[it][0] = *reinterpret_cast<const float4*>(pa); ra[it][1] = *reinterpret_cast<const float4*>(pa + 4);
-        rb[it][0] = *reinterpret_cast<const float4*>(pb); rb[it][1] = *reinterpret_cast<const float4*>(pb + 4);
+        xa[it][0] = *reinterpret_cast<const float4*>(pa); xa[it][1] = *reinterpret_cast<const float4*>(pa + 4);
+        xb[it][0] = *reinterpret_cast<const float4*>(pb); xb[it][1] = *reinterpret_cast<const float4*>(pb + 4);
       } else {
-        ra[it][0] = ra[it][1] = rb[it][0] = rb[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xa[it][0] = xa[it][1] = xb[it][0] = xb[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    if (s > 0) {
-      mbar_wait(&bar_mma, (uint32_t)((s - 1) & 1));
+  };
+  load_stage(0, ra, rb);
+  for (int s = 0; s < nstage; ++s) {
+    uint8_t* buf = smem + (uint32_t)(s & 1) * kWBuf;
+    uint8_t *a_hi = buf, *a_lo = buf + kWImg, *b_hi = buf + 2 * kWImg, *b_lo = buf + 3 * kWImg;
+    if (s + 1 < nstage) load_stage(s + 1, na, nb);      // in flight while this stage is converted
+    if (s >= 2) {                                      // the UMMAs that read this buffer two stages ago are done
+      mbar_wait(&bar_buf[s & 1], (uint32_t)(((s >> 1) - 1) & 1));
       tc_fence_after();
     }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int tok = it * 16 + tsub, gm = kbeg + s * kBK + tok;
+    for (int it = 0; it < 2; ++it) {
+      const int tok = it * 16 + tsub, gm = kbeg + s * kWTok + tok;
       if (gm < kend) {
         if (job.proA != PRO_NONE) {
           const uint32_t idx = (uint32_t)gm * (uint32_t)job.lda + i0 + fchunk * 8;
@@ -534,16 +551,21 @@ static __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable ta
       tc_fence_after();
       const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
 #pragma unroll
-      for (int k = 0; k < kBK / 16; ++k) {             // 16 tokens = two 8-token groups = 2048 bytes
+      for (int k = 0; k < kWTok / 16; ++k) {           // 16 tokens = two 8-token groups = 2048 bytes
         const uint32_t ko = (uint32_t)k * 2048u;
         umma_bf16(tmem, sw128_desc_mn(ah + ko), sw128_desc_mn(bh + ko), kIdescMN, (s > 0 || k > 0) ? 1u : 0u);
         umma_bf16(tmem, sw128_desc_mn(ah + ko), sw128_desc_mn(bl + ko), kIdescMN, 1u);
         umma_bf16(tmem, sw128_desc_mn(al + ko), sw128_desc_mn(bh + ko), kIdescMN, 1u);
       }
-      umma_commit(&bar_mma);
+      umma_commit(&bar_buf[s & 1]);
+      if (s + 1 == nstage) umma_commit(&bar_done);
+    }
+    if (s + 1 < nstage) {
+#pragma unroll
+      for (int it = 0; it < 2; ++it) { ra[it][0] = na[it][0]; ra[it][1] = na[it][1]; rb[it][0] = nb[it][0]; rb[it][1] = nb[it][1]; }
     }
   }
-  mbar_wait(&bar_mma, (uint32_t)((nstage - 1) & 1));
+  mbar_wait(&bar_done, 0u);
   tc_fence_after();
   const int lane = tid & 31, quad = warp & 3, half = warp >> 2;
   const int row = quad * 32 + lane;

@@ -113,6 +113,10 @@ DR4SR_API int dr4sr_set_attn_backend(int backend);
  * packed rows, through every layer: gather, QKV, attention, out-proj+LN, FFN+LN on tcgen05) where the shape allows
  * (D = F = 128, 2 heads); 0 = one kernel per operator.  Both are parity-tested. */
 DR4SR_API int dr4sr_set_fused_backend(int backend);
+/* The tiling the fused kernels run on: greedy groups of whole sequences with <= 128 packed rows (no sequence is split,
+ * so attention never leaves a tile).  tiles[0] = n_tiles, tiles[1 + k] = first sequence of tile k, tiles[1 + n_tiles] = B;
+ * tiles_len (ints) must be >= B*L/64 + 6.  Exposed for tests; dr4sr_sasrec_fwd builds it in its workspace. */
+DR4SR_API int dr4sr_fused_tiles(const int32_t* tok_off, int32_t B, int32_t L, int32_t* tiles, size_t tiles_len, dr4sr_stream_t stream);
 
 DR4SR_API size_t dr4sr_sasrec_param_count(const dr4sr_sasrec_cfg* cfg);
 DR4SR_API size_t dr4sr_sasrec_workspace_bytes(const dr4sr_sasrec_cfg* cfg);

@@ -372,6 +372,38 @@ def test_fused_schedule_matches_per_op_kernels_with_dropout(backend):
     assert rel_err(out[1][3].cpu(), out[0][3].cpu()) < 2e-4
 
 
+@pytest.mark.parametrize('B,L,seed', [(1024, 50, 3), (97, 50, 4), (1, 50, 5), (300, 64, 6), (64, 7, 7)])
+def test_fused_tiles_are_whole_sequences_of_at_most_128_rows(B, L, seed, backend):
+    """The fused kernels' tiling: covers every sequence once, never splits one, <= 128 packed rows per tile, and is
+    the greedy packing (a tile closes only when the next sequence would not fit)."""
+    _need_gpu()
+    if backend != 'fused':
+        pytest.skip('schedule-independent')
+    from dr4sr_b200 import _lib
+    from dr4sr_b200.engine import _p, _stream
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(0 if B > 1 else 1, L + 1, (B,), generator=g)
+    off = torch.zeros(B + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(lens, 0).to(torch.int32)
+    cap = B * L // 64 + 6
+    tiles = torch.full((cap,), -7, dtype=torch.int32, device=DEV)
+    offd = off.to(DEV)
+    _lib.check(_lib.lib().dr4sr_fused_tiles(_p(offd), B, L, _p(tiles), cap, _stream()), 'fused_tiles')
+    t = tiles.cpu().tolist()
+    n = t[0]
+    first = t[1:2 + n]
+    assert first[0] == 0 and first[-1] == B and all(a <= b_ for a, b_ in zip(first, first[1:]))
+    want, r0 = [0], 0                                        # greedy reference
+    for b in range(B):
+        if int(off[b + 1]) - r0 > 128:
+            want.append(b)
+            r0 = int(off[b])
+    assert first[:-1] == want
+    for k in range(n):
+        rows = int(off[first[k + 1]]) - int(off[first[k]])
+        assert 0 <= rows <= 128
+
+
 def test_neg_sampling_range_uniformity_determinism():
     _need_gpu()
     from dr4sr_b200 import engine
