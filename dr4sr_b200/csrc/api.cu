@@ -58,7 +58,7 @@ extern "C" int dr4sr_set_attn_backend(int backend) {
   return DR4SR_OK;
 }
 extern "C" int dr4sr_set_fused_backend(int backend) {
-  if (backend != 0 && backend != 1) return DR4SR_EINVAL;
+  if (backend < 0 || backend > 2) return DR4SR_EINVAL;
   g_fused_backend.store(backend);
   return DR4SR_OK;
 }

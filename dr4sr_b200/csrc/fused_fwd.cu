@@ -785,6 +785,232 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
 #endif
 }
 
+
+// =====================================================================================================================
+// Backward of the position-wise half of a layer as one persistent kernel over 128-row tiles (no sequence alignment needed):
+//   g3   = LN2'(gin; z2)                                     (dz2)
+//   dpre = ((g3 . mask_ffn_out) W2) . mask_ffn_h . gelu'(pre)
+//   dx1  = g3 + dpre W1
+//   g1   = LN1'(dx1; z1)                                     (dz1)
+//   g2   = (g1 . mask_attn_out) Wo                           (gradient w.r.t. the attention output)
+// replacing ln_bwd + gemm_bwd_dpre + gemm_bwd_dx1 + ln_bwd + gemm_bwd_dattn on the critical path.  g3, dpre, dx1, g1 also go
+// to HBM: the weight-gradient GEMMs and the LayerNorm / bias column sums consume them on the side stream.
+struct FusedBwdFfnArgs {
+  const float *gin, *z2, *st2, *pre, *z1, *st1, *gamma2, *gamma1;
+  const uint16_t *w2_hi, *w2_lo, *w1_hi, *w1_lo, *out_hi, *out_lo;   // images of W2^T, W1^T, Wo^T (backward-data operands)
+  float *g3, *dpre, *dx1, *g1, *g2;
+  const int32_t* counts;
+  int T_cap;
+  Dropout d_ffn_out, d_ffn_h, d_attn_out;
+};
+
+// dz = LN'(dy; z, mu, rstd, gamma) for this thread's 64 columns; `gd` holds dy on entry.  Writes dz to `dz_out` (global) and the
+// next A operand dz . mask(dm); optionally parks dz (fp32) in TMEM columns [128,256) for a later residual add.
+__device__ __forceinline__ void ln_bwd_rows(Me me, float* gd, const float* zrows, const float* stats, const float* s_gamma, Dropout dm,
+                                         float* dz_out, bool park, float (*s_x)[128]) {
+  const float mu = me.live ? stats[2 * me.m] : 0.f, rstd = me.live ? stats[2 * me.m + 1] : 0.f;
+  const float* zrow = zrows + (size_t)me.m * 128 + me.half * 64;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float4 zz[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) zz[j] = me.live ? *reinterpret_cast<const float4*>(zrow + g * 16 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float zv[16] = {zz[0].x, zz[0].y, zz[0].z, zz[0].w, zz[1].x, zz[1].y, zz[1].z, zz[1].w,
+                          zz[2].x, zz[2].y, zz[2].z, zz[2].w, zz[3].x, zz[3].y, zz[3].z, zz[3].w};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float xh = (zv[j] - mu) * rstd;
+      gd[g * 16 + j] *= s_gamma[me.half * 64 + g * 16 + j];          // dxhat
+      s1 += gd[g * 16 + j];
+      s2 = fmaf(gd[g * 16 + j], xh, s2);
+    }
+  }
+  s_x[me.half][me.row] = s1;
+  __syncthreads();
+  s1 = (s_x[0][me.row] + s_x[1][me.row]) * (1.0f / 128.0f);
+  __syncthreads();
+  s_x[me.half][me.row] = s2;
+  __syncthreads();
+  s2 = (s_x[0][me.row] + s_x[1][me.row]) * (1.0f / 128.0f);
+  RowDrop rd;
+  rd.init(dm, (uint32_t)me.m);
+  float* orow = dz_out + (size_t)me.m * 128 + me.half * 64;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n0 = me.half * 64 + g * 16;
+    float4 zz[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) zz[j] = me.live ? *reinterpret_cast<const float4*>(zrow + g * 16 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float zv[16] = {zz[0].x, zz[0].y, zz[0].z, zz[0].w, zz[1].x, zz[1].y, zz[1].z, zz[1].w,
+                          zz[2].x, zz[2].y, zz[2].z, zz[2].w, zz[3].x, zz[3].y, zz[3].z, zz[3].w};
+    float v[16], f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = rstd * (gd[g * 16 + j] - s1 - (zv[j] - mu) * rstd * s2);
+    if (me.live) {
+      st_global_v8(orow + g * 16, v);
+      st_global_v8(orow + g * 16 + 8, v + 8);
+    }
+    if (park) tmem_st16(me.trow + kPark + (uint32_t)(g * 16), v);
+    rd.factors16(n0, f);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= f[j];
+    store_image16(v, me.row, n0, me.smem);
+  }
+}
+
+__global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __grid_constant__ FusedBwdFfnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[5];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_x[2][128];
+  __shared__ __align__(16) float s_gam[256];               // gamma2, gamma1
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = min(a.T_cap, *a.counts);
+  const int n_tiles = (T + 127) / 128;
+  if ((int)blockIdx.x >= n_tiles) return;
+
+  Ctx c;
+  c.smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  c.full = &bars[0]; c.empty = &bars[2]; c.acc = &bars[4];
+  c.fetched = 0; c.used = 0; c.n_acc = 0;
+#ifdef DR4SR_TRACE
+  __shared__ int s_trace[256];
+  c.tr_n = 0; c.tr_t0 = clock64(); c.tr_buf = s_trace;
+#endif
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  s_gam[tid] = tid < 128 ? a.gamma2[tid] : a.gamma1[tid - 128];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem = tmem_slot;
+  c.row = (warp & 3) * 32 + lane;
+  c.half = warp >> 2;
+  c.trow = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c.half * 64);
+
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    c.r0 = tile * 128;
+    c.R = min(128, T - c.r0);
+    c.live = c.row < c.R;
+    c.m = c.r0 + c.row;
+    TRACE(1);
+    if (tid == 0 && c.fetched == c.used) prefetch_chunk(c, a.w2_hi, a.w2_lo, 128, 0);   // else queued by the previous tile
+    // ---- g3 = LN2'(gin) -> HBM, park, A operand (g3 . mask_ffn_out) ----
+    {
+      float gd[64];
+      const float* grow = a.gin + (size_t)c.m * 128 + c.half * 64;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 v = c.live ? *reinterpret_cast<const float4*>(grow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gd[4 * j] = v.x; gd[4 * j + 1] = v.y; gd[4 * j + 2] = v.z; gd[4 * j + 3] = v.w;
+      }
+      ln_bwd_rows(me_of(c), gd, a.z2, a.st2, s_gam, a.d_ffn_out, a.g3, true, s_x);
+    }
+    TRACE(2);
+    sync_for_mma();
+    TRACE(3);
+    // ---- dpre = (A W2) . mask_ffn_h . gelu'(pre) -> HBM and the next A operand ----
+    if (tid == 0) issue_chunk(c, a.w2_hi, a.w2_lo, 128, 0, a.w1_hi, a.w1_lo, 128, 0);
+    TRACE(4);
+    wait_acc(c);
+    TRACE(5);
+    {
+      RowDrop rd;
+      rd.init(a.d_ffn_h, (uint32_t)c.m);
+      const float* prow = a.pre + (size_t)c.m * 128 + c.half * 64;
+      float* orow = a.dpre + (size_t)c.m * 128 + c.half * 64;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        const int n0 = c.half * 64 + g * 16;
+        float v[16], f[16];
+        float4 pp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pp[j] = c.live ? *reinterpret_cast<const float4*>(prow + g * 16 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tmem_ld16_nowait(c.trow + (uint32_t)(g * 16), v);
+        rd.factors16(n0, f);
+        tmem_ld_fence(v, true);
+        const float pv[16] = {pp[0].x, pp[0].y, pp[0].z, pp[0].w, pp[1].x, pp[1].y, pp[1].z, pp[1].w,
+                              pp[2].x, pp[2].y, pp[2].z, pp[2].w, pp[3].x, pp[3].y, pp[3].z, pp[3].w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= f[j] * gelu_grad_f(pv[j]);
+        if (c.live) {
+          st_global_v8(orow + g * 16, v);
+          st_global_v8(orow + g * 16 + 8, v + 8);
+        }
+        store_image16(v, c.row, n0, c.smem);
+      }
+    }
+    TRACE(6);
+    sync_for_mma();
+    TRACE(7);
+    // ---- dx1 = g3 + A W1 -> HBM ; g1 = LN1'(dx1) -> HBM and the next A operand (g1 . mask_attn_out) ----
+    if (tid == 0) issue_chunk(c, a.w1_hi, a.w1_lo, 128, 0, a.out_hi, a.out_lo, 128, 0);
+    TRACE(8);
+    wait_acc(c);
+    TRACE(9);
+    {
+      float gd[64];
+      float* xrow = a.dx1 + (size_t)c.m * 128 + c.half * 64;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float r[16];
+        tmem_ld16_nowait(c.trow + (uint32_t)(g * 16), gd + g * 16);
+        tmem_ld16_nowait(c.trow + kPark + (uint32_t)(g * 16), r);
+        tmem_ld_fence(gd + g * 16, true);
+        tmem_ld_fence(r, false);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) gd[g * 16 + j] += r[j];
+        if (c.live) {
+          st_global_v8(xrow + g * 16, gd + g * 16);
+          st_global_v8(xrow + g * 16 + 8, gd + g * 16 + 8);
+        }
+      }
+      TRACE(10);
+      ln_bwd_rows(me_of(c), gd, a.z1, a.st1, s_gam + 128, a.d_attn_out, a.g1, false, s_x);
+    }
+    TRACE(11);
+    sync_for_mma();
+    TRACE(12);
+    // ---- g2 = A Wo -> HBM ----
+    const bool more = tile + (int)gridDim.x < n_tiles;
+    if (tid == 0) issue_chunk(c, a.out_hi, a.out_lo, 128, 0, more ? a.w2_hi : nullptr, a.w2_lo, 128, 0);
+    TRACE(13);
+    wait_acc(c);
+    TRACE(14);
+    {
+      float* orow = a.g2 + (size_t)c.m * 128 + c.half * 64;
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        float v[32];
+        tmem_ld16_nowait(c.trow + (uint32_t)(g * 32), v);
+        tmem_ld16_nowait(c.trow + (uint32_t)(g * 32 + 16), v + 16);
+        tmem_ld_fence(v, true);
+        tmem_ld_fence(v + 16, false);
+        if (c.live) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) st_global_v8(orow + g * 32 + j, v + j);
+        }
+      }
+    }
+    TRACE(15);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(c.tmem, 256);
+#ifdef DR4SR_TRACE
+  if (tid == 0 && g_trace && blockIdx.x < 8)
+    for (int i = 0; i < 2 * c.tr_n; ++i) g_trace[2048 + blockIdx.x * 256 + i] = c.tr_buf[i];
+#endif
+}
+
 }  // namespace
 
 // debug only: install (or clear with null) a host-mapped int buffer of 4 ints per CTA for the progress trace
@@ -846,6 +1072,25 @@ int launch_sasrec_fwd_fused(const FusedFwdHost& h, cudaStream_t st) {
   const int grid = cap < 2 * kNumSMs ? cap : 2 * kNumSMs;
   sasrec_fwd_fused_kernel<<<grid, kFT, kFusedSmem, st>>>(a);
   DR4SR_LAUNCH_CHECK("sasrec_fwd_fused_kernel");
+  return DR4SR_OK;
+}
+
+
+int launch_sasrec_bwd_ffn_fused(const FusedBwdFfnHost& h, cudaStream_t st) {
+  FusedBwdFfnArgs a{};
+  a.gin = h.gin; a.z2 = h.z2; a.st2 = h.st2; a.pre = h.pre; a.z1 = h.z1; a.st1 = h.st1; a.gamma2 = h.gamma2; a.gamma1 = h.gamma1;
+  a.w2_hi = h.img[0]; a.w2_lo = h.img[1]; a.w1_hi = h.img[2]; a.w1_lo = h.img[3]; a.out_hi = h.img[4]; a.out_lo = h.img[5];
+  a.g3 = h.g3; a.dpre = h.dpre; a.dx1 = h.dx1; a.g1 = h.g1; a.g2 = h.g2; a.counts = h.counts; a.T_cap = h.T_cap;
+  a.d_ffn_out = h.d_ffn_out; a.d_ffn_h = h.d_ffn_h; a.d_attn_out = h.d_attn_out;
+  ProfScope prof("sasrec_bwd_ffn_fused", st);
+  if (cudaFuncSetAttribute(sasrec_bwd_ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "sasrec_bwd_ffn_fused smem attribute");
+    return DR4SR_ECUDA;
+  }
+  const int tiles = ceil_div(h.T_cap, 128);
+  const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
+  sasrec_bwd_ffn_fused_kernel<<<grid, kFT, kFusedSmem, st>>>(a);
+  DR4SR_LAUNCH_CHECK("sasrec_bwd_ffn_fused_kernel");
   return DR4SR_OK;
 }
 

@@ -40,6 +40,16 @@ int fused_tiles_cap(int B, int L);
 int launch_fused_tiles(const int32_t* tok_off, int B, int32_t* tiles, cudaStream_t st);
 int launch_sasrec_fwd_fused(const FusedFwdHost& h, cudaStream_t st);
 int fused_fwd_set_trace(int* host_mapped);
+// backward of the position-wise half of a layer (LN2', dpre, dx1, LN1', d(attn)) as one persistent kernel  [fused_fwd.cu]
+struct FusedBwdFfnHost {
+  const float *gin, *z2, *st2, *pre, *z1, *st1, *gamma2, *gamma1;
+  const uint16_t* img[6];   // W2^T hi, lo, W1^T hi, lo, Wo^T hi, lo (backward-data weight images)
+  float *g3, *dpre, *dx1, *g1, *g2;
+  const int32_t* counts;
+  int T_cap;
+  Dropout d_ffn_out, d_ffn_h, d_attn_out;
+};
+int launch_sasrec_bwd_ffn_fused(const FusedBwdFfnHost& h, cudaStream_t st);
 
 // LayerNorm backward over packed rows + column partials  [rowops.cu]
 //   dz = LN'(dy; z, stats, gamma);  partials[blk][0..D) = sum dy*xhat, [D..2D) = sum dy,

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         float4 o;
         o.x = rstd * (g[c].x - s1 - xh[c].x * s2); o.y = rstd * (g[c].y - s1 - xh[c].y * s2);
         o.z = rstd * (g[c].z - s1 - xh[c].z * s2); o.w = rstd * (g[c].w - s1 - xh[c].w * s2);
-        *reinterpret_cast<float4*>(dz + (size_t)row * D + col) = o;
+        if (dz) *reinterpret_cast<float4*>(dz + (size_t)row * D + col) = o;   // null: column partials only
         const uint32_t idx = (uint32_t)row * (uint32_t)D + col;
         const float4 f = bias_drop.factor4(idx);
         acc_bias[c].x += o.x * f.x; acc_bias[c].y += o.y * f.y; acc_bias[c].z += o.z * f.z; acc_bias[c].w += o.w * f.w;

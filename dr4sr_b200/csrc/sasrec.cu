@@ -40,6 +40,7 @@ struct Workspace {
   float *g0, *g2;
   struct Bwd {
     float *g1, *g3, *dqkv, *dpre;
+    float *dx1, *gout;                // fused backward: dx1 rows (LN1' input, re-read by the side stream) and this layer's dx
     float *part_w;                    // [kSplit][3DD + DD + FD + DF] weight-gradient partials
     float *part_ln2, *part_ln1;       // [kLnBwdBlocks][3D]
     float *part_cs_in, *part_cs_b1;   // [kColsumBlocks][3D], [kColsumBlocks][F]
@@ -70,6 +71,7 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
   for (int l = 0; l < c.n_layer; ++l) {
     auto& b = w.bwd[l];
     b.g1 = take(T * D); b.g3 = take(T * D); b.dqkv = take(T * 3 * D); b.dpre = take(T * F);
+    b.dx1 = take(T * D); b.gout = take(T * D);
     b.part_w = take((size_t)kSplit * (3 * D * D + D * D + 2 * F * D));
     b.part_ln2 = take((size_t)kLnBwdBlocks * 3 * D);
     b.part_ln1 = take((size_t)kLnBwdBlocks * 3 * D);
@@ -129,6 +131,29 @@ int build_weight_images(const dr4sr_sasrec_cfg& c, const float* params, const Wo
   }
   return DR4SR_OK;
 }
+// fixed-order reduction of every partial of a layer into the flat gradient buffer
+int reduce_layer_partials(const float* part_w, size_t pw_in, size_t pw_out, size_t pw_w1, size_t pw_w2, const float* part_cs_in,
+                          const float* part_cs_b1, const float* part_ln1, const float* part_ln2, float* lg, const LayerOffsets& lo, int D,
+                          int F, cudaStream_t sw) {
+  ReduceTable tab{};
+  int k = 0;
+  auto seg = [&](const float* src, float* dst, int ns, int64_t stride, int n) { tab.seg[k++] = ReduceSeg{src, dst, ns, stride, n}; };
+  seg(part_w + pw_in, lg + lo.in_w, kSplit, (int64_t)3 * D * D, 3 * D * D);
+  seg(part_w + pw_out, lg + lo.out_w, kSplit, (int64_t)D * D, D * D);
+  seg(part_w + pw_w1, lg + lo.w1, kSplit, (int64_t)F * D, F * D);
+  seg(part_w + pw_w2, lg + lo.w2, kSplit, (int64_t)D * F, D * F);
+  seg(part_cs_in, lg + lo.in_b, kColsumBlocks, 3 * D, 3 * D);
+  seg(part_cs_b1, lg + lo.b1, kColsumBlocks, F, F);
+  seg(part_ln1, lg + lo.g1, kLnBwdBlocks, 3 * D, D);
+  seg(part_ln1 + D, lg + lo.be1, kLnBwdBlocks, 3 * D, D);
+  seg(part_ln1 + 2 * D, lg + lo.out_b, kLnBwdBlocks, 3 * D, D);
+  seg(part_ln2, lg + lo.g2, kLnBwdBlocks, 3 * D, D);
+  seg(part_ln2 + D, lg + lo.be2, kLnBwdBlocks, 3 * D, D);
+  seg(part_ln2 + 2 * D, lg + lo.b2, kLnBwdBlocks, 3 * D, D);
+  tab.count = k;
+  return launch_reduce_segments(tab, sw);
+}
+
 // Side stream for the weight-gradient work of the backward (fork/join with events; also legal inside a
 // CUDA-graph capture of the main stream).  One per device, created on first use, never destroyed.
 struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork[16] = {}, join = nullptr; bool ok = false; };
@@ -335,6 +360,64 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
     const Dropout d_attn_out = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_OUT, l), tr);
     const Dropout d_attn_p = make_dropout(p, c->seed, c->step, layer_site(SITE_ATTN_P, l), tr);
 
+    if (fused_bwd_enabled() && fused_fwd_supported(c->L, D, F, c->n_head)) {
+      // ---- position-wise half of the layer as one persistent kernel (main stream) ----
+      FusedBwdFfnHost h{};
+      h.gin = gin; h.z2 = y.z2; h.st2 = y.st2; h.pre = y.pre; h.z1 = y.z1; h.st1 = y.st1; h.gamma2 = lp + lo.g2; h.gamma1 = lp + lo.g1;
+      h.img[0] = w.img[l].w2_b.hi; h.img[1] = w.img[l].w2_b.lo; h.img[2] = w.img[l].w1_b.hi; h.img[3] = w.img[l].w1_b.lo;
+      h.img[4] = w.img[l].out_b.hi; h.img[5] = w.img[l].out_b.lo;
+      h.g3 = s.g3; h.dpre = s.dpre; h.dx1 = s.dx1; h.g1 = s.g1; h.g2 = w.g2; h.counts = counts; h.T_cap = T;
+      h.d_ffn_out = d_ffn_out; h.d_ffn_h = d_ffn_h; h.d_attn_out = d_attn_out;
+      DR4SR_TRY(launch_sasrec_bwd_ffn_fused(h, st));
+      const Dropout none = no_dropout();
+      if (side.ok) {   // dz2, dpre, dx1, dz1 are final: everything that does not need dqkv starts now (side stream)
+        if (cudaEventRecord(side.fork[2 * l], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[2 * l], 0) != cudaSuccess) {
+          set_cuda_error(cudaGetLastError(), "backward fork");
+          return DR4SR_ECUDA;
+        }
+      }
+      // LayerNorm affine / bias column sums (partials only: dz = null), bias-1 column sums, three weight gradients
+      DR4SR_TRY(launch_ln_bwd(gin, y.z2, y.st2, lp + lo.g2, nullptr, s.part_ln2, D, T, counts, d_ffn_out, sw));
+      DR4SR_TRY(launch_ln_bwd(s.dx1, y.z1, y.st1, lp + lo.g1, nullptr, s.part_ln1, D, T, counts, d_attn_out, sw));
+      DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
+      {
+        tc::WgradTable tab{};
+        tab.job[0] = tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
+        tab.job[1] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
+        tab.job[2] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
+        tab.count = 3; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
+        DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
+      }
+      if (attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head))
+        DR4SR_TRY(launch_attn_tc_bwd(y.qkv, w.g2, in_item_id, tok_off, row_seq, w.tile_first, s.dqkv, c->B, c->L, D, c->n_head,
+                                     d_attn_p, st));
+      else
+        DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, s.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
+      if (side.ok) {
+        if (cudaEventRecord(side.fork[2 * l + 1], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[2 * l + 1], 0) != cudaSuccess) {
+          set_cuda_error(cudaGetLastError(), "backward fork");
+          return DR4SR_ECUDA;
+        }
+      }
+      {  // dx = dz1 + dqkv Win  (layer 0: times the embedding-dropout mask) -> this layer's own output buffer / dx0
+        float* dst = l == 0 ? dx0_packed : s.gout;
+        GemmArgs g = gemm_args(s.dqkv, 3 * D, lp + lo.in_w, D, dst, D, T, D, 3 * D, counts);
+        g.add = s.g1; g.ldadd = D;
+        if (l == 0) g.dropE = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
+        g.tag = "gemm_bwd_dx";
+        DR4SR_TRY(gemm_nn(g, w.img[l].in_b, st));
+      }
+      DR4SR_TRY(launch_colsum(s.dqkv, 3 * D, T, counts, s.part_cs_in, sw));
+      {
+        tc::WgradTable tab{};
+        tab.job[0] = tc::WgradJob{s.dqkv, 3 * D, PRO_NONE, none, xin, D, PRO_NONE, none, 3 * D, D, s.part_w + pw_in, 0};
+        tab.count = 1; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
+        DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
+      }
+      DR4SR_TRY(reduce_layer_partials(s.part_w, pw_in, pw_out, pw_w1, pw_w2, s.part_cs_in, s.part_cs_b1, s.part_ln1, s.part_ln2, lg, lo, D, F, sw));
+      gin = s.gout;
+      continue;
+    }
     // ---- data-gradient chain (main stream) ----
     // LN2 backward: g3 = dz2 ; partials -> dgamma2, dbeta2, db2
     DR4SR_TRY(launch_ln_bwd(gin, y.z2, y.st2, lp + lo.g2, s.g3, s.part_ln2, D, T, counts, d_ffn_out, st));
@@ -425,25 +508,7 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
         DR4SR_TRY(gemm_tn(g, s.part_w + pw_in, sw));
       }
     }
-    {  // fixed-order reduction of every partial of this layer into the flat gradient buffer
-      ReduceTable tab{};
-      int k = 0;
-      auto seg = [&](const float* src, float* dst, int ns, int64_t stride, int n) { tab.seg[k++] = ReduceSeg{src, dst, ns, stride, n}; };
-      seg(s.part_w + pw_in, lg + lo.in_w, kSplit, (int64_t)3 * D * D, 3 * D * D);
-      seg(s.part_w + pw_out, lg + lo.out_w, kSplit, (int64_t)D * D, D * D);
-      seg(s.part_w + pw_w1, lg + lo.w1, kSplit, (int64_t)F * D, F * D);
-      seg(s.part_w + pw_w2, lg + lo.w2, kSplit, (int64_t)D * F, D * F);
-      seg(s.part_cs_in, lg + lo.in_b, kColsumBlocks, 3 * D, 3 * D);
-      seg(s.part_cs_b1, lg + lo.b1, kColsumBlocks, F, F);
-      seg(s.part_ln1, lg + lo.g1, kLnBwdBlocks, 3 * D, D);
-      seg(s.part_ln1 + D, lg + lo.be1, kLnBwdBlocks, 3 * D, D);
-      seg(s.part_ln1 + 2 * D, lg + lo.out_b, kLnBwdBlocks, 3 * D, D);
-      seg(s.part_ln2, lg + lo.g2, kLnBwdBlocks, 3 * D, D);
-      seg(s.part_ln2 + D, lg + lo.be2, kLnBwdBlocks, 3 * D, D);
-      seg(s.part_ln2 + 2 * D, lg + lo.b2, kLnBwdBlocks, 3 * D, D);
-      tab.count = k;
-      DR4SR_TRY(launch_reduce_segments(tab, sw));
-    }
+    DR4SR_TRY(reduce_layer_partials(s.part_w, pw_in, pw_out, pw_w1, pw_w2, s.part_cs_in, s.part_cs_b1, s.part_ln1, s.part_ln2, lg, lo, D, F, sw));
     gin = w.g0;
   }
   if (join) return dr4sr_sasrec_bwd_join(stream);

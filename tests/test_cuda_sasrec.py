@@ -22,16 +22,17 @@ DEV = 'cuda:0'
 TOL = {'tc': dict(fwd=1e-4, loss=1e-4, grad=1e-3, adam=1e-4), 'ffma': dict(fwd=1e-5, loss=1e-5, grad=1e-4, adam=2e-5)}
 TOL['tc_attn'] = TOL['tc']          # tcgen05 dense layers + tcgen05 attention tiles
 TOL['fused'] = TOL['tc']            # persistent fused encoder kernels (default schedule)
+TOL['fused_bwd'] = TOL['tc']        # + fused backward FFN block
 
 
-@pytest.fixture(params=['fused', 'tc', 'tc_attn', 'ffma'], autouse=True)
+@pytest.fixture(params=['fused', 'fused_bwd', 'tc', 'tc_attn', 'ffma'], autouse=True)
 def backend(request):
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     from dr4sr_b200 import _lib
     _lib.check(_lib.lib().dr4sr_set_gemm_backend(1 if request.param == 'ffma' else 0), 'set_gemm_backend')
     _lib.check(_lib.lib().dr4sr_set_attn_backend(1 if request.param == 'tc_attn' else 0), 'set_attn_backend')
-    _lib.check(_lib.lib().dr4sr_set_fused_backend(1 if request.param == 'fused' else 0), 'set_fused_backend')
+    _lib.check(_lib.lib().dr4sr_set_fused_backend({'fused': 1, 'fused_bwd': 2}.get(request.param, 0)), 'set_fused_backend')
     yield request.param
     _lib.lib().dr4sr_set_gemm_backend(0)
     _lib.lib().dr4sr_set_attn_backend(0)
@@ -355,7 +356,7 @@ def test_fused_schedule_matches_per_op_kernels_with_dropout(backend):
     m = make_model(N, D, p=0.5).train()
     batch = to_dev(synthetic_batch(97, 50, N, seed=21))
     out = {}
-    for fused in (1, 0):
+    for fused in (1, 2, 0):
         _lib.check(_lib.lib().dr4sr_set_fused_backend(fused), 'set_fused_backend')
         m.engine.step = 40
         m.optimizer.zero_grad()
@@ -365,11 +366,12 @@ def test_fused_schedule_matches_per_op_kernels_with_dropout(backend):
                       [p.grad.clone() for p in m.query_encoder.flat_parameters()], m.item_embedding.weight.grad.clone())
     _lib.lib().dr4sr_set_fused_backend(1)
     n = int(m.engine.buffers(97).counts[0])
-    assert abs(out[1][0] - out[0][0]) / abs(out[0][0]) < 1e-5
-    assert rel_err(out[1][1][:n].cpu(), out[0][1][:n].cpu()) < 2e-5
-    for a, b_ in zip(out[1][2], out[0][2]):
-        assert rel_err(a.cpu(), b_.cpu()) < 2e-4
-    assert rel_err(out[1][3].cpu(), out[0][3].cpu()) < 2e-4
+    for sched in (1, 2):
+        assert abs(out[sched][0] - out[0][0]) / abs(out[0][0]) < 1e-5
+        assert rel_err(out[sched][1][:n].cpu(), out[0][1][:n].cpu()) < 2e-5
+        for a, b_ in zip(out[sched][2], out[0][2]):
+            assert rel_err(a.cpu(), b_.cpu()) < 2e-4
+        assert rel_err(out[sched][3].cpu(), out[0][3].cpu()) < 2e-4
 
 
 @pytest.mark.parametrize('B,L,seed', [(1024, 50, 3), (97, 50, 4), (1, 50, 5), (300, 64, 6), (64, 7, 7)])
