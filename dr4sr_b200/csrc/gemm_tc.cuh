@@ -107,6 +107,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global accesses (32-byte aligned): a thread that owns a row moves a full 32 B sector per instruction
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]),
+               "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p) : "memory");
+}
+
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 64 bf16 (128 B), 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -307,29 +317,46 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
       tmem_ld32(trow + (uint32_t)(c * 32), v);
       if (!live) continue;
       const int nb = n0 + ncol0 + c * 32;
+      const bool wide = ((g.ldc | g.ldadd) & 7) == 0;      // 32-byte aligned rows: 256-bit row accesses
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < 32; j += 8) {
         const int n = nb + j;
-        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        float o[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
         if (EPI == TC_GELU_BWD) {
-          const float4 p = *reinterpret_cast<const float4*>(g.pre + (size_t)m * g.ldc + n);
-          const float4 f = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n);
-          o.x *= f.x * gelu_grad_f(p.x); o.y *= f.y * gelu_grad_f(p.y); o.z *= f.z * gelu_grad_f(p.z); o.w *= f.w * gelu_grad_f(p.w);
+          float p[8];
+          if (wide) ld_global_v8(g.pre + (size_t)m * g.ldc + n, p);
+          else {
+            const float4 p0 = *reinterpret_cast<const float4*>(g.pre + (size_t)m * g.ldc + n), p1 = *reinterpret_cast<const float4*>(g.pre + (size_t)m * g.ldc + n + 4);
+            p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
+          }
+          const float4 f0 = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n), f1 = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n + 4);
+          o[0] *= f0.x * gelu_grad_f(p[0]); o[1] *= f0.y * gelu_grad_f(p[1]); o[2] *= f0.z * gelu_grad_f(p[2]); o[3] *= f0.w * gelu_grad_f(p[3]);
+          o[4] *= f1.x * gelu_grad_f(p[4]); o[5] *= f1.y * gelu_grad_f(p[5]); o[6] *= f1.z * gelu_grad_f(p[6]); o[7] *= f1.w * gelu_grad_f(p[7]);
         } else {
           if (g.bias) {
-            const float4 bb = *reinterpret_cast<const float4*>(g.bias + n);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n), b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);
+            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
           }
           if (g.add) {
-            const float4 aa = *reinterpret_cast<const float4*>(g.add + (size_t)m * g.ldadd + n);
-            o.x += aa.x; o.y += aa.y; o.z += aa.z; o.w += aa.w;
+            float a[8];
+            if (wide) ld_global_v8(g.add + (size_t)m * g.ldadd + n, a);
+            else {
+              const float4 a0 = *reinterpret_cast<const float4*>(g.add + (size_t)m * g.ldadd + n), a1 = *reinterpret_cast<const float4*>(g.add + (size_t)m * g.ldadd + n + 4);
+              a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] += a[q];
           }
           if (g.dropE.thresh) {
-            const float4 f = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n);
-            o.x *= f.x; o.y *= f.y; o.z *= f.z; o.w *= f.w;
+            const float4 f0 = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n), f1 = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n + 4);
+            o[0] *= f0.x; o[1] *= f0.y; o[2] *= f0.z; o[3] *= f0.w; o[4] *= f1.x; o[5] *= f1.y; o[6] *= f1.z; o[7] *= f1.w;
           }
         }
-        *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = o;
+        if (wide) st_global_v8(g.C + (size_t)m * g.ldc + n, o);
+        else {
+          *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(g.C + (size_t)m * g.ldc + n + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
       }
     }
   } else {
