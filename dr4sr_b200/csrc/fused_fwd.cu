@@ -605,8 +605,9 @@ __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, co
       tmem_ld16(to + (uint32_t)(g * 16), o);
       if (c.live) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4*>(dst + g * 16 + j) = make_float4(o[j] * inv, o[j + 1] * inv, o[j + 2] * inv, o[j + 3] * inv);
+        for (int j = 0; j < 16; ++j) o[j] *= inv;
+        st_global_v8(dst + g * 16, o);
+        st_global_v8(dst + g * 16 + 8, o + 8);
       }
     }
   }
@@ -679,23 +680,28 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       rd.init(a.d_embed, (uint32_t)c.m);
       const float* e = a.table + (size_t)s_id[c.row] * 128 + c.half * 64;
       const float* p = a.pos + (size_t)(c.row - s_start[c.row]) * 128 + c.half * 64;
-      float4 ev[16];                                            // the thread's 64 table floats: every load in flight at once
+      float ev[64];                                             // the thread's 64 table floats: every (256-bit) load in flight at once
 #pragma unroll
-      for (int j = 0; j < 16; ++j) ev[j] = c.live ? *reinterpret_cast<const float4*>(e + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 8; ++j) {
+        if (c.live) ld_global_v8(e + 8 * j, ev + 8 * j);
+        else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ev[8 * j + q] = 0.f;
+        }
+      }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int n0 = c.half * 64 + g * 16;
         float v[16], f[16];
         if (c.live) {
           rd.factors16(n0, f);
+          float pv[16];
+          ld_global_v8(p + g * 16, pv);
+          ld_global_v8(p + g * 16 + 8, pv + 8);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 pv = *reinterpret_cast<const float4*>(p + g * 16 + j);
-            const float4 x = ev[g * 4 + j / 4];
-            v[j] = (x.x + pv.x) * f[j]; v[j + 1] = (x.y + pv.y) * f[j + 1];
-            v[j + 2] = (x.z + pv.z) * f[j + 2]; v[j + 3] = (x.w + pv.w) * f[j + 3];
-            *reinterpret_cast<float4*>(a.x0 + (size_t)c.m * 128 + n0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
+          for (int j = 0; j < 16; ++j) v[j] = (ev[g * 16 + j] + pv[j]) * f[j];
+          st_global_v8(a.x0 + (size_t)c.m * 128 + n0, v);
+          st_global_v8(a.x0 + (size_t)c.m * 128 + n0 + 8, v + 8);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
