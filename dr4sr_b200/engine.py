@@ -132,8 +132,10 @@ class SASRecEngine:
         return b.loss_pos
 
     def reduce_loss(self, b: _Buffers) -> torch.Tensor:
-        check(self.lib.dr4sr_sum(_p(b.loss_pos), b.loss_pos.numel(), _p(b.loss), _stream()), 'dr4sr_sum')
-        return b.loss
+        """Sum of the per-slot loss terms into a FRESH scalar (the caller keeps it; no clone needed)."""
+        out = torch.empty((), dtype=torch.float32, device=self.device)
+        check(self.lib.dr4sr_sum(_p(b.loss_pos), b.loss_pos.numel(), _p(out), _stream()), 'dr4sr_sum')
+        return out
 
     def scale_grads(self, b: _Buffers, upstream: torch.Tensor) -> None:
         """dq, dscore (computed in the forward sweep with upstream = 1) *= upstream; a no-op kernel when it is 1."""
@@ -279,8 +281,9 @@ class FMLPEngine:
         return b.loss_pos
 
     def reduce_loss(self, b: _FmlpBuffers) -> torch.Tensor:
-        check(self.lib.dr4sr_sum(_p(b.loss_pos), b.loss_pos.numel(), _p(b.loss), _stream()), 'dr4sr_sum')
-        return b.loss
+        out = torch.empty((), dtype=torch.float32, device=self.device)
+        check(self.lib.dr4sr_sum(_p(b.loss_pos), b.loss_pos.numel(), _p(out), _stream()), 'dr4sr_sum')
+        return out
 
     def encode_bwd(self, b: _FmlpBuffers, table: torch.Tensor, flat: torch.Tensor, in_ids: torch.Tensor, grads_flat: torch.Tensor) -> None:
         B = in_ids.size(0)

@@ -97,7 +97,7 @@ class FMLP(BaseModel):
             eng.step += 1
         eng.encode(b, table, self._flat, in_ids, train=self.training)
         eng.score_bce(b, table, item_id, neg, want_grad=False)
-        loss = eng.reduce_loss(b).clone() if reduce else b.loss_pos.clone()
+        loss = eng.reduce_loss(b) if reduce else b.loss_pos.clone()
         if reduce:
             self._dp_sum(loss)
         return loss, (b.q_last.clone() if return_query else None), (b, in_ids, item_id, neg)

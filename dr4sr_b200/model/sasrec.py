@@ -101,7 +101,7 @@ class SASRec(BaseModel):
         # in the backward); the weighted / per-position variants recompute them there
         fused_grad = bool(reduce and self.training)
         eng.score_bce(b, table, item_id, neg, want_grad=fused_grad)
-        loss = eng.reduce_loss(b).clone() if reduce else b.loss_pos.clone()
+        loss = eng.reduce_loss(b) if reduce else b.loss_pos.clone()
         if reduce:
             self._dp_sum(loss)
         return loss, q_dense, (b, table, in_ids, item_id, neg, fused_grad)
