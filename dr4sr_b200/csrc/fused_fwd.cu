@@ -492,9 +492,17 @@ __device__ __noinline__ void epi_ln(Me me, const float* s_b, const float* s_g, c
   if (me.live && me.half == 0) { stats[2 * me.m] = mu; stats[2 * me.m + 1] = rstd; }
 }
 
+// bit j set <=> key c0 + j lies in the row's causal window [start, row] (and the row exists)
+__device__ __forceinline__ uint32_t key_bits(bool live, int start, int row, int c0) {
+  const int lo = max(start - c0, 0), hi = min(row - c0, 15);
+  if (!live || hi < lo) return 0u;
+  return ((2u << hi) - 1u) & ~((1u << lo) - 1u);
+}
+
 // ---- attention of one head over the tile (block-diagonal causal mask) -----------------------------------
+// s_padbits[g]: bit j set <=> key 16 g + j is a real (non-pad) item
 __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, const FusedLayer& y, int h, const int* s_start,
-                                               const int* s_seq, const int* s_pad, float (*s_x)[128]) {
+                                               const int* s_seq, const uint32_t* s_padbits, float (*s_x)[128]) {
   const int tid = threadIdx.x;
   uint8_t *q_hi = c.smem, *q_lo = c.smem + kImg, *k_hi = c.smem + 2 * kImg, *k_lo = c.smem + 3 * kImg;
   uint8_t *v_hi = c.smem + 4 * kImg, *v_lo = c.smem + 5 * kImg;
@@ -531,12 +539,9 @@ __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, co
     const int c0 = c.half * 64 + g * 16;
     float s[16];
     tmem_ld16(c.trow + (uint32_t)(g * 16), s);
+    const uint32_t okb = key_bits(c.live, start, row, c0) & s_padbits[c0 >> 4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int key = c0 + j;
-      const bool ok = c.live && key >= start && key <= row && !s_pad[key];
-      mx = fmaxf(mx, ok ? s[j] * a.scale : -INFINITY);
-    }
+    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, (okb >> j & 1u) ? s[j] * a.scale : -INFINITY);
   }
   s_x[c.half][row] = mx;
   __syncthreads();
@@ -556,17 +561,22 @@ __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, co
     const uint32_t idx0 = dbase + (uint32_t)(c0 - start);
     uint32_t e16[8];
     if (dp.thresh != 0u) {
-      const uint32_t p0 = idx0 >> 1, odd = idx0 & 1u;
+      // draw32(key, p) = mix32(p * C + key) ^ mix32(key ^ (p >> 7)); the nine pair indices p0 .. p0+8 span at most two values of p >> 7
+      const uint32_t p0 = idx0 >> 1, odd = idx0 & 1u, hi0 = p0 >> 7;
+      const uint32_t ha = mix32(dp.key ^ hi0), hb = mix32(dp.key ^ (hi0 + 1u));
       uint32_t d[9];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) d[k] = draw32(dp.key, p0 + (uint32_t)k);
+      for (int k = 0; k < 9; ++k) {
+        const uint32_t pk = p0 + (uint32_t)k;
+        d[k] = mix32(pk * 0x9E3779B1u + dp.key) ^ ((pk >> 7) == hi0 ? ha : hb);
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) e16[k] = odd ? __funnelshift_r(d[k], d[k + 1], 16) : d[k];
     }
+    const uint32_t okb = mx > -INFINITY ? key_bits(c.live, start, row, c0) & s_padbits[c0 >> 4] : 0u;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int key = c0 + j;
-      const bool ok = c.live && key >= start && key <= row && !s_pad[key] && mx > -INFINITY;
+      const bool ok = okb >> j & 1u;
       const float e = ok ? expf(s[j] * a.scale - mx) : 0.f;
       sum += e;
       float f = dp.scale;
@@ -623,7 +633,8 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
-  __shared__ int s_start[128], s_seq[128], s_pad[128], s_id[128];
+  __shared__ int s_start[128], s_seq[128], s_id[128];
+  __shared__ uint32_t s_padbits[8];
   __shared__ float s_x[2][128];
   __shared__ __align__(16) float s_par[kParTotal];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -668,8 +679,13 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
         st = off - c.r0;
         id = (int)a.in_ids[(size_t)sq * a.L + (c.r0 + tid - off)];
         pd = id == 0;
+        // pull the whole 512 B table row into L2 as ONE contiguous request: the row-per-thread gather below would
+        // otherwise reach DRAM as scattered 32 B sectors
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.table + (size_t)id * 128), "r"(512) : "memory");
       }
-      s_start[tid] = st; s_seq[tid] = sq; s_pad[tid] = pd; s_id[tid] = id;
+      s_start[tid] = st; s_seq[tid] = sq; s_id[tid] = id;
+      const uint32_t real = __ballot_sync(0xffffffffu, !pd);        // warps 0..3 are complete: 32 keys each
+      if (lane == 0) { s_padbits[2 * warp] = real & 0xFFFFu; s_padbits[2 * warp + 1] = real >> 16; }
     }
     TRACE(1);
     if (tid == 0) prefetch_chunk(c, a.layer[0].in_hi, a.layer[0].in_lo, 384, 0);
@@ -745,7 +761,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         TRACE(100 * l + 20 + h);
-        attention_head(c, a, y, h, s_start, s_seq, s_pad, s_x);
+        attention_head(c, a, y, h, s_start, s_seq, s_padbits, s_x);
       }
       TRACE(100 * l + 30);
       // ---- out-proj + dropout + residual + LN1 (x1 -> park and the FFN-up operand) ----
