@@ -94,21 +94,29 @@ struct FusedFwdArgs {
 // ---- tiles: greedy groups of whole sequences with <= 128 packed rows ------------------------------
 // tiles[0] = n_tiles, tiles[1 + k] = first sequence of tile k, tiles[1 + n_tiles] = B.
 __global__ void __launch_bounds__(1024) fused_tiles_kernel(const int32_t* __restrict__ tok_off, int B, int32_t* __restrict__ tiles) {
-  extern __shared__ int32_t s_off[];
+  extern __shared__ int32_t s_off[];            // [B + 1] offsets, then [B] next-tile-start of a tile opened at sequence b
+  int32_t* s_nxt = s_off + (B + 1);
   for (int i = threadIdx.x; i <= B; i += blockDim.x) s_off[i] = tok_off[i];
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int k = 0, r0 = 0;
-    tiles[1] = 0;
-    for (int b = 0; b < B; ++b) {
-      if (s_off[b + 1] - r0 > 128) {          // sequence b does not fit: it opens the next tile
-        ++k;
-        tiles[1 + k] = b;
-        r0 = s_off[b];
-      }
+  // greedy packing: a tile opened at sequence s closes before the first b > s with off[b + 1] - off[s] > 128.  Every b
+  // finds its successor by binary search in parallel; one thread then follows the ~T/110 links.
+  for (int s0 = threadIdx.x; s0 < B; s0 += blockDim.x) {
+    const int lim = s_off[s0] + 128;
+    int lo = s0 + 1, hi = B + 1;                 // smallest j in [s0 + 1, B] with off[j] > lim, or B + 1
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] > lim) hi = mid; else lo = mid + 1;
     }
-    if (s_off[B] - r0 > 0 || k == 0) ++k;      // the open tile (or a single empty one)
-    tiles[1 + k] = B;
+    s_nxt[s0] = lo > B ? B : lo - 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int k = 0, s0 = 0;
+    tiles[1] = 0;
+    while (s0 < B) {
+      s0 = s_nxt[s0];
+      tiles[1 + ++k] = s0;
+    }
     tiles[0] = k;
   }
 }
@@ -1048,7 +1056,7 @@ bool fused_fwd_supported(int L, int D, int F, int n_head) { return D == 128 && F
 int fused_tiles_cap(int B, int L) { return (B * L) / 64 + 4; }   // two consecutive greedy tiles hold > 128 rows
 
 int launch_fused_tiles(const int32_t* tok_off, int B, int32_t* tiles, cudaStream_t st) {
-  const size_t smem = (size_t)(B + 1) * sizeof(int32_t);
+  const size_t smem = (size_t)(2 * B + 1) * sizeof(int32_t);
   if (smem > 200 * 1024) return DR4SR_EINVAL;
   ProfScope prof("fused_tiles", st);
   if (smem > 48 * 1024 &&

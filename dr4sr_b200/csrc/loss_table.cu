@@ -74,8 +74,12 @@ __global__ void __launch_bounds__(256) score_bce_kernel(const float* __restrict_
 
 // fixed-shape tree: every thread strides the array, then a block reduction; single CTA => deterministic
 __global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
-  float s = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;           // four loads in flight per thread; fixed combination order
+  const int64_t step = blockDim.x;
+  int64_t i = threadIdx.x;
+  for (; i + 3 * step < n; i += 4 * step) { s0 += x[i]; s1 += x[i + step]; s2 += x[i + 2 * step]; s3 += x[i + 3 * step]; }
+  for (; i < n; i += step) s0 += x[i];
+  float s = (s0 + s1) + (s2 + s3);
   s = warp_sum(s);
   __shared__ float part[32];
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
