@@ -108,57 +108,54 @@ __device__ __forceinline__ void mm_abt(const float* __restrict__ A, const float*
 // C[r][4c..4c+3] = sum_x S(r,x) * M[x][4c..], S(r,x) = TRANS ? S[x][r] : S[r][x].
 // Causal structure: !TRANS sums x <= r (keys up to the query), TRANS sums x >= r (queries from the key
 // on); S holds exact zeros outside the band, so the loop bounds only have to cover it.
+// A thread owns 4 CONSECUTIVE rows r = 4 tr .. 4 tr + 3 and one float4 of columns, so that its four S operands of a
+// step are one 16-byte shared load (a row segment for !TRANS, a column segment of the transposed access for TRANS):
+// 8 LDS.128 per 64 FMAs.  Rows >= len read stale but in-bounds shared memory and are never reported.
 template <bool TRANS, class Out>
 __device__ __forceinline__ void mm_pv(const float* __restrict__ S, int lds, const float* __restrict__ M, int ld, int len, int dh, Out out) {
   const int ncol = dh / 4;                       // float4 columns (16 for dh = 64)
   const int tc = threadIdx.x % ncol, tr = threadIdx.x / ncol;
-  const int rstep = kAttnThreads / ncol;         // row stride between a thread's rows (16 for dh = 64)
-  for (int r0 = tr; r0 < len; r0 += 4 * rstep) {
-    const int na = min(4, (len - r0 + rstep - 1) / rstep);          // live rows of this thread
-    const int na_u = min(4, (len - (r0 - tr) + rstep - 1) / rstep); // CTA-uniform bound for the unrolled body
+  const int rows_per_pass = 4 * (kAttnThreads / ncol);
+  for (int rb = 4 * tr; rb < len; rb += rows_per_pass) {
     float4 acc[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int x_lo = TRANS ? r0 : 0, x_hi = TRANS ? len : min(len, r0 + (na - 1) * rstep + 1);
-    // rows >= len read S as 0 through a clamped, always-valid address (their results are discarded)
+    const int x_lo = TRANS ? rb : 0, x_hi = TRANS ? len : min(len, rb + 4);
     int rs[4];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) rs[a] = min(r0 + a * rstep, len - 1);
-    int x = x_lo;
-    for (; x + 3 < x_hi; x += 4) {                 // 4 keys per trip: 4 + 16 independent shared loads in flight
-      float4 m[4];
-      float sv[4][4];
+    for (int a = 0; a < 4; ++a) rs[a] = min(rb + a, len - 1);        // !TRANS: clamped, always-valid row addresses
+    int x = x_lo;                                                  // multiple of 4 in both cases
+    for (; x + 3 < x_hi; x += 4) {
+      float4 m[4], sv[4];                        // sv[u].{x,y,z,w} = S(rb + {0,1,2,3}, x + u)  (TRANS) ; sv[a] = S(rb + a, x .. x+3) (!TRANS)
 #pragma unroll
       for (int u = 0; u < 4; ++u) m[u] = *reinterpret_cast<const float4*>(M + (x + u) * ld + tc * 4);
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-        if (a < na_u) {
+      for (int q = 0; q < 4; ++q)
+        sv[q] = TRANS ? *reinterpret_cast<const float4*>(S + (x + q) * lds + rb) : *reinterpret_cast<const float4*>(S + rs[q] * lds + x);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) sv[a][u] = TRANS ? S[(x + u) * lds + rs[a]] : S[rs[a] * lds + x + u];
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 t = TRANS ? sv[u] : sv[a];
+          const int k = TRANS ? a : u;
+          const float s = k == 0 ? t.x : (k == 1 ? t.y : (k == 2 ? t.z : t.w));
+          acc[a].x = fmaf(s, m[u].x, acc[a].x); acc[a].y = fmaf(s, m[u].y, acc[a].y);
+          acc[a].z = fmaf(s, m[u].z, acc[a].z); acc[a].w = fmaf(s, m[u].w, acc[a].w);
         }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-        if (a < na_u) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            acc[a].x = fmaf(sv[a][u], m[u].x, acc[a].x); acc[a].y = fmaf(sv[a][u], m[u].y, acc[a].y);
-            acc[a].z = fmaf(sv[a][u], m[u].z, acc[a].z); acc[a].w = fmaf(sv[a][u], m[u].w, acc[a].w);
-          }
-        }
+      }
     }
     for (; x < x_hi; ++x) {
       const float4 m = *reinterpret_cast<const float4*>(M + x * ld + tc * 4);
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
-        if (a < na_u) {
-          const float s = TRANS ? S[x * lds + rs[a]] : S[rs[a] * lds + x];
-          acc[a].x = fmaf(s, m.x, acc[a].x); acc[a].y = fmaf(s, m.y, acc[a].y);
-          acc[a].z = fmaf(s, m.z, acc[a].z); acc[a].w = fmaf(s, m.w, acc[a].w);
-        }
+      for (int a = 0; a < 4; ++a) {
+        const float s = TRANS ? S[x * lds + rb + a] : S[rs[a] * lds + x];
+        acc[a].x = fmaf(s, m.x, acc[a].x); acc[a].y = fmaf(s, m.y, acc[a].y);
+        acc[a].z = fmaf(s, m.z, acc[a].z); acc[a].w = fmaf(s, m.w, acc[a].w);
+      }
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
-      if (r0 + a * rstep < len) out(r0 + a * rstep, tc * 4, acc[a]);
+      if (rb + a < len) out(rb + a, tc * 4, acc[a]);
   }
 }
 
