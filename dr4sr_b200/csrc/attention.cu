@@ -66,33 +66,36 @@ __device__ __forceinline__ void load_qkv(const float* __restrict__ src, int D, i
 // b > a that lie strictly above the causal diagonal (their outputs are reported as `above`).
 // Rows >= len of A / B hold stale shared memory; each output depends only on its own two rows, and
 // outputs with i or j >= len are never reported.
+// Packed fp32x2 FMA (FFMA2 on sm_100): both halves of a 64-bit register pair in one instruction.
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 template <class Out>
 __device__ __forceinline__ void mm_abt(const float* __restrict__ A, const float* __restrict__ B, int ld, int len, int dh, Out out) {
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
   const int nblk = (len + 15) >> 4;                       // CTA-uniform
-  float acc[4][4];
+  unsigned long long acc[4][4];                           // two partial sums (even / odd d) per output, FFMA2-accumulated
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0ull;
 #pragma unroll 2
   for (int d = 0; d < dh; d += 4) {
-    float4 av[4], bv[4];
+    ulonglong2 av[4], bv[4];                               // {x,y}, {z,w} of a float4
 #pragma unroll
     for (int a = 0; a < 4; ++a)
       if (a < nblk) {
-        av[a] = *reinterpret_cast<const float4*>(A + (ti + 16 * a) * ld + d);
-        bv[a] = *reinterpret_cast<const float4*>(B + (tj + 16 * a) * ld + d);
+        av[a] = *reinterpret_cast<const ulonglong2*>(A + (ti + 16 * a) * ld + d);
+        bv[a] = *reinterpret_cast<const ulonglong2*>(B + (tj + 16 * a) * ld + d);
       }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
       if (a < nblk) {
 #pragma unroll
         for (int b = 0; b <= a; ++b) {
-          acc[a][b] = fmaf(av[a].x, bv[b].x, acc[a][b]);
-          acc[a][b] = fmaf(av[a].y, bv[b].y, acc[a][b]);
-          acc[a][b] = fmaf(av[a].z, bv[b].z, acc[a][b]);
-          acc[a][b] = fmaf(av[a].w, bv[b].w, acc[a][b]);
+          ffma2(acc[a][b], av[a].x, bv[b].x);
+          ffma2(acc[a][b], av[a].y, bv[b].y);
         }
       }
   }
@@ -101,7 +104,8 @@ __device__ __forceinline__ void mm_abt(const float* __restrict__ A, const float*
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int i = ti + 16 * a, j = tj + 16 * b;
-      if (i < len && j < len) out(i, j, acc[a][b], b > a);
+      if (i < len && j < len)
+        out(i, j, __uint_as_float((uint32_t)acc[a][b]) + __uint_as_float((uint32_t)(acc[a][b] >> 32)), b > a);
     }
 }
 
@@ -117,18 +121,19 @@ __device__ __forceinline__ void mm_pv(const float* __restrict__ S, int lds, cons
   const int tc = threadIdx.x % ncol, tr = threadIdx.x / ncol;
   const int rows_per_pass = 4 * (kAttnThreads / ncol);
   for (int rb = 4 * tr; rb < len; rb += rows_per_pass) {
-    float4 acc[4];
+    unsigned long long acc[4][2];                 // {x,y}, {z,w} of the thread's float4 of columns, FFMA2-accumulated
 #pragma unroll
-    for (int a = 0; a < 4; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = 0ull;
     const int x_lo = TRANS ? rb : 0, x_hi = TRANS ? len : min(len, rb + 4);
     int rs[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) rs[a] = min(rb + a, len - 1);        // !TRANS: clamped, always-valid row addresses
     int x = x_lo;                                                  // multiple of 4 in both cases
     for (; x + 3 < x_hi; x += 4) {
-      float4 m[4], sv[4];                        // sv[u].{x,y,z,w} = S(rb + {0,1,2,3}, x + u)  (TRANS) ; sv[a] = S(rb + a, x .. x+3) (!TRANS)
+      ulonglong2 m[4];
+      float4 sv[4];                              // sv[u].{x,y,z,w} = S(rb + {0,1,2,3}, x + u)  (TRANS) ; sv[a] = S(rb + a, x .. x+3) (!TRANS)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) m[u] = *reinterpret_cast<const float4*>(M + (x + u) * ld + tc * 4);
+      for (int u = 0; u < 4; ++u) m[u] = *reinterpret_cast<const ulonglong2*>(M + (x + u) * ld + tc * 4);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         sv[q] = TRANS ? *reinterpret_cast<const float4*>(S + (x + q) * lds + rb) : *reinterpret_cast<const float4*>(S + rs[q] * lds + x);
@@ -139,23 +144,29 @@ __device__ __forceinline__ void mm_pv(const float* __restrict__ S, int lds, cons
           const float4 t = TRANS ? sv[u] : sv[a];
           const int k = TRANS ? a : u;
           const float s = k == 0 ? t.x : (k == 1 ? t.y : (k == 2 ? t.z : t.w));
-          acc[a].x = fmaf(s, m[u].x, acc[a].x); acc[a].y = fmaf(s, m[u].y, acc[a].y);
-          acc[a].z = fmaf(s, m[u].z, acc[a].z); acc[a].w = fmaf(s, m[u].w, acc[a].w);
+          unsigned long long ss;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+          ffma2(acc[a][0], ss, m[u].x);
+          ffma2(acc[a][1], ss, m[u].y);
         }
       }
     }
     for (; x < x_hi; ++x) {
-      const float4 m = *reinterpret_cast<const float4*>(M + x * ld + tc * 4);
+      const ulonglong2 m = *reinterpret_cast<const ulonglong2*>(M + x * ld + tc * 4);
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
         const float s = TRANS ? S[x * lds + rb + a] : S[rs[a] * lds + x];
-        acc[a].x = fmaf(s, m.x, acc[a].x); acc[a].y = fmaf(s, m.y, acc[a].y);
-        acc[a].z = fmaf(s, m.z, acc[a].z); acc[a].w = fmaf(s, m.w, acc[a].w);
+        unsigned long long ss;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+        ffma2(acc[a][0], ss, m.x);
+        ffma2(acc[a][1], ss, m.y);
       }
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
-      if (rb + a < len) out(rb + a, tc * 4, acc[a]);
+      if (rb + a < len)
+        out(rb + a, tc * 4, make_float4(__uint_as_float((uint32_t)acc[a][0]), __uint_as_float((uint32_t)(acc[a][0] >> 32)),
+                                        __uint_as_float((uint32_t)acc[a][1]), __uint_as_float((uint32_t)(acc[a][1] >> 32))));
   }
 }
 
