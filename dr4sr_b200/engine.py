@@ -60,6 +60,7 @@ class SASRecEngine:
         self.step = 0                       # dropout stream counter (bumped per training forward)
         self.fwd_token = 0                  # identifies whose activations the workspace holds
         self._bufs: Dict[int, _Buffers] = {}
+        self._cfgs: Dict[int, SasrecCfg] = {}
         self._fn_count, self._fn_ws = self.lib.dr4sr_sasrec_param_count, self.lib.dr4sr_sasrec_workspace_bytes
         self._fn_fwd, self._fn_bwd, self._name = self.lib.dr4sr_sasrec_fwd, self.lib.dr4sr_sasrec_bwd, 'dr4sr_sasrec'
         self._fn_bwd_async = self.lib.dr4sr_sasrec_bwd_async
@@ -75,8 +76,14 @@ class SASRecEngine:
 
     # ---- configuration ------------------------------------------------------------------------
     def cfg(self, B: int, step: Optional[int] = None) -> SasrecCfg:
-        return SasrecCfg(B=B, L=self.L, D=self.D, F=self.F, n_head=self.H, n_layer=self.n_layer, N=self.N,
-                         dropout_p=self.p, ln_eps=self.eps, seed=self.seed, step=self.step if step is None else step)
+        c = self._cfgs.get(B) if hasattr(self, '_cfgs') else None
+        if c is None:
+            c = SasrecCfg(B=B, L=self.L, D=self.D, F=self.F, n_head=self.H, n_layer=self.n_layer, N=self.N,
+                          dropout_p=self.p, ln_eps=self.eps, seed=self.seed, step=0)
+            if hasattr(self, '_cfgs'):
+                self._cfgs[B] = c
+        c.step = self.step if step is None else step      # the struct is read during the (synchronous) C call only
+        return c
 
     def buffers(self, B: int) -> _Buffers:
         b = self._bufs.get(B)

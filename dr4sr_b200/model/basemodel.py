@@ -240,7 +240,11 @@ class BaseModel(nn.Module):
                                   self._neg_step, tgt.device)
 
     def _publish_grads(self) -> None:
-        """Expose the kernel-written gradient buffers as .grad (what loss.backward() leaves behind)."""
+        """Expose the kernel-written gradient buffers as .grad (what loss.backward() leaves behind).  The buffers are
+        persistent, so after the first backward this is a two-pointer check."""
+        if self._flat_params[-1].grad is self._grad_views[-1] and self._flat_params[0].grad is self._grad_views[0] \
+                and self.item_embedding.weight.grad is self._table_grad:
+            return
         for p, g in zip(self._flat_params, self._grad_views):
             p.grad = g
         self.item_embedding.weight.grad = self._table_grad

@@ -89,7 +89,8 @@ class SASRec(BaseModel):
         in_ids, item_id, neg = batch['in_' + self.fiid], batch[self.fiid], batch['neg_item']
         neg = neg.view(item_id.shape)
         b = eng.prep(batch['seqlen'], item_id)
-        self._dp_sum(b.counts[1:2])           # data parallel: normalise by the global number of valid targets
+        if getattr(self, '_dp_group', None) is not None:
+            self._dp_sum(b.counts[1:2])       # data parallel: normalise by the global number of valid targets
         if self.training:
             eng.step += 1
         q_dense = None
@@ -102,7 +103,7 @@ class SASRec(BaseModel):
         fused_grad = bool(reduce and self.training)
         eng.score_bce(b, table, item_id, neg, want_grad=fused_grad)
         loss = eng.reduce_loss(b) if reduce else b.loss_pos.clone()
-        if reduce:
+        if reduce and getattr(self, '_dp_group', None) is not None:
             self._dp_sum(loss)
         return loss, q_dense, (b, table, in_ids, item_id, neg, fused_grad)
 
