@@ -698,6 +698,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
     TRACE(1);
     if (tid == 0) prefetch_chunk(c, a.layer[0].in_hi, a.layer[0].in_lo, 384, 0);
     __syncthreads();
+    TRACE(2);
     // ---- x0 = dropout(E[id] + P[t]) -> global (the backward needs it), park (residual) and the first A operand ----
     {
       RowDrop rd;
@@ -713,6 +714,8 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
           for (int q = 0; q < 8; ++q) ev[8 * j + q] = 0.f;
         }
       }
+      if (ev[0] == 12345.678f) TRACE(3);           // (forces the first load to land before the timestamp below)
+      TRACE(4);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int n0 = c.half * 64 + g * 16;
@@ -733,6 +736,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
         tmem_st16(c.trow + kPark + (uint32_t)(g * 16), v);
         store_image16(v, c.row, n0, c.smem);
       }
+      TRACE(5);
     }
 #pragma unroll 1
     for (int l = 0; l < a.n_layer; ++l) {
@@ -748,6 +752,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
                          : i < kParBe2 ? y.g2 + (i - kParG2) : y.be2 + (i - kParBe2);
         s_par[i] = *src;
       }
+      TRACE(6);
       // ---- QKV projection: A operand already staged (embedding stage or the previous layer's LN2 epilogue) ----
       sync_for_mma();
 #pragma unroll 1
