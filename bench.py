@@ -363,7 +363,7 @@ def main():
                 n *= d
             batch[k] = flat[off:off + n].view(shp)
             off += n
-        sink.append(float(step(batch)))           # .item(): device -> host read of the loss
+        sink.append(float(step(batch).detach()))  # .item(): device -> host read of the loss
 
     for i in range(3):
         e2e_step(i)

@@ -1,4 +1,5 @@
-// fused_fwd.cu -- the whole SASRec encoder forward as ONE persistent kernel (D = F = 128, 2 heads of 64).
+// fused_fwd.cu -- the whole SASRec encoder forward as ONE persistent kernel (D = F = 128, 2 heads of 64), and (further
+// down, opt-in schedule 2) the backward of a layer's position-wise half as one persistent kernel per layer.
 //
 // Replaces SASRecQueryEncoder.forward (reference model/sasrec.py:39-75): embedding gather + learned
 // positions + dropout, then n_layer post-norm TransformerEncoderLayers (model/sasrec.py:21-34).
