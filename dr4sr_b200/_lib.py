@@ -67,6 +67,7 @@ SIGNATURES = {
     'dr4sr_fmlp_fwd': (c_i32, [C.POINTER(FmlpCfg), c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p]),
     'dr4sr_fmlp_bwd': (c_i32, [C.POINTER(FmlpCfg), c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
     'dr4sr_score_bce': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p]),
+    'dr4sr_score_loss': (c_i32, [c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p]),
     'dr4sr_sum': (c_i32, [c_p, c_i64, c_p, c_p]),
     'dr4sr_table_grad_workspace_bytes': (c_sz, [c_i32, c_i32]),
     'dr4sr_table_grad': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_sz, c_p]),

@@ -10,6 +10,11 @@ namespace {
 //   t <  len : q = packed row; s+ = <q,E+>, s- = <q,E->  (skipped when item_id == 0)
 //   t >= len : the reference's 'origin' pooling has zeroed q, so a non-pad target there contributes
 //              (-logsig(0) + softplus(0)) / n and no gradient.
+//
+// KIND 0: sampled BCE (model/loss_func.py:9-35, the loss training_step uses);  KIND 1: BPR as model/loss_func.py:40-49
+// intends it, l = -logsig(s+ - s-) / n with one negative (unreachable through the reference's training_step, which
+// passes `reduce` to a two-argument forward -- the "fixed BPR" extension of SURVEY.md Appendix C.6).
+template <int KIND>
 __global__ void __launch_bounds__(256) score_bce_kernel(const float* __restrict__ q, const float* __restrict__ table,
                                                         const int64_t* __restrict__ item_id, const int64_t* __restrict__ neg_item,
                                                         const int32_t* __restrict__ tok_off, const int32_t* __restrict__ counts,
@@ -36,7 +41,7 @@ __global__ void __launch_bounds__(256) score_bce_kernel(const float* __restrict_
       continue;
     }
     if (!in_seq) {
-      if (lane == 0) loss_pos[slot] = (0.69314718055994531f + 0.69314718055994531f) * inv_n;
+      if (lane == 0) loss_pos[slot] = (KIND == 0 ? 2.f : 1.f) * 0.69314718055994531f * inv_n;
       continue;
     }
     const int64_t nid = neg_item[slot];
@@ -56,9 +61,17 @@ __global__ void __launch_bounds__(256) score_bce_kernel(const float* __restrict_
     sp = warp_sum(sp);
     sn = warp_sum(sn);
     const float w = (loss_weight ? loss_weight[slot] : 1.0f);
-    if (lane == 0) loss_pos[slot] = (-log_sigmoid_f(sp) + softplus_f(sn)) * inv_n;
-    const float dsp = -sigmoid_f(-sp) * inv_n * w * up;
-    const float dsn = sigmoid_f(sn) * inv_n * w * up;
+    float dsp, dsn;
+    if (KIND == 0) {
+      if (lane == 0) loss_pos[slot] = (-log_sigmoid_f(sp) + softplus_f(sn)) * inv_n;
+      dsp = -sigmoid_f(-sp) * inv_n * w * up;
+      dsn = sigmoid_f(sn) * inv_n * w * up;
+    } else {
+      const float x = sp - sn;
+      if (lane == 0) loss_pos[slot] = -log_sigmoid_f(x) * inv_n;
+      dsp = -sigmoid_f(-x) * inv_n * w * up;
+      dsn = -dsp;
+    }
     if (lane == 0) { dscore[2 * (size_t)row] = dsp; dscore[2 * (size_t)row + 1] = dsn; }
     if (dq) {
       k = 0;
@@ -221,20 +234,32 @@ extern "C" int dr4sr_scale_grads(const float* upstream, const int32_t* counts, i
   return DR4SR_OK;
 }
 
+extern "C" int dr4sr_score_loss(int32_t kind, const float* q_packed, const float* table, const int64_t* item_id,
+                                const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts,
+                                int32_t B, int32_t L, int32_t D, const float* loss_weight, const float* upstream, float* loss_pos,
+                                float* dscore, float* dq_packed, dr4sr_stream_t stream) {
+  (void)row_seq;
+  if (!q_packed || !table || !item_id || !neg_item || !tok_off || !counts || !loss_pos || !dscore) return DR4SR_EINVAL;
+  if (D % 4 || D > 256 || (kind != DR4SR_LOSS_BCE && kind != DR4SR_LOSS_BPR)) return DR4SR_EINVAL;
+  const int total = B * L;
+  const int blocks = ceil_div(total, 8) < 8 * kNumSMs ? ceil_div(total, 8) : 8 * kNumSMs;
+  ProfScope prof(kind == DR4SR_LOSS_BCE ? "score_bce" : "score_bpr", as_stream(stream));
+  if (kind == DR4SR_LOSS_BCE)
+    score_bce_kernel<0><<<blocks, 256, 0, as_stream(stream)>>>(q_packed, table, item_id, neg_item, tok_off, counts, B, L, D,
+                                                                loss_weight, upstream, loss_pos, dscore, dq_packed);
+  else
+    score_bce_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(q_packed, table, item_id, neg_item, tok_off, counts, B, L, D,
+                                                                loss_weight, upstream, loss_pos, dscore, dq_packed);
+  DR4SR_LAUNCH_CHECK("score_bce_kernel");
+  return DR4SR_OK;
+}
+
 extern "C" int dr4sr_score_bce(const float* q_packed, const float* table, const int64_t* item_id, const int64_t* neg_item,
                                const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
                                int32_t D, const float* loss_weight, const float* upstream, float* loss_pos, float* dscore,
                                float* dq_packed, dr4sr_stream_t stream) {
-  (void)row_seq;
-  if (!q_packed || !table || !item_id || !neg_item || !tok_off || !counts || !loss_pos || !dscore) return DR4SR_EINVAL;
-  if (D % 4 || D > 256) return DR4SR_EINVAL;
-  const int total = B * L;
-  const int blocks = ceil_div(total, 8) < 8 * kNumSMs ? ceil_div(total, 8) : 8 * kNumSMs;
-  ProfScope prof("score_bce", as_stream(stream));
-  score_bce_kernel<<<blocks, 256, 0, as_stream(stream)>>>(q_packed, table, item_id, neg_item, tok_off, counts, B, L, D,
-                                                           loss_weight, upstream, loss_pos, dscore, dq_packed);
-  DR4SR_LAUNCH_CHECK("score_bce_kernel");
-  return DR4SR_OK;
+  return dr4sr_score_loss(DR4SR_LOSS_BCE, q_packed, table, item_id, neg_item, tok_off, row_seq, counts, B, L, D, loss_weight,
+                          upstream, loss_pos, dscore, dq_packed, stream);
 }
 
 extern "C" int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t stream) {

@@ -45,10 +45,13 @@ class _Buffers:
     loss_pos: torch.Tensor
     loss: torch.Tensor
     q_last: torch.Tensor
+    fwd_train: bool = True          # whether the forward whose activations `ws` holds drew dropout masks
+    fwd_step: int = 0               # ... and with which dropout-stream step
 
 
 class SASRecEngine:
     """Kernels + workspaces of one SASRec encoder (reference model/sasrec.py:10-75)."""
+    loss_kind = 0                       # DR4SR_LOSS_BCE; BaseModel._init_model sets it from config['model']['loss_fn']
 
     def __init__(self, num_items: int, embed_dim: int, max_seq_len: int, hidden_size: int, head_num: int,
                  layer_num: int, dropout_rate: float, layer_norm_eps: float, seed: int, device: torch.device) -> None:
@@ -120,6 +123,8 @@ class SASRecEngine:
         in_ids = _req(in_ids, torch.int64, 'in_item_id')
         B = in_ids.size(0)
         cfg = self.cfg(B)
+        b.fwd_train, b.fwd_step = bool(train), self.step
+        self.fwd_token += 1                 # the workspace now holds THIS forward's activations (stale backwards are refused)
         check(self._fn_fwd(C.byref(cfg), _p(_req(table, torch.float32, 'table')),
                                         _p(_req(flat, torch.float32, 'params')), _p(in_ids), _p(b.tok_off), _p(b.row_seq),
                                         _p(b.counts), _p(b.ws), b.ws.numel(), 1 if train else 0, _p(b.q_packed),
@@ -133,9 +138,9 @@ class SASRecEngine:
         neg_item = _req(neg_item, torch.int64, 'neg_item')
         B = item_id.size(0)
         q = b.q_packed if q_packed is None else q_packed
-        check(self.lib.dr4sr_score_bce(_p(q), _p(table), _p(item_id), _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
+        check(self.lib.dr4sr_score_loss(self.loss_kind, _p(q), _p(table), _p(item_id), _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
                                        B, self.L, self.D, _p(loss_weight), _p(upstream), _p(b.loss_pos), _p(b.dscore),
-                                       _p(b.dq) if want_grad else None, _stream()), 'dr4sr_score_bce')
+                                       _p(b.dq) if want_grad else None, _stream()), 'dr4sr_score_loss')
         return b.loss_pos
 
     def reduce_loss(self, b: _Buffers) -> torch.Tensor:
@@ -155,7 +160,10 @@ class SASRecEngine:
         the caller must call join_bwd() before anything reads `grads_flat` (dx0 is already ordered)."""
         in_ids = _req(in_ids, torch.int64, 'in_item_id')
         B = in_ids.size(0)
-        cfg = self.cfg(B)
+        cfg = self.cfg(B, step=b.fwd_step)
+        if not b.fwd_train and cfg.dropout_p != 0.0:      # an eval-mode forward applied no masks: the backward must not either
+            cfg = type(cfg).from_buffer_copy(cfg)
+            cfg.dropout_p = 0.0
         dq = b.dq if dq is None else dq
         fn = self._fn_bwd_async if (defer_join and getattr(self, '_fn_bwd_async', None) is not None) else self._fn_bwd
         check(fn(C.byref(cfg), _p(table), _p(flat), _p(in_ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
@@ -218,10 +226,12 @@ class _FmlpBuffers:
     row_seqD: torch.Tensor
     countsD: torch.Tensor         # dense [B, L] problem
     q_packed: torch.Tensor = None  # alias of q_last (engine-generic name used by the data-parallel hooks)
+    fwd_train: bool = True         # whether the forward whose activations `ws` holds drew dropout masks
 
 
 class FMLPEngine:
     """Kernels + workspaces of the FMLP encoder (reference model/fmlp.py:8-39, module/layers.py:740-808)."""
+    loss_kind = 0
 
     def __init__(self, num_items: int, embed_dim: int, max_seq_len: int, layer_num: int, dropout_rate: float, seed: int,
                  device: torch.device, layer_norm_eps: float = 1e-12) -> None:
@@ -274,6 +284,8 @@ class FMLPEngine:
         if in_ids.size(1) != self.L:
             raise _lib.Dr4srError(f'FMLP expects sequences of length {self.L}, got {in_ids.size(1)}')
         B = in_ids.size(0)
+        b.fwd_train = bool(train)
+        self.fwd_token += 1
         check(self.lib.dr4sr_fmlp_fwd(C.byref(self.cfg(B)), _p(_req(table, torch.float32, 'table')), _p(flat), _p(in_ids), _p(b.ws),
                                       b.ws.numel(), 1 if train else 0, _p(b.q_last), _stream()), 'dr4sr_fmlp_fwd')
         return b.q_last
@@ -281,10 +293,10 @@ class FMLPEngine:
     def score_bce(self, b: _FmlpBuffers, table: torch.Tensor, item_id: torch.Tensor, neg_item: torch.Tensor, want_grad: bool,
                   loss_weight: Optional[torch.Tensor] = None, upstream: Optional[torch.Tensor] = None) -> torch.Tensor:
         B = item_id.numel()
-        check(self.lib.dr4sr_score_bce(_p(b.q_last), _p(table), _p(_req(item_id, torch.int64, 'item_id')),
+        check(self.lib.dr4sr_score_loss(self.loss_kind, _p(b.q_last), _p(table), _p(_req(item_id, torch.int64, 'item_id')),
                                        _p(_req(neg_item, torch.int64, 'neg_item')), _p(b.tok_off1), _p(b.row_seq1), _p(b.counts), B, 1,
                                        self.D, _p(loss_weight), _p(upstream), _p(b.loss_pos), _p(b.dscore),
-                                       _p(b.dq) if want_grad else None, _stream()), 'dr4sr_score_bce')
+                                       _p(b.dq) if want_grad else None, _stream()), 'dr4sr_score_loss')
         return b.loss_pos
 
     def reduce_loss(self, b: _FmlpBuffers) -> torch.Tensor:
@@ -294,7 +306,10 @@ class FMLPEngine:
 
     def encode_bwd(self, b: _FmlpBuffers, table: torch.Tensor, flat: torch.Tensor, in_ids: torch.Tensor, grads_flat: torch.Tensor) -> None:
         B = in_ids.size(0)
-        check(self.lib.dr4sr_fmlp_bwd(C.byref(self.cfg(B)), _p(table), _p(flat), _p(in_ids), _p(b.ws), b.ws.numel(), _p(b.dq),
+        cfg = self.cfg(B)
+        if not b.fwd_train:
+            cfg.dropout_p = 0.0                            # an eval-mode forward applied no masks
+        check(self.lib.dr4sr_fmlp_bwd(C.byref(cfg), _p(table), _p(flat), _p(in_ids), _p(b.ws), b.ws.numel(), _p(b.dq),
                                       _p(grads_flat), _p(b.dz0), _stream()), 'dr4sr_fmlp_bwd')
 
     def table_grad(self, b: _FmlpBuffers, in_ids: torch.Tensor, item_id: torch.Tensor, neg_item: torch.Tensor,

@@ -99,9 +99,12 @@ class BaseModel(nn.Module):
             from ..dist import shard_rows
             self._shard_rows = shard_rows(self.num_items, int(ts[1]))[int(ts[0])]
             lo, hi = self._shard_rows
-            self.item_embedding = nn.Embedding(hi - lo, self.embed_dim, padding_idx=0 if lo == 0 else None)
+            rows, pad = hi - lo, (0 if lo == 0 else None)
         else:
-            self.item_embedding = nn.Embedding(self.num_items, self.embed_dim, padding_idx=0)
+            rows, pad = self.num_items, 0
+        # config['train']['table_init_device'] (optional): allocate + initialise the table there directly (a 10M-row table
+        # costs ~10 s of host RNG otherwise); absent => on the host like the reference, then moved by _init_model
+        self.item_embedding = nn.Embedding(rows, self.embed_dim, padding_idx=pad, device=config['train'].get('table_init_device'))
         self.eval_domain = self.domain_name_list[0]
         self.engine = None
         self._dead_cache: Dict[str, torch.Tensor] = {}
@@ -136,6 +139,7 @@ class BaseModel(nn.Module):
         self._flatten()
         self.optimizer = self._get_optimizers()
         self.loss_fn = self._get_loss_func()
+        self.engine.loss_kind = {'bce': 0, 'bpr': 1}[self.loss_fn.kind]      # DR4SR_LOSS_* of include/dr4sr.h
 
     def _flatten(self) -> None:
         """Re-home the encoder parameters as views of one flat fp32 buffer (the C ABI's layout) and
@@ -157,7 +161,20 @@ class BaseModel(nn.Module):
             off += k
         self._flat_params = params
         self._table_grad = torch.zeros_like(self.item_embedding.weight.data)
+        old_table = getattr(self, '_table_group', None)
         self._table_group: Optional[FlatGroup] = None
+        opt = getattr(self, 'optimizer', None)
+        if isinstance(opt, FusedAdam):
+            # parameters were moved / re-created after _init_model: re-point the optimizer's flat groups at the new
+            # buffers and carry the Adam moments over, so the live parameters keep being the ones that are updated
+            for g in opt.flat_groups:
+                new_p, new_g = (self.item_embedding.weight.data, self._table_grad) if g is old_table else (self._flat, self._flat_grad)
+                if g.m.shape != new_p.shape:
+                    raise _engine._lib.Dr4srError(f'parameter buffer {g.name!r} changed shape after _init_model; rebuild the optimizer')
+                g.param, g.grad = new_p, new_g
+                g.m, g.v = g.m.to(new_p.device), g.v.to(new_p.device)
+                g.dirty = False
+            self._table_group = old_table
 
     def _check_flat(self) -> None:
         p0 = self._flat_params[0]
@@ -193,6 +210,19 @@ class BaseModel(nn.Module):
         gradients are summed over ranks, so N ranks x B sequences compute exactly the single-process step
         on the N*B global batch (up to fp32 summation order)."""
         self._dp_group = group
+        self._sync_replicas(group, table=True)
+
+    def _sync_replicas(self, group, table: bool) -> None:
+        """Every rank starts from rank 0's replicated parameters (the callers need not seed the ranks identically)."""
+        import torch.distributed as dist
+        self._check_flat()
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(self._flat, src=src, group=group)
+        if table:
+            dist.broadcast(self.item_embedding.weight.data, src=src, group=group)
+        extra = [p.data for p in self.parameters() if p is not self.item_embedding.weight and all(p is not q for q in self._flat_params)]
+        for t in extra:                                   # parameters outside the flat encoder buffer (none for the shipped models)
+            dist.broadcast(t, src=src, group=group)
 
     def enable_sharded_table(self, group) -> None:
         """Row-sharded item table (config['train']['table_shard'] must have sized the embedding as the shard):
@@ -204,6 +234,7 @@ class BaseModel(nn.Module):
         self._dp_group = group
         self._shard = ShardedTable(self.num_items, self.embed_dim, group, self.item_embedding.weight.device)
         assert (self._shard.lo, self._shard.hi) == tuple(self._shard_rows)
+        self._sync_replicas(group, table=False)           # the encoder is replicated; each rank keeps its own table rows
 
     def _rows_for(self, bufs, in_ids, item_id, neg):
         """(table, in_ids, item_id, neg) the kernels run on: the parameter itself, or the staged local rows."""
@@ -361,6 +392,7 @@ class BaseModel(nn.Module):
                 best, bad = score, 0
                 self._best_state = {k: v.detach().clone() for k, v in self.state_dict().items()}
                 self._best_epoch = epoch
+                self._best_metrics = dict(self.logged_metrics)      # the reference stores the best epoch's metrics (callbacks.py:70-76)
             else:
                 bad += 1
                 if bad >= t['early_stop_patience']:
@@ -374,7 +406,7 @@ class BaseModel(nn.Module):
         path = path or os.path.join(root, time.strftime('%Y-%m-%d-%H-%M-%S') + '.ckpt')
         state = self._best_state if getattr(self, '_best_state', None) is not None else self.state_dict()
         torch.save({'config': self.config, 'model': type(self).__name__, 'epoch': getattr(self, '_best_epoch', 0),
-                    'parameters': state, 'metric': dict(getattr(self, 'logged_metrics', {}))}, path)
+                    'parameters': state, 'metric': dict(getattr(self, '_best_metrics', None) or getattr(self, 'logged_metrics', {}))}, path)
         self.ckpt_path = path
         return path
 

@@ -65,6 +65,10 @@ class FMLP(BaseModel):
 
     def _build_engine(self) -> None:
         m = self.config['model']
+        if self._shard_rows is not None:
+            # the FMLP kernels index the table with global ids; a row-sharded table would be read out of bounds
+            raise _engine._lib.Dr4srError("FMLP does not support config['train']['table_shard'] (row-sharded item table); "
+                                          'use the replicated data-parallel layout')
         self.engine = _engine.FMLPEngine(self.num_items, self.embed_dim, self.max_seq_len, m['layer_num'], m.get('dropout_rate', 0.5),
                                          self.config['train'].get('seed', 0), self.item_embedding.weight.device)
 
@@ -77,6 +81,9 @@ class FMLP(BaseModel):
         return out
 
     @torch.no_grad()
+    def enable_sharded_table(self, group) -> None:
+        raise _engine._lib.Dr4srError('FMLP does not support the row-sharded item table; use enable_data_parallel')
+
     def forward(self, batch, need_pooling=True):
         """Last position of the last layer, [B, D], in train and eval alike (model/fmlp.py:37-39)."""
         self._check_flat()
@@ -130,9 +137,6 @@ class FMLP(BaseModel):
             y = f.LayerNorm(f.out_dropout(torch.fft.irfft(spec, n=L, dim=1, norm='ortho')) + x)
             x = i.LayerNorm(i.dropout(i.dense_2(F.gelu(i.dense_1(y)))) + y)
         return x[:, -1]
-
-    def current_epoch_trainloaders(self, nepoch):
-        return super().current_epoch_trainloaders(nepoch)
 
     def training_step(self, batch, reduce=True, return_query=False, align=False):
         return super().training_step(batch, reduce, return_query)

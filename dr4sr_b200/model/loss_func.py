@@ -18,8 +18,12 @@ class BinaryCrossEntropyLoss(nn.Module):
 
 
 class BPRLoss(nn.Module):
+    """`config['model']['loss_fn'] = 'bpr'`: -logsig(s+ - s-) averaged over the non-pad targets, one negative
+    (model/loss_func.py:40-49).  The reference cannot reach it -- training_step passes `reduce` to this two-argument
+    forward (TypeError at model/basemodel.py:210) -- so this is the intended loss, fixed: `dr4sr_score_loss` with
+    DR4SR_LOSS_BPR computes it, and its gradients, in the same fused sweep as the BCE."""
     kind = 'bpr'
 
-    def forward(self, pos_score, neg_score):
-        raise RuntimeError('BPR is unreachable through training_step in the reference (TypeError at '
-                           'model/basemodel.py:210); not built in this round.')
+    def forward(self, pos_score, neg_score, reduce=True):
+        raise RuntimeError('dr4sr_b200 computes the sampled BPR loss inside the fused scoring kernel; '
+                           'call model.training_step(batch) (there is no PyTorch fallback).')

@@ -183,19 +183,24 @@ class MetaModel(BaseModel):
         weight = weight.masked_fill(mask, 1).masked_fill(pad, 0)
         return (per * weight).sum()
 
-    def _outter_loop(self, nepoch):
+    def _outer_step(self, val_batch, train_batch, return_grads=False):
+        """One hypergradient update of the meta module from a validation batch and a training batch (both with
+        `neg_item`): the else-branch of the reference's _outter_loop (metamodel.py:149-166)."""
         from torch.nn.attention import SDPBackend, sdpa_kernel
+        with sdpa_kernel(SDPBackend.MATH), torch.backends.cudnn.flags(enabled=False):
+            meta_loss = self._composite_losses(val_batch, weighted=False)
+            meta_train_loss = self._composite_losses(train_batch, weighted=True)
+            return self.meta_optimizer.step(val_loss=meta_loss, train_loss=meta_train_loss,
+                                            aux_params=list(self.meta_module.parameters()),
+                                            parameters=list(self.sub_model.parameters()), return_grads=return_grads)
+
+    def _outter_loop(self, nepoch):
         def one_batch(loader):
             batch = next(iter(loader))
             batch = {k: v.to(self.device) for k, v in batch.items()}
             batch['neg_item'] = self.sub_model._neg_sampling(batch)
             return batch
-        with sdpa_kernel(SDPBackend.MATH), torch.backends.cudnn.flags(enabled=False):
-            meta_loss = self._composite_losses(one_batch(self.current_epoch_metaloaders(nepoch)), weighted=False)
-            meta_train_loss = self._composite_losses(one_batch(self.current_epoch_trainloaders(nepoch)), weighted=True)
-            self.meta_optimizer.step(val_loss=meta_loss, train_loss=meta_train_loss,
-                                     aux_params=list(self.meta_module.parameters()),
-                                     parameters=list(self.sub_model.parameters()), return_grads=False)
+        self._outer_step(one_batch(self.current_epoch_metaloaders(nepoch)), one_batch(self.current_epoch_trainloaders(nepoch)))
 
     # ---- delegate the rest to the sub-model ------------------------------------------------------------
     def topk(self, batch, k, user_h=None):

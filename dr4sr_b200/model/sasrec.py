@@ -66,9 +66,6 @@ class SASRec(BaseModel):
     def _flat_parameters(self):
         return self.query_encoder.flat_parameters()
 
-    def current_epoch_trainloaders(self, nepoch):
-        return super().current_epoch_trainloaders(nepoch)
-
     @torch.no_grad()
     def forward(self, batch, need_pooling=True):
         """Eval: row seqlen-1 ('last' pooling) [B, D]; train: zero-padded rows ('origin') [B, L, D]."""

@@ -222,6 +222,15 @@ DR4SR_API int dr4sr_score_bce(const float* q_packed, const float* table, const i
                     const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
                     int32_t D, const float* loss_weight, const float* upstream, float* loss_pos, float* dscore,
                     float* dq_packed, dr4sr_stream_t stream);
+/* The same sweep with the loss selected by `kind`: DR4SR_LOSS_BCE = dr4sr_score_bce; DR4SR_LOSS_BPR = the BPR loss as
+ * model/loss_func.py:40-49 intends it with one negative, loss_pos[b,t] = -logsig(s+ - s-) / n, ds+ = -sigmoid(s- - s+) w/n,
+ * ds- = -ds+ (the reference's training_step cannot reach it: it passes `reduce` to BPRLoss.forward, a TypeError at
+ * model/basemodel.py:210 -- this is the "fixed BPR" extension, selected by config['model']['loss_fn'] = 'bpr'). */
+enum { DR4SR_LOSS_BCE = 0, DR4SR_LOSS_BPR = 1 };
+DR4SR_API int dr4sr_score_loss(int32_t kind, const float* q_packed, const float* table, const int64_t* item_id,
+                     const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B,
+                     int32_t L, int32_t D, const float* loss_weight, const float* upstream, float* loss_pos, float* dscore,
+                     float* dq_packed, dr4sr_stream_t stream);
 /* dq_packed and dscore of a dr4sr_score_bce call made with upstream = NULL, multiplied afterwards by the device scalar
  * `upstream` (autograd's grad_output arrives only at backward time): lets the forward pass compute the gradients in
  * the same sweep as the loss; the kernel exits at once when *upstream == 1. */

@@ -161,39 +161,63 @@ def run_case(name: str, oracle_cls, okw: dict, N: int, D: int, B: int, layout: s
           f'({sum(v.nbytes for v in fx.values()) / 1e6:.2f} MB raw)')
 
 
-def toys_checkpoint_case(n_users_topk: int = 256):
-    """Known answer: shipped SASRec checkpoint on amazon-toys val."""
-    cfg = load_config({'model': 'SASRec', 'dataset': 'amazon-toys'})
+def bpr_case(out: str = 'bpr_loss.npz'):
+    """BPRLoss.forward of the reference (model/loss_func.py:40-49) on random scores with -inf at pad targets."""
+    from model.loss_func import BPRLoss
+    torch.manual_seed(5)
+    pos = torch.randn(7, 50) * 3
+    pos[:, 31:] = -float('inf')
+    pos[2, 5:] = -float('inf')
+    neg = torch.randn(7, 50, 1) * 3
+    want = BPRLoss()(pos.clone(), neg.clone())
+    got = orc.bpr_loss(pos, neg)
+    assert torch.equal(want, got), (float(want), float(got))
+    np.savez_compressed(os.path.join(HERE, out), pos=pos.numpy(), neg=neg.numpy(), loss=want.numpy())
+    print(out, 'loss', float(want))
+
+
+CKPTS = {   # fixture -> (dataset config name, domain / directory name)      SURVEY.md section 4: the four shipped known answers
+    'toys_ckpt.npz': ('amazon-toys', 'toy'),
+    'beauty_ckpt.npz': ('amazon-beauty', 'beauty'),
+    'sport_ckpt.npz': ('amazon-sport', 'sport'),
+    'yelp_ckpt.npz': ('yelp', 'yelp'),
+}
+
+
+def checkpoint_case(out: str, dataset: str, domain: str, n_users_topk: int = 256):
+    """Known answer: the shipped SASRec checkpoint of `dataset` on its val split."""
+    cfg = load_config({'model': 'SASRec', 'dataset': dataset})
     cfg['train']['device'] = 'cpu'
     seed_everything(cfg['train']['seed'])
     ds = ref_utils.prepare_datasets(cfg)
     m = ref_utils.prepare_model(cfg, ds)
     m._init_model(ds[0])
-    ck = torch.load('dataset/amazon-toys/toy/pre-trained_embedding.ckpt', weights_only=False, map_location='cpu')
+    ck = torch.load(f'dataset/{dataset}/{domain}/pre-trained_embedding.ckpt', weights_only=False, map_location='cpu')
     m.load_state_dict(ck['parameters'])
     m.eval()
-    m.set_eval_domain('toy'); ds[1].set_eval_domain('toy')
+    m.set_eval_domain(domain); ds[1].set_eval_domain(domain)
     o = orc.OracleSASRec(ds[0].num_items, embed_dim=64)
     o.load_state_dict(ck['parameters'])
     o.eval()
-    uid, hist, tgt, slen, label, dom, _ = ds[1].data['toy']
+    uid, hist, tgt, slen, label, dom, _ = ds[1].data[domain]
     batch = {'user_id': uid, 'in_item_id': hist, 'item_id': tgt, 'seqlen': slen, 'user_hist': hist}
     ndcg, rec, ids_all = [], [], []
     with torch.no_grad():
         for s in range(0, len(uid), 2048):
             b = {k: v[s:s + 2048] for k, v in batch.items()}
             sc_r, id_r = m.topk(b, 100, b['user_hist'])
-            sc_o, id_o = o.topk(b, 100, m.domain_item_mapping['toy'])
+            sc_o, id_o = o.topk(b, 100, m.domain_item_mapping[domain])
             assert torch.equal(id_r, id_o)
             hit = orc.hit_matrix(id_r, b['item_id'])
             ndcg.append(orc.ndcg_at_k(hit, 20)); rec.append(orc.recall_at_k(hit, 20))
             ids_all.append(id_r)
     ndcg, rec, ids_all = torch.cat(ndcg), torch.cat(rec), torch.cat(ids_all)
     stored = ck['metric']
-    print('toys ckpt: ndcg@20', float(ndcg.mean()), 'recall@20', float(rec.mean()), 'stored', stored)
+    print(f'{dataset} ckpt: ndcg@20', float(ndcg.mean()), 'recall@20', float(rec.mean()), 'stored', stored)
     assert abs(float(ndcg.mean()) - float(stored['ndcg@20'])) < 5e-7
     assert abs(float(rec.mean()) - float(stored['recall@20'])) < 5e-7
-    dom_items = np.asarray(sorted(m.domain_item_mapping['toy']), dtype=np.int32)
+    assert ds[0].num_items < 32767
+    dom_items = np.asarray(sorted(m.domain_item_mapping[domain]), dtype=np.int32)
     fx = {f'param/{k}': v.numpy() for k, v in ck['parameters'].items() if k not in ALIASES}
     fx.update({
         'val/in_item_id': hist.numpy().astype(np.int16), 'val/item_id': tgt.numpy().astype(np.int16),
@@ -203,8 +227,103 @@ def toys_checkpoint_case(n_users_topk: int = 256):
         'top20_all_users': ids_all[:, :20].numpy().astype(np.int16),
         'num_items': np.int64(ds[0].num_items),
     })
-    np.savez_compressed(os.path.join(HERE, 'toys_ckpt.npz'), **fx)
-    print('toys_ckpt.npz written', os.path.getsize(os.path.join(HERE, 'toys_ckpt.npz')) / 1e6, 'MB')
+    np.savez_compressed(os.path.join(HERE, out), **fx)
+    print(out, 'written', os.path.getsize(os.path.join(HERE, out)) / 1e6, 'MB')
+
+
+def metamodel_case(out: str, N: int, D: int, B: int, seed: int):
+    """MetaModel (DR4SR+, sub_model = SASRec): the weighted inner step (model/metamodel.py:169-194) and one outer
+    hypergradient step (metamodel.py:123-166 else-branch, utils/utils.py:145-255) of the UNMODIFIED reference, dropout 0.
+    The only randomness left is F.gumbel_softmax's noise: it is drawn from a known seed right before the call, and the
+    same noise tensor (regenerated here with the same formula, asserted to reproduce the reference's loss) is stored so
+    that the CUDA path can inject it."""
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+    import model.metamodel as ref_meta
+    L = 50
+    fake = FakeDataset(N)
+
+    class CpuMetaModel(ref_meta.MetaModel):
+        # configuration only (SURVEY.md section 8c): the reference hard-codes the sub-model to GPU 0 and opens a DataLoader
+        def _register_sub_model(self):
+            sc = load_config({'dataset': self.config['data']['dataset'], 'model': self.config['model']['sub_model']})
+            sc['train']['device'] = 'cpu'
+            sc['model']['embed_dim'] = D
+            sc['model']['dropout_rate'] = 0.0
+            return ref_utils.get_model_class(sc['model'])(sc, self.dataset_list)
+
+        def current_epoch_metaloaders(self, nepoch):
+            return [None]
+
+    cfg = load_config({'model': 'MetaModel', 'dataset': 'amazon-toys'})
+    cfg['train']['device'] = 'cpu'
+    cfg['model']['sub_model'] = 'SASRec'
+    cfg['model']['embed_dim'] = D
+    cfg['model']['dropout_rate'] = 0.0
+    seed_everything(seed)
+    ref = CpuMetaModel(cfg, [fake] * 3)
+    ref._init_model(None)
+    ref.train()
+    # make the meta module non-trivial: the reference initialises it N(0, 0.02), which makes every weight ~0.5
+    with torch.no_grad():
+        for p in ref.meta_module.parameters():
+            p.add_(torch.randn_like(p) * 0.3)
+    fx = {}
+    fx.update(pack('param', ref.sub_model.state_dict()))
+    fx.update(pack('meta', ref.meta_module.state_dict()))
+    fx['meta_cfg/tau'] = ref.tau.detach().numpy().copy()
+    fx['meta_cfg/tau_min'] = np.float64(cfg['model']['tau_min'])
+    for k in ('meta_optimizer', 'meta_learning_rate', 'hpo_learning_rate', 'meta_weight_decay'):
+        fx[f'meta_cfg/{k}'] = np.asarray(cfg['train'][k])
+
+    def gumbel_like(shape, s):
+        torch.manual_seed(s)
+        return -torch.empty(shape, dtype=torch.float32).exponential_().log()    # F.gumbel_softmax's first statement
+
+    tr = synthetic_batch(B, L, N, seed=seed)
+    tr['user_id'][::3] = 0            # mined patterns keep weight 1 (metamodel.py:180-183)
+    va = synthetic_batch(B, L, N, seed=seed + 1)
+    fx.update(pack('batch', tr)); fx.update(pack('valbatch', va))
+    g_in = gumbel_like((B, L, 2), 1234)
+    fx['inner/gumbel'] = g_in.numpy()
+
+    # ---- inner weighted step ----
+    with sdpa_kernel(SDPBackend.MATH):
+        ref.sub_model.optimizer.zero_grad()
+        torch.manual_seed(1234)
+        loss = ref.training_step(batch={k: v.clone() for k, v in tr.items()}, align=False)
+        # oracle restatement with the injected noise must agree
+        o = orc.OracleSASRec(N, embed_dim=D, dropout_rate=0.0).train()
+        o.load_state_dict(ref.sub_model.state_dict())
+        per_o, q_o = o.training_step(tr, reduce=False, return_query=True)
+        mm = ref.meta_module
+        want = orc.meta_weighted_loss(per_o, q_o, mm[0].weight, mm[0].bias, mm[2].weight, mm[2].bias, ref.tau,
+                                      cfg['model']['tau_min'], g_in, tr['user_id'], tr['item_id'])
+        assert torch.allclose(loss, want, rtol=1e-6, atol=0), (float(loss), float(want))
+        loss.backward()
+    fx['inner/loss'] = loss.detach().numpy()
+    fx.update(pack('inner_grad', {k: (p.grad if p.grad is not None else torch.zeros_like(p))
+                                  for k, p in ref.sub_model.named_parameters()}))
+    fx.update(pack('inner_meta_grad', {k: (p.grad if p.grad is not None else torch.zeros_like(p))
+                                       for k, p in ref.meta_module.named_parameters()}))
+
+    # ---- one outer step: the else-branch of _outter_loop on (va, tr) with known Gumbel noise ----
+    g_out = gumbel_like((B, L, 2), 4321)
+    fx['outer/gumbel'] = g_out.numpy()
+    with sdpa_kernel(SDPBackend.MATH):
+        meta_loss = ref.sub_model.training_step(batch={k: v.clone() for k, v in va.items()}, align=False)
+        torch.manual_seed(4321)
+        meta_train_loss = ref.training_step(batch={k: v.clone() for k, v in tr.items()}, align=False)
+        grads = ref.meta_optimizer.step(val_loss=meta_loss, train_loss=meta_train_loss,
+                                        aux_params=list(ref.meta_module.parameters()),
+                                        parameters=list(ref.sub_model.parameters()), return_grads=True)
+    fx['outer/val_loss'] = meta_loss.detach().numpy()
+    fx['outer/train_loss'] = meta_train_loss.detach().numpy()
+    for (k, _), g in zip(ref.meta_module.named_parameters(), grads):
+        fx[f'outer_hypergrad/{k}'] = g.detach().numpy().copy()       # after clip_grad_norm_ (in place on the same tensors)
+    fx.update(pack('meta_after', ref.meta_module.state_dict()))
+    np.savez_compressed(os.path.join(HERE, out), **fx)
+    print(f'{out}: inner loss {float(loss):.6f}, |hypergrad| '
+          f'{float(torch.cat([g.reshape(-1) for g in grads]).norm()):.3e} ({sum(v.nbytes for v in fx.values()) / 1e6:.2f} MB raw)')
 
 
 if __name__ == '__main__':
@@ -218,4 +337,8 @@ if __name__ == '__main__':
              out='gru4rec_d128.npz')
     run_case('FMLP', orc.OracleFMLP, dict(dropout_rate=0.0), N=300, D=64, B=6, layout='pre', seed=15,
              out='fmlp_d64.npz')
-    toys_checkpoint_case()
+    bpr_case()
+    for _out, (_ds, _dom) in CKPTS.items():
+        checkpoint_case(_out, _ds, _dom)
+    metamodel_case('metamodel_sasrec_d64.npz', N=300, D=64, B=6, seed=21)
+    metamodel_case('metamodel_sasrec_d128.npz', N=1000, D=128, B=16, seed=22)

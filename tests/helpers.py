@@ -19,7 +19,8 @@ def load_fixture(name: str) -> Dict[str, Dict[str, torch.Tensor]]:
     with np.load(os.path.join(GOLDEN, name)) as z:
         for key in z.files:
             group, _, leaf = key.partition('/')
-            out.setdefault(group, {})[leaf] = torch.from_numpy(np.array(z[key]))
+            a = np.array(z[key])
+            out.setdefault(group, {})[leaf] = str(a) if a.dtype.kind in 'US' else torch.from_numpy(a)
     return out
 
 
@@ -51,3 +52,13 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max |a-b| / max |b| -- the scale-relative error used for fp32 parity."""
     a, b = a.double(), b.double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---- measured parity errors: every fp comparison records (label, error, tolerance); tests/conftest.py prints the worst
+# error per label in the terminal summary and writes gpurun_out/parity_errors.json, so the margins are known ----------
+ERRLOG = []
+
+
+def check_err(label: str, err: float, tol: float) -> None:
+    ERRLOG.append((label, float(err), float(tol)))
+    assert err < tol, f'{label}: error {err:.3e} >= tolerance {tol:.1e}'

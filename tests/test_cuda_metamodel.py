@@ -1,11 +1,12 @@
 """GPU tests of MetaModel (DR4SR+): the weighted inner step (per-slot loss weights + gradient on the query fed
-back into the kernels) against the CPU oracle with the same injected Gumbel noise, and the outer
-hypergradient step (composite, twice-differentiable) runs and moves only the meta parameters."""
+back into the kernels) and the outer hypergradient step (composite, twice-differentiable), both against goldens dumped
+from the UNMODIFIED reference MetaModel with known Gumbel noise (tests/golden/make_golden.py::metamodel_case), plus the
+CPU oracle with injected noise for the FMLP sub-model."""
 import pytest
 import torch
 
 from oracle import dr4sr_oracle as orc
-from tests.helpers import rel_err
+from tests.helpers import load_fixture, load_params, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
@@ -77,3 +78,70 @@ def test_meta_outer_step_runs_and_moves_only_meta_parameters():
     moved = sum(float((a - b.detach()).abs().sum()) for a, b in zip(before_meta, m.meta_module.parameters()))
     assert moved > 0.0
     assert torch.equal(before_sub, m.sub_model._flat)
+
+
+def _meta_from_fixture(fx):
+    N, D = fx['param']['item_embedding.weight'].shape
+    m = make_meta('SASRec', N, D)
+    m.config['train'].update(meta_optimizer=fx['meta_cfg']['meta_optimizer'], meta_learning_rate=float(fx['meta_cfg']['meta_learning_rate']),
+                             hpo_learning_rate=float(fx['meta_cfg']['hpo_learning_rate']),
+                             meta_weight_decay=float(fx['meta_cfg']['meta_weight_decay']))
+    m.config['model']['tau_min'] = float(fx['meta_cfg']['tau_min'])
+    load_params(m.sub_model, {k: v.to(DEV) for k, v in fx['param'].items()})
+    m.meta_module.load_state_dict({k: v.to(DEV) for k, v in fx['meta'].items()})
+    m.tau.data.copy_(fx['meta_cfg']['tau'].to(DEV))
+    m.meta_optimizer = m._get_meta_optimizers()
+    return m.train()
+
+
+@pytest.mark.parametrize('name,backend', [('metamodel_sasrec_d64.npz', 'default'), ('metamodel_sasrec_d128.npz', 'default'),
+                                          ('metamodel_sasrec_d128.npz', 'ffma')])
+def test_meta_inner_step_matches_reference_golden(name, backend):
+    """MetaModel.training_step + backward on the kernels vs the reference's loss / sub-model gradients / meta-module
+    gradients (model/metamodel.py:169-194) under the same Gumbel noise."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dr4sr_b200 import _lib
+    _lib.lib().dr4sr_set_gemm_backend(1 if backend == 'ffma' else 0)
+    try:
+        fx = load_fixture(name)
+        m = _meta_from_fixture(fx)
+        m._gumbel_override = fx['inner']['gumbel'].to(DEV)
+        m.sub_model.optimizer.zero_grad()
+        m.meta_module.zero_grad()
+        loss = m.training_step({k: v.to(DEV) for k, v in fx['batch'].items()})
+        loss.backward()
+        lerr = abs(float(loss.detach()) - float(fx['inner']['loss'])) / abs(float(fx['inner']['loss']))
+        worst = ('', 0.0)
+        for k, p in m.sub_model.named_parameters():
+            if k in fx['inner_grad']:
+                e = rel_err(p.grad.cpu(), fx['inner_grad'][k])
+                worst = max(worst, (k, e), key=lambda t: t[1])
+        mworst = max(rel_err(p.grad.cpu(), fx['inner_meta_grad'][k]) for k, p in m.meta_module.named_parameters())
+        print(f'[{name} {backend}] inner loss rel err {lerr:.2e}; worst sub-model grad {worst[0]} {worst[1]:.2e}; meta grad {mworst:.2e}')
+        tol = 2e-5 if backend == 'ffma' or fx['param']['item_embedding.weight'].shape[1] == 64 else 3e-4
+        assert lerr < 1e-5
+        assert worst[1] < tol, worst
+        assert mworst < tol
+    finally:
+        _lib.lib().dr4sr_set_gemm_backend(0)
+
+
+@pytest.mark.parametrize('name', ['metamodel_sasrec_d64.npz', 'metamodel_sasrec_d128.npz'])
+def test_meta_outer_step_matches_reference_golden(name):
+    """One outer step (implicit hypergradient, 3 Neumann terms, clip, meta SGD) vs the reference's
+    MetaOptimizer.step on the same (val, train) batches and noise (metamodel.py:149-166, utils/utils.py:145-255)."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    fx = load_fixture(name)
+    m = _meta_from_fixture(fx)
+    m._gumbel_override = fx['outer']['gumbel'].to(DEV)
+    sub_before = m.sub_model._flat.clone()
+    grads = m._outer_step({k: v.to(DEV) for k, v in fx['valbatch'].items()}, {k: v.to(DEV) for k, v in fx['batch'].items()},
+                          return_grads=True)
+    errs = {k: rel_err(g.cpu(), fx['outer_hypergrad'][k]) for (k, _), g in zip(m.meta_module.named_parameters(), grads)}
+    perr = {k: rel_err(v.cpu(), fx['meta_after'][k]) for k, v in m.meta_module.state_dict().items()}
+    print(f'[{name}] hypergradient rel err {errs}; meta params after the step {perr}')
+    assert max(errs.values()) < 1e-3, errs
+    assert max(perr.values()) < 1e-5, perr
+    assert torch.equal(sub_before, m.sub_model._flat)         # the outer step never touches the sub-model

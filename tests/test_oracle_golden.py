@@ -111,9 +111,10 @@ def test_bce_closed_form():
     assert abs(float(orc.bce_loss(pos, neg, reduce=False).sum()) - float(want)) < 1e-6
 
 
-def test_toys_checkpoint_known_answer():
-    """Shipped SASRec checkpoint reproduces its stored val ndcg@20 / recall@20."""
-    fx = load_fixture('toys_ckpt.npz')
+@pytest.mark.parametrize('ckpt', ['toys_ckpt.npz', 'beauty_ckpt.npz', 'sport_ckpt.npz', 'yelp_ckpt.npz'])
+def test_shipped_checkpoint_known_answer(ckpt):
+    """Each shipped SASRec checkpoint reproduces its stored val ndcg@20 / recall@20."""
+    fx = load_fixture(ckpt)
     N = int(fx['num_items'][''])
     m = load_params(orc.OracleSASRec(N, embed_dim=64), fx['param']).eval()
     hist = fx['val']['in_item_id'].long()
@@ -128,3 +129,32 @@ def test_toys_checkpoint_known_answer():
         nd.append(orc.ndcg_at_k(hit, 20)); rc.append(orc.recall_at_k(hit, 20))
     assert abs(float(torch.cat(nd).mean()) - float(fx['metric']['ndcg@20'])) < 5e-7
     assert abs(float(torch.cat(rc).mean()) - float(fx['metric']['recall@20'])) < 5e-7
+
+
+@pytest.mark.parametrize('name', ['metamodel_sasrec_d64.npz', 'metamodel_sasrec_d128.npz'])
+def test_metamodel_inner_step_oracle_matches_reference_golden(name):
+    """orc.meta_weighted_loss (+ the oracle SASRec under it) against the loss and sub-model gradients the UNMODIFIED
+    reference MetaModel.training_step produced with the same Gumbel noise (model/metamodel.py:169-194)."""
+    fx = load_fixture(name)
+    o = oracle_from_fixture('sasrec', fx).train()
+    batch = fx['batch']
+    mm = {k: v.clone().requires_grad_(True) for k, v in fx['meta'].items()}
+    per, q = o.training_step(batch, reduce=False, return_query=True)
+    loss = orc.meta_weighted_loss(per, q, mm['0.weight'], mm['0.bias'], mm['2.weight'], mm['2.bias'], fx['meta_cfg']['tau'],
+                                  float(fx['meta_cfg']['tau_min']), fx['inner']['gumbel'], batch['user_id'], batch['item_id'])
+    loss.backward()
+    assert abs(float(loss.detach()) - float(fx['inner']['loss'])) <= 1e-6 * abs(float(fx['inner']['loss']))
+    for k, p in o.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert rel_err(g, fx['inner_grad'][k]) < 1e-5, k
+    for k, p in mm.items():
+        assert rel_err(p.grad, fx['inner_meta_grad'][k]) < 1e-5, k
+
+
+def test_bpr_loss_matches_reference_golden():
+    """orc.bpr_loss vs the reference's BPRLoss.forward (model/loss_func.py:40-49) on stored random scores."""
+    import numpy as np, os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, 'bpr_loss.npz'))
+    got = orc.bpr_loss(torch.from_numpy(z['pos']), torch.from_numpy(z['neg']))
+    assert float(got) == float(z['loss'])
