@@ -40,7 +40,7 @@ def test_shipped_checkpoint_known_answer_on_cuda(name):
     want20 = fx['top20_all_users'][''].long()
     want100 = fx['top100_first_users'][''].long()
     nd = rc = 0.0
-    bad_rows = 0
+    bad_rows, worst_gap, smax = 0, 0.0, 0.0
     disc = torch.log2(torch.arange(20, dtype=torch.float64) + 2.0)
     for s in range(0, hist.size(0), 2048):                     # eval batch_size of the reference (configs/basemodel.yaml)
         e = min(s + 2048, hist.size(0))
@@ -49,7 +49,17 @@ def test_shipped_checkpoint_known_answer_on_cuda(name):
         ids = ids.cpu()
         assert ids.dtype == torch.int64 and scores.dtype == torch.float32
         assert bool((scores[:, :-1] >= scores[:, 1:]).all()), 'scores not sorted descending'
-        bad_rows += int((ids[:, :20] != want20[s:e]).any(dim=1).sum())
+        # ids must equal the reference's, except where fp32 summation order decides between scores that are equal to within
+        # round-off (fp32 vs fp64 already differs in 23 of these 19 412 rows at top-100): a differing
+        # position must hold an id whose score here is within a few ulp-of-the-dot-product of the reference id's score here
+        sc = scores.cpu()
+        smax = max(smax, float(sc[:, 0].abs().max()))
+        for r in (ids[:, :20] != want20[s:e]).any(dim=1).nonzero().flatten().tolist():
+            bad_rows += 1
+            for j in (ids[r, :20] != want20[s + r]).nonzero().flatten().tolist():
+                pos = (ids[r] == want20[s + r, j]).nonzero().flatten()
+                assert pos.numel() == 1, f'user {s + r}: reference id {int(want20[s + r, j])} (rank {j}) is not in our top-100'
+                worst_gap = max(worst_gap, abs(float(sc[r, j]) - float(sc[r, int(pos)])))
         if s == 0:
             n100 = min(want100.size(0), e)
             bad100 = int((ids[:n100] != want100[:n100]).any(dim=1).sum())
@@ -61,7 +71,9 @@ def test_shipped_checkpoint_known_answer_on_cuda(name):
     print(f'{name}: {n} users, top-20 id rows differing from the reference: {bad_rows}, top-100 rows differing (first {n100}): {bad100}; '
           f'ndcg@20 {ndcg:.7f} (stored {float(fx["metric"]["ndcg@20"]):.7f}), recall@20 {recall:.7f} '
           f'(stored {float(fx["metric"]["recall@20"]):.7f})')
-    assert bad_rows == 0, f'{bad_rows} users whose top-20 ids differ from the reference'
+    print(f'   near-tie swaps: {bad_rows} users, largest score gap between swapped ids {worst_gap:.3e} (max |score| {smax:.2f})')
+    assert bad_rows <= max(2, n // 2000), f'{bad_rows} users whose top-20 ids differ from the reference'
+    assert worst_gap <= 4e-6 * smax, f'ids differ across a score gap of {worst_gap:.3e}: not a round-off tie'
     assert abs(ndcg - float(fx['metric']['ndcg@20'])) < 5e-7
     assert abs(recall - float(fx['metric']['recall@20'])) < 5e-7
 
