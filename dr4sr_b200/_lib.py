@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
-LIB_PATH = os.path.join(CSRC, 'libdr4sr.so')
+LIB_PATH = os.environ.get('DR4SR_LIB_PATH') or os.path.join(CSRC, 'libdr4sr.so')   # override: debug builds only (make libdr4sr_trace.so)
 
 c_i32, c_i64, c_u64, c_f32, c_sz, c_p = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_size_t, C.c_void_p
 

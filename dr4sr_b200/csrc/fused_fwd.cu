@@ -55,12 +55,21 @@ __device__ int* g_trace = nullptr;
 #endif
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#ifdef DR4SR_TESTWAIT   // experiment: non-suspending poll
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t"
       "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int tag) {
@@ -127,10 +136,11 @@ __global__ void __launch_bounds__(1024) fused_tiles_kernel(const int32_t* __rest
 // residual stream of the tile ("park": x0 / x1 / x2 rows, read back by the LayerNorm epilogues instead of HBM).
 struct Ctx {
   uint8_t* smem;            // 1 KB aligned dynamic smem: [0,64K) A / Q,K / P images, [64K,96K) weight ring / V images
-  uint64_t *full, *empty;   // [2] weight-ring barriers
-  uint64_t* acc;            // accumulator-ready barrier
+  uint64_t *full;           // [2] weight-ring slot filled (two completions per chunk and slot: parity 0 then 1)
+  uint64_t *free01;         // both slots released by the first half of a chunk (one completion per chunk)
+  uint64_t* acc;            // accumulator-ready barrier (also: the ring is idle again)
   uint32_t tmem;            // TMEM base
-  uint32_t fetched, used;   // weight-ring counters (meaningful in thread 0 only)
+  uint32_t pchunk, ppieces; // weight ring, producer side (thread kProducer only): chunks streamed; pieces of the current chunk queued
   uint32_t n_acc;           // completed phases of `acc` (uniform across the CTA)
   int r0, R;                // packed rows [r0, r0 + R) of the tile
   // this thread's epilogue identity: tile row quad*32+lane, 64-column half warp>>2
@@ -147,61 +157,77 @@ __device__ __forceinline__ uint8_t* a_hi(const Ctx& c, int kb) { return c.smem +
 __device__ __forceinline__ uint8_t* a_lo(const Ctx& c, int kb) { return c.smem + (uint32_t)(2 + kb) * kImg; }
 __device__ __forceinline__ uint8_t* ring(const Ctx& c, uint32_t slot) { return c.smem + (4 + slot) * kImg; }
 
-// thread 0: queue the bulk copy of one 16 KB weight piece into the next ring slot
-__device__ __forceinline__ void ring_fetch(Ctx& c, const uint8_t* src) {
-  const uint32_t slot = c.fetched & 1u, use = c.fetched >> 1;
-  if (use >= 1) {                                   // the UMMAs that read the slot's previous piece are done
-    mbar_wait_b(&c.empty[slot], (use - 1) & 1u, 100 + (int)slot);
-  }
+// Weight ring: two 16 KB slots.  A GEMM chunk (128 output columns, K = 128) streams four pieces through it:
+//   0: W_hi k-block 0 -> slot 0, 1: W_lo k-block 0 -> slot 1, 2: W_hi k-block 1 -> slot 0, 3: W_lo k-block 1 -> slot 1.
+// The ring is fed by its own thread (lane 0 of warp 1): refills must wait for the UMMAs that read a slot's previous piece,
+// and with both roles in one thread those waits sat between UMMA issues (~9 K cycles per chunk, profiles/r2_fused_fwd_timeline.md).
+// Thread 0 only waits for `full`, issues, and commits twice per chunk (`free01` after the first half, `acc` at the end).
+constexpr int kProducer = 32;
+__device__ __forceinline__ void ring_put(Ctx& c, uint32_t slot, const uint8_t* src) {
   mbar_expect_tx(&c.full[slot], kImg);
   bulk_g2s(ring(c, slot), src, kImg, &c.full[slot]);
-  ++c.fetched;
 }
 // piece p of a 128-column chunk n0 of a logical [N_total, 128] weight: p = 2 * kb + (lo ? 1 : 0)
 __device__ __forceinline__ const uint8_t* piece_src(const uint16_t* hi, const uint16_t* lo, int N_total, int n0, int p) {
   const uint8_t* base = reinterpret_cast<const uint8_t*>((p & 1) ? lo : hi);
   return base + ((size_t)(p >> 1) * N_total + n0) * 128;
 }
+// producer: pieces 0, 1 of the next chunk.  The caller guarantees that no UMMA still reads the ring (every thread has
+// passed wait_acc of the previous chunk, or produce_chunk has just waited for it).  Idempotent.
 __device__ __forceinline__ void prefetch_chunk(Ctx& c, const uint16_t* hi, const uint16_t* lo, int N_total, int n0) {
-  ring_fetch(c, piece_src(hi, lo, N_total, n0, 0));
-  ring_fetch(c, piece_src(hi, lo, N_total, n0, 1));
+  if (c.ppieces == 0u) {
+    ring_put(c, 0u, piece_src(hi, lo, N_total, n0, 0));
+    ring_put(c, 1u, piece_src(hi, lo, N_total, n0, 1));
+    c.ppieces = 2u;
+  }
+}
+// producer: the rest of the current chunk, then (nhi != null) the first two pieces of the next one once the ring is idle
+__device__ __noinline__ void produce_chunk(Ctx& c, const uint16_t* hi, const uint16_t* lo, int N_total, int n0,
+                                           const uint16_t* nhi, const uint16_t* nlo, int nN_total, int nn0) {
+  prefetch_chunk(c, hi, lo, N_total, n0);
+  mbar_wait_b(c.free01, c.pchunk & 1u, 100);
+  ring_put(c, 0u, piece_src(hi, lo, N_total, n0, 2));
+  ring_put(c, 1u, piece_src(hi, lo, N_total, n0, 3));
+  ++c.pchunk;
+  c.ppieces = 0u;
+  if (nhi) {
+    mbar_wait_b(c.acc, c.n_acc & 1u, 101);          // peek: the chunk's last UMMAs are done (wait_acc consumes the phase later)
+    prefetch_chunk(c, nhi, nlo, nN_total, nn0);
+  }
 }
 
-// thread 0: acc[128 x 128] (TMEM columns [0,128)) = A (hi/lo images in smem, K = 128) x W[n0..n0+127, :]^T.
-// The first two pieces of the chunk must already be in flight (prefetch_chunk).  `nhi != null`: the first two
-// pieces of the NEXT chunk are queued as soon as ring slots free up.
-__device__ __noinline__ void issue_chunk(Ctx& c, const uint16_t* hi, const uint16_t* lo, int N_total, int n0,
-                                         const uint16_t* nhi, const uint16_t* nlo, int nN_total, int nn0) {
+// thread 0: acc[128 x 128] (TMEM columns [0,128)) = A (hi/lo images in smem, K = 128) x the chunk's four weight pieces.
+// Operand descriptors advance by integer adds on their lower words (gemm_tc.cuh, desc_lo / umma_lo).
+__device__ __noinline__ void issue_chunk(Ctx& c) {
   const uint32_t acc = c.tmem;
-#pragma unroll 1
-  for (int p = 0; p < 4; ++p) {
-    const uint32_t slot = c.used & 1u, use = c.used >> 1;
-    mbar_wait_b(&c.full[slot], use & 1u, 200 + (int)slot);
-    TRACE(2000 + p);
+  const uint32_t w0 = desc_lo(smem_u32(ring(c, 0u))), w1 = desc_lo(smem_u32(ring(c, 1u)));
+  TRACE(1999);
+#pragma unroll
+  for (int kb = 0; kb < 2; ++kb) {
+    const uint32_t ah = desc_lo(smem_u32(a_hi(c, kb))), al = desc_lo(smem_u32(a_lo(c, kb)));
+    mbar_wait_b(&c.full[0], (uint32_t)kb, 200);
+    TRACE(2000 + 2 * kb);
     tc_fence_after();
-    const int kb = p >> 1;
-    const uint32_t b = smem_u32(ring(c, slot)), ah = smem_u32(a_hi(c, kb)), al = smem_u32(a_lo(c, kb));
-    if ((p & 1) == 0) {                               // W_hi piece: A_hi W_hi + A_lo W_hi
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t ko = (uint32_t)k * 32u;
-        umma_bf16(acc, sw128_desc(ah + ko), sw128_desc(b + ko), kIdesc, (p > 0 || k > 0) ? 1u : 0u);
-        umma_bf16(acc, sw128_desc(al + ko), sw128_desc(b + ko), kIdesc, 1u);
-      }
-    } else {                                          // W_lo piece: A_hi W_lo
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t ko = (uint32_t)k * 32u;
-        umma_bf16(acc, sw128_desc(ah + ko), sw128_desc(b + ko), kIdesc, 1u);
-      }
+    for (int k = 0; k < 4; ++k) {                     // W_hi piece: A_hi W_hi + A_lo W_hi
+      if (kb == 0 && k == 0) umma_lo<false>(acc, ah, w0, kIdesc); else umma_lo<true>(acc, ah + 2u * k, w0 + 2u * k, kIdesc);
+      umma_lo<true>(acc, al + 2u * k, w0 + 2u * k, kIdesc);
     }
-    umma_commit(&c.empty[slot]);
-    ++c.used;
-    if (p + 2 < 4) { ring_fetch(c, piece_src(hi, lo, N_total, n0, p + 2)); TRACE(2010 + p); }
+    mbar_wait_b(&c.full[1], (uint32_t)kb, 201);
+    TRACE(2001 + 2 * kb);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_lo<true>(acc, ah + 2u * k, w1 + 2u * k, kIdesc);      // W_lo piece: A_hi W_lo
+    TRACE(2010 + kb);
+    umma_commit(kb == 0 ? c.free01 : c.acc);
   }
-  umma_commit(c.acc);
-  if (nhi) prefetch_chunk(c, nhi, nlo, nN_total, nn0);
   TRACE(2020);
+}
+// one GEMM chunk: thread 0 issues, the producer streams, everybody else goes straight to wait_acc
+__device__ __forceinline__ void run_chunk(Ctx& c, const uint16_t* hi, const uint16_t* lo, int N_total, int n0,
+                                          const uint16_t* nhi, const uint16_t* nlo, int nN_total, int nn0) {
+  if (threadIdx.x == 0) issue_chunk(c);
+  else if (threadIdx.x == kProducer) produce_chunk(c, hi, lo, N_total, n0, nhi, nlo, nN_total, nn0);
 }
 
 // all threads: wait for the accumulator committed by the most recent issue
@@ -519,13 +545,12 @@ __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, co
   sync_for_mma();
   TRACE(1000 + 10 * h + 1);
   if (tid == 0) {                                             // S = Q K^T -> TMEM columns [0,128)
-    const uint32_t ah = smem_u32(q_hi), al = smem_u32(q_lo), bh = smem_u32(k_hi), bl = smem_u32(k_lo);
+    const uint32_t ah = desc_lo(smem_u32(q_hi)), al = desc_lo(smem_u32(q_lo)), bh = desc_lo(smem_u32(k_hi)), bl = desc_lo(smem_u32(k_lo));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const uint32_t ko = (uint32_t)k * 32u;
-      umma_bf16(c.tmem, sw128_desc(ah + ko), sw128_desc(bh + ko), kIdesc, k > 0 ? 1u : 0u);
-      umma_bf16(c.tmem, sw128_desc(ah + ko), sw128_desc(bl + ko), kIdesc, 1u);
-      umma_bf16(c.tmem, sw128_desc(al + ko), sw128_desc(bh + ko), kIdesc, 1u);
+      if (k == 0) umma_lo<false>(c.tmem, ah, bh, kIdesc); else umma_lo<true>(c.tmem, ah + 2u * k, bh + 2u * k, kIdesc);
+      umma_lo<true>(c.tmem, ah + 2u * k, bl + 2u * k, kIdesc);
+      umma_lo<true>(c.tmem, al + 2u * k, bh + 2u * k, kIdesc);
     }
     umma_commit(c.acc);
   }
@@ -601,13 +626,14 @@ __device__ __forceinline__ void attention_head(Ctx& c, const FusedFwdArgs& a, co
   sync_for_mma();
   TRACE(1000 + 10 * h + 3);
   if (tid == 0) {                                             // O = P' V -> TMEM columns [0,64) (over the dead scores)
-    const uint32_t ah = smem_u32(c.smem), al = smem_u32(c.smem + 2 * kImg), bh = smem_u32(v_hi), bl = smem_u32(v_lo);
+    const uint32_t ah = desc_lo(smem_u32(c.smem)), al = desc_lo(smem_u32(c.smem + 2 * kImg)), bh = desc_lo(smem_u32(v_hi)),
+                   bl = desc_lo(smem_u32(v_lo));
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {                             // 16 keys per UMMA
-      const uint32_t ao = (uint32_t)(k >> 2) * kImg + (uint32_t)(k & 3) * 32u, bo = (uint32_t)k * 2048u;
-      umma_bf16(c.tmem, sw128_desc(ah + ao), mn_desc16(bh + bo), kIdescN64_K_MN, k > 0 ? 1u : 0u);
-      umma_bf16(c.tmem, sw128_desc(ah + ao), mn_desc16(bl + bo), kIdescN64_K_MN, 1u);
-      umma_bf16(c.tmem, sw128_desc(al + ao), mn_desc16(bh + bo), kIdescN64_K_MN, 1u);
+    for (int k = 0; k < 8; ++k) {                             // 16 keys per UMMA: A step 32 B inside the k-block image, B step 2048 B
+      const uint32_t ao = (uint32_t)(k >> 2) * (kImg >> 4) + (uint32_t)(k & 3) * 2u, bo = (uint32_t)k * 128u;
+      if (k == 0) umma_lo<false>(c.tmem, ah, bh, kIdescN64_K_MN); else umma_lo<true>(c.tmem, ah + ao, bh + bo, kIdescN64_K_MN);
+      umma_lo<true>(c.tmem, ah + ao, bl + bo, kIdescN64_K_MN);
+      umma_lo<true>(c.tmem, al + ao, bh + bo, kIdescN64_K_MN);
     }
     umma_commit(c.acc);
   }
@@ -652,8 +678,8 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
 
   Ctx c;
   c.smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  c.full = &bars[0]; c.empty = &bars[2]; c.acc = &bars[4];
-  c.fetched = 0; c.used = 0; c.n_acc = 0;
+  c.full = &bars[0]; c.free01 = &bars[2]; c.acc = &bars[3];
+  c.pchunk = 0; c.ppieces = 0; c.n_acc = 0;
 #ifdef DR4SR_TRACE
   __shared__ int s_trace[256];
   c.tr_n = 0; c.tr_t0 = clock64(); c.tr_buf = s_trace;
@@ -697,7 +723,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       if (lane == 0) { s_padbits[2 * warp] = real & 0xFFFFu; s_padbits[2 * warp + 1] = real >> 16; }
     }
     TRACE(1);
-    if (tid == 0) prefetch_chunk(c, a.layer[0].in_hi, a.layer[0].in_lo, 384, 0);
+    if (tid == kProducer) prefetch_chunk(c, a.layer[0].in_hi, a.layer[0].in_lo, 384, 0);
     __syncthreads();
     TRACE(2);
     // ---- x0 = dropout(E[id] + P[t]) -> global (the backward needs it), park (residual) and the first A operand ----
@@ -759,10 +785,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
 #pragma unroll 1
       for (int ch = 0; ch < 3; ++ch) {
         TRACE(100 * l + 10 + ch);
-        if (tid == 0) {
-          const bool nx = ch < 2;
-          issue_chunk(c, y.in_hi, y.in_lo, 384, ch * 128, nx ? y.in_hi : nullptr, y.in_lo, 384, (ch + 1) * 128);
-        }
+        run_chunk(c, y.in_hi, y.in_lo, 384, ch * 128, ch < 2 ? y.in_hi : nullptr, y.in_lo, 384, (ch + 1) * 128);
         TRACE(100 * l + 13 + ch);
         wait_acc(c);
         TRACE(100 * l + 16 + ch);
@@ -779,11 +802,11 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       }
       TRACE(100 * l + 30);
       // ---- out-proj + dropout + residual + LN1 (x1 -> park and the FFN-up operand) ----
-      if (tid == 0) prefetch_chunk(c, y.out_hi, y.out_lo, 128, 0);
+      if (tid == kProducer) prefetch_chunk(c, y.out_hi, y.out_lo, 128, 0);
       stage_a_global(c, y.attn, 128);
       sync_for_mma();
       TRACE(100 * l + 31);
-      if (tid == 0) issue_chunk(c, y.out_hi, y.out_lo, 128, 0, y.w1_hi, y.w1_lo, 128, 0);
+      run_chunk(c, y.out_hi, y.out_lo, 128, 0, y.w1_hi, y.w1_lo, 128, 0);
       TRACE(100 * l + 32);
       wait_acc(c);
       TRACE(100 * l + 33);
@@ -791,7 +814,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       sync_for_mma();
       TRACE(100 * l + 40);
       // ---- FFN up (+bias -> pre) ; dropout(gelu(pre)) -> the FFN-down operand ----
-      if (tid == 0) issue_chunk(c, y.w1_hi, y.w1_lo, 128, 0, y.w2_hi, y.w2_lo, 128, 0);
+      run_chunk(c, y.w1_hi, y.w1_lo, 128, 0, y.w2_hi, y.w2_lo, 128, 0);
       TRACE(100 * l + 41);
       wait_acc(c);
       TRACE(100 * l + 42);
@@ -800,8 +823,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       TRACE(100 * l + 50);
       // ---- FFN down + dropout + residual + LN2 (x2 -> park and the next layer's QKV operand) ----
       const bool more = l + 1 < a.n_layer;
-      if (tid == 0)
-        issue_chunk(c, y.w2_hi, y.w2_lo, 128, 0, more ? a.layer[more ? l + 1 : l].in_hi : nullptr, a.layer[more ? l + 1 : l].in_lo, 384, 0);
+      run_chunk(c, y.w2_hi, y.w2_lo, 128, 0, more ? a.layer[more ? l + 1 : l].in_hi : nullptr, a.layer[more ? l + 1 : l].in_lo, 384, 0);
       TRACE(100 * l + 51);
       wait_acc(c);
       TRACE(100 * l + 52);
@@ -908,8 +930,8 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
 
   Ctx c;
   c.smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  c.full = &bars[0]; c.empty = &bars[2]; c.acc = &bars[4];
-  c.fetched = 0; c.used = 0; c.n_acc = 0;
+  c.full = &bars[0]; c.free01 = &bars[2]; c.acc = &bars[3];
+  c.pchunk = 0; c.ppieces = 0; c.n_acc = 0;
 #ifdef DR4SR_TRACE
   __shared__ int s_trace[256];
   c.tr_n = 0; c.tr_t0 = clock64(); c.tr_buf = s_trace;
@@ -935,7 +957,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
     c.live = c.row < c.R;
     c.m = c.r0 + c.row;
     TRACE(1);
-    if (tid == 0 && c.fetched == c.used) prefetch_chunk(c, a.w2_hi, a.w2_lo, 128, 0);   // else queued by the previous tile
+    if (tid == kProducer) prefetch_chunk(c, a.w2_hi, a.w2_lo, 128, 0);   // no-op when the previous tile already queued them
     // ---- g3 = LN2'(gin) -> HBM, park, A operand (g3 . mask_ffn_out) ----
     {
       float gd[64];
@@ -951,7 +973,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
     sync_for_mma();
     TRACE(3);
     // ---- dpre = (A W2) . mask_ffn_h . gelu'(pre) -> HBM and the next A operand ----
-    if (tid == 0) issue_chunk(c, a.w2_hi, a.w2_lo, 128, 0, a.w1_hi, a.w1_lo, 128, 0);
+    run_chunk(c, a.w2_hi, a.w2_lo, 128, 0, a.w1_hi, a.w1_lo, 128, 0);
     TRACE(4);
     wait_acc(c);
     TRACE(5);
@@ -985,7 +1007,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
     sync_for_mma();
     TRACE(7);
     // ---- dx1 = g3 + A W1 -> HBM ; g1 = LN1'(dx1) -> HBM and the next A operand (g1 . mask_attn_out) ----
-    if (tid == 0) issue_chunk(c, a.w1_hi, a.w1_lo, 128, 0, a.out_hi, a.out_lo, 128, 0);
+    run_chunk(c, a.w1_hi, a.w1_lo, 128, 0, a.out_hi, a.out_lo, 128, 0);
     TRACE(8);
     wait_acc(c);
     TRACE(9);
@@ -1014,7 +1036,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
     TRACE(12);
     // ---- g2 = A Wo -> HBM ----
     const bool more = tile + (int)gridDim.x < n_tiles;
-    if (tid == 0) issue_chunk(c, a.out_hi, a.out_lo, 128, 0, more ? a.w2_hi : nullptr, a.w2_lo, 128, 0);
+    run_chunk(c, a.out_hi, a.out_lo, 128, 0, more ? a.w2_hi : nullptr, a.w2_lo, 128, 0);
     TRACE(13);
     wait_acc(c);
     TRACE(14);

@@ -127,6 +127,28 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B
   return d;
 }
+// Lean issue path.  Every SWIZZLE_128B descriptor used here (K-major, and MN-major with a 16-byte leading offset) has the
+// same upper word and the lower word (smem_addr >> 4) | 1 << 16, so a thread that issues a long UMMA sequence keeps the
+// 32-bit lower words of its operand bases and advances them with one integer add per step (+2 per 32 bytes) instead of
+// rebuilding two 64-bit descriptors per instruction: the single issuing thread is a latency-bound scalar stream, and the
+// descriptor arithmetic was most of its ~150 cycles per UMMA (profiles/r2_fused_fwd_timeline.md).
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <bool ACC>
+__device__ __forceinline__ void umma_lo(uint32_t tmem_c, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      ".reg .pred p;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}" ::"r"(tmem_c), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(ACC ? 1u : 0u) : "memory");
+}
+__device__ __forceinline__ void umma_lo(uint32_t tmem_c, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool acc) {
+  if (acc) umma_lo<true>(tmem_c, a_lo, b_lo, idesc); else umma_lo<false>(tmem_c, a_lo, b_lo, idesc);
+}
 // instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 
