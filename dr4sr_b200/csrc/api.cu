@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 #include "common.cuh"
-namespace dr4sr { int fused_fwd_set_trace(int* host_mapped); }
+namespace dr4sr { int fused_fwd_set_trace(int* host_mapped); int attn_bwd_set_trace(int* host_mapped); }
 
 namespace dr4sr {
 static thread_local char g_err[256] = "";
@@ -17,7 +17,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
 }
 
 std::atomic<int> g_gemm_backend{0};
-std::atomic<int> g_attn_backend{0};
+std::atomic<int> g_attn_backend{2};
 std::atomic<int> g_fused_backend{1};
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -53,7 +53,7 @@ extern "C" int dr4sr_set_gemm_backend(int backend) {
   return DR4SR_OK;
 }
 extern "C" int dr4sr_set_attn_backend(int backend) {
-  if (backend != 0 && backend != 1) return DR4SR_EINVAL;
+  if (backend < 0 || backend > 2) return DR4SR_EINVAL;
   g_attn_backend.store(backend);
   return DR4SR_OK;
 }
@@ -62,7 +62,10 @@ extern "C" int dr4sr_set_fused_backend(int backend) {
   g_fused_backend.store(backend);
   return DR4SR_OK;
 }
-extern "C" int dr4sr_debug_trace(int* host_mapped) { return fused_fwd_set_trace(host_mapped); }
+extern "C" int dr4sr_debug_trace(int* host_mapped) {
+  const int rc = fused_fwd_set_trace(host_mapped);
+  return rc != DR4SR_OK ? rc : attn_bwd_set_trace(host_mapped);
+}
 extern "C" long long dr4sr_launch_count(void) { return g_launches.load(); }
 
 extern "C" int dr4sr_prof_enable(int on) {

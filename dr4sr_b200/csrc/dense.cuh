@@ -8,7 +8,7 @@
 
 namespace dr4sr {
 
-extern std::atomic<int> g_attn_backend;   // 0 = FFMA attention kernels (default), 1 = tcgen05 attention tiles (dr4sr_set_attn_backend)
+extern std::atomic<int> g_attn_backend;   // 0 = FFMA attention kernels, 1 = tcgen05 window tiles (fwd + bwd), 2 (default) = persistent tcgen05 backward on the greedy tiles (dr4sr_set_attn_backend)
 extern std::atomic<int> g_gemm_backend;   // 0 = tcgen05 where the shape allows, 1 = FFMA everywhere (dr4sr_set_gemm_backend)
 extern std::atomic<int> g_fused_backend;  // 0 = per-op kernels, 1 = persistent fused forward where the shape allows (default), 2 = + fused backward FFN block
 constexpr int kSplit = 64;                // token splits of the weight-gradient GEMMs (partials reduced in fixed order)
@@ -18,6 +18,7 @@ inline bool tc_enabled() { return g_gemm_backend.load(std::memory_order_relaxed)
 inline bool fused_enabled() { return tc_enabled() && g_fused_backend.load(std::memory_order_relaxed) >= 1; }
 inline bool fused_bwd_enabled() { return tc_enabled() && g_fused_backend.load(std::memory_order_relaxed) == 2; }
 inline bool attn_tc_enabled() { return tc_enabled() && g_attn_backend.load(std::memory_order_relaxed) == 1; }
+inline bool attn_bwd_tc2_enabled() { return tc_enabled() && g_attn_backend.load(std::memory_order_relaxed) == 2; }
 
 inline bool use_tc(const GemmArgs& g, const Img& im, bool ln) {
   return tc_enabled() && im.hi && tc::tc_supported(g.N, g.K, ln);

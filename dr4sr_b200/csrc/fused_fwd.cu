@@ -86,7 +86,7 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int 
 }
 
 struct FusedLayer {
-  float *qkv, *attn, *z1, *st1, *x1, *pre, *z2, *st2, *x2;                        // saved activations (packed rows)
+  float *qkv, *attn, *z1, *st1, *x1, *pre, *hm, *z2, *st2, *x2;                   // saved activations (packed rows); hm = dropout(gelu(pre))
   const uint16_t *in_hi, *in_lo, *out_hi, *out_lo, *w1_hi, *w1_lo, *w2_hi, *w2_lo;   // weight images
   const float *in_b, *out_b, *b1, *b2, *g1, *be1, *g2, *be2;
   Dropout d_attn_p, d_attn_out, d_ffn_h, d_ffn_out;
@@ -437,7 +437,8 @@ __device__ __forceinline__ void tmem_ld_fence(float* v, bool wait) {
 }
 
 // out[row, n] = acc + bias[n]; gelu_stage: the next A operand = dropout(gelu(out)) goes straight to shared memory
-__device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, int ldo, bool gelu_stage, Dropout dh) {
+// (also written to `hm`: the FFN-down weight gradient reads it instead of recomputing GELU + dropout per element)
+__device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, int ldo, bool gelu_stage, Dropout dh, float* hm) {
   RowDrop rd;
   rd.init(dh, (uint32_t)me.m);
   float* orow = out + (size_t)me.m * ldo + me.half * 64;
@@ -466,6 +467,11 @@ __device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, 
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[q * 16 + j] = gelu_f(v[q * 16 + j]) * f[j];
         store_image16(v + q * 16, me.row, n0 + q * 16, me.smem);
+      }
+      if (me.live && hm) {
+        float* hrow = hm + (size_t)me.m * ldo + me.half * 64 + g * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st_global_v8(hrow + j, v + j);
       }
     }
   }
@@ -789,7 +795,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
         TRACE(100 * l + 13 + ch);
         wait_acc(c);
         TRACE(100 * l + 16 + ch);
-        epi_linear(me_of(c), s_par + kParIn + ch * 128, y.qkv + ch * 128, 384, false, y.d_ffn_h);
+        epi_linear(me_of(c), s_par + kParIn + ch * 128, y.qkv + ch * 128, 384, false, y.d_ffn_h, nullptr);
         tc_fence_before();
         __syncthreads();                                      // accumulator free; qkv rows visible to the whole CTA
         tc_fence_after();
@@ -818,7 +824,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       TRACE(100 * l + 41);
       wait_acc(c);
       TRACE(100 * l + 42);
-      epi_linear(me_of(c), s_par + kParB1, y.pre, 128, true, y.d_ffn_h);
+      epi_linear(me_of(c), s_par + kParB1, y.pre, 128, true, y.d_ffn_h, y.hm);
       sync_for_mma();
       TRACE(100 * l + 50);
       // ---- FFN down + dropout + residual + LN2 (x2 -> park and the next layer's QKV operand) ----
@@ -1115,7 +1121,7 @@ int launch_sasrec_fwd_fused(const FusedFwdHost& h, cudaStream_t st) {
   for (int l = 0; l < h.n_layer; ++l) {
     const FusedLayerHost& s = h.layer[l];
     FusedLayer& d = a.layer[l];
-    d.qkv = s.qkv; d.attn = s.attn; d.z1 = s.z1; d.st1 = s.st1; d.x1 = s.x1; d.pre = s.pre; d.z2 = s.z2; d.st2 = s.st2; d.x2 = s.x2;
+    d.qkv = s.qkv; d.attn = s.attn; d.z1 = s.z1; d.st1 = s.st1; d.x1 = s.x1; d.pre = s.pre; d.hm = s.hm; d.z2 = s.z2; d.st2 = s.st2; d.x2 = s.x2;
     d.in_hi = s.img[0]; d.in_lo = s.img[1]; d.out_hi = s.img[2]; d.out_lo = s.img[3];
     d.w1_hi = s.img[4]; d.w1_lo = s.img[5]; d.w2_hi = s.img[6]; d.w2_lo = s.img[7];
     d.in_b = s.in_b; d.out_b = s.out_b; d.b1 = s.b1; d.b2 = s.b2; d.g1 = s.g1; d.be1 = s.be1; d.g2 = s.g2; d.be2 = s.be2;

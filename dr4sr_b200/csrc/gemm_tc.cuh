@@ -308,13 +308,12 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
     if (tid == 0) {
       mbar_wait(&bar_b, (uint32_t)(s & 1));                 // weight stage landed
       tc_fence_after();
-      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      const uint32_t ah = desc_lo(smem_u32(a_hi)), al = desc_lo(smem_u32(a_lo)), bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
 #pragma unroll
-      for (int k = 0; k < kBK / 16; ++k) {                  // UMMA K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
-        const uint32_t ko = (uint32_t)k * 32u;
-        umma_bf16(tmem, sw128_desc(ah + ko), sw128_desc(bh + ko), kIdesc, (s > 0 || k > 0) ? 1u : 0u);
-        umma_bf16(tmem, sw128_desc(ah + ko), sw128_desc(bl + ko), kIdesc, 1u);
-        umma_bf16(tmem, sw128_desc(al + ko), sw128_desc(bh + ko), kIdesc, 1u);
+      for (int k = 0; k < kBK / 16; ++k) {                  // UMMA K = 16 bf16 = 32 bytes inside the 128-byte swizzle row (+2 in 16 B units)
+        umma_lo(tmem, ah + 2u * k, bh + 2u * k, kIdesc, s > 0 || k > 0);
+        umma_lo<true>(tmem, ah + 2u * k, bl + 2u * k, kIdesc);
+        umma_lo<true>(tmem, al + 2u * k, bh + 2u * k, kIdesc);
       }
       umma_commit(&bar_mma);                                // arrives when every UMMA above has finished
     }
@@ -598,13 +597,15 @@ static __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(WgradTable ta
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      // MN-major descriptors: same upper word as desc_lo's, leading byte offset kWFeatStride in the lower word
+      constexpr uint32_t kLbo = ((kWFeatStride >> 4) << 16) - (1u << 16);
+      const uint32_t ah = desc_lo(smem_u32(a_hi)) + kLbo, al = desc_lo(smem_u32(a_lo)) + kLbo, bh = desc_lo(smem_u32(b_hi)) + kLbo,
+                     bl = desc_lo(smem_u32(b_lo)) + kLbo;
 #pragma unroll
-      for (int k = 0; k < kWTok / 16; ++k) {           // 16 tokens = two 8-token groups = 2048 bytes
-        const uint32_t ko = (uint32_t)k * 2048u;
-        umma_bf16(tmem, sw128_desc_mn(ah + ko), sw128_desc_mn(bh + ko), kIdescMN, (s > 0 || k > 0) ? 1u : 0u);
-        umma_bf16(tmem, sw128_desc_mn(ah + ko), sw128_desc_mn(bl + ko), kIdescMN, 1u);
-        umma_bf16(tmem, sw128_desc_mn(al + ko), sw128_desc_mn(bh + ko), kIdescMN, 1u);
+      for (int k = 0; k < kWTok / 16; ++k) {           // 16 tokens = two 8-token groups = 2048 bytes (+128 in 16 B units)
+        umma_lo(tmem, ah + 128u * k, bh + 128u * k, kIdescMN, s > 0 || k > 0);
+        umma_lo<true>(tmem, ah + 128u * k, bl + 128u * k, kIdescMN);
+        umma_lo<true>(tmem, al + 128u * k, bh + 128u * k, kIdescMN);
       }
       umma_commit(&bar_buf[s & 1]);
       if (s + 1 == nstage) umma_commit(&bar_done);

@@ -19,9 +19,13 @@ int launch_attn_tc_fwd(const float* qkv, const int64_t* in_ids, const int32_t* t
 int launch_attn_tc_bwd(const float* qkv, const float* d_out, const int64_t* in_ids, const int32_t* tok_off, const int32_t* row_seq,
                        const int32_t* tile_first, float* d_qkv, int B, int L, int D, int n_head, Dropout drop, cudaStream_t st);
 
+// persistent tcgen05 attention backward over the greedy whole-sequence tiles of the fused forward  [attention_bwd_tc.cu]
+int launch_attn_bwd_tc2(const float* qkv, const float* d_out, const int64_t* in_ids, const int32_t* tok_off, const int32_t* row_seq,
+                        const int32_t* tiles, int tiles_cap, float* d_qkv, int B, int L, int D, int n_head, Dropout drop, cudaStream_t st);
+
 // whole-encoder forward as one persistent tcgen05 kernel (D = F = 128, 2 heads)  [fused_fwd.cu]
 struct FusedLayerHost {
-  float *qkv, *attn, *z1, *st1, *x1, *pre, *z2, *st2, *x2;
+  float *qkv, *attn, *z1, *st1, *x1, *pre, *hm, *z2, *st2, *x2;   // hm (optional) = dropout(gelu(pre)), kept for the FFN-down weight gradient
   const uint16_t* img[8];   // in_hi, in_lo, out_hi, out_lo, w1_hi, w1_lo, w2_hi, w2_lo (forward weight images)
   const float *in_b, *out_b, *b1, *b2, *g1, *be1, *g2, *be2;
   Dropout d_attn_p, d_attn_out, d_ffn_h, d_ffn_out;
@@ -40,6 +44,7 @@ int fused_tiles_cap(int B, int L);
 int launch_fused_tiles(const int32_t* tok_off, int B, int32_t* tiles, cudaStream_t st);
 int launch_sasrec_fwd_fused(const FusedFwdHost& h, cudaStream_t st);
 int fused_fwd_set_trace(int* host_mapped);
+int attn_bwd_set_trace(int* host_mapped);
 // backward of the position-wise half of a layer (LN2', dpre, dx1, LN1', d(attn)) as one persistent kernel  [fused_fwd.cu]
 struct FusedBwdFfnHost {
   const float *gin, *z2, *st2, *pre, *z1, *st1, *gamma2, *gamma1;

@@ -3,6 +3,7 @@
 // Replaces SASRecQueryEncoder.forward (reference model/sasrec.py:39-75) = embedding + learned
 // positions + dropout -> 2 x post-norm TransformerEncoderLayer (model/sasrec.py:21-34) -> pooling,
 // and its autograd backward.  Spec: SURVEY.md Appendix C.1, C.2, C.5.
+#include <stdlib.h>
 #include "dense.cuh"
 
 namespace dr4sr {
@@ -34,7 +35,7 @@ LayerOffsets layer_offsets(int D, int F) {
 struct Workspace {
   // saved activations
   float* x0;
-  struct Layer { float *qkv, *attn, *z1, *st1, *x1, *pre, *z2, *st2, *x2; } layer[8];
+  struct Layer { float *qkv, *attn, *z1, *st1, *x1, *pre, *hm, *z2, *st2, *x2; } layer[8];   // hm = dropout(gelu(pre)) (fused forward only)
   // backward scratch.  g0 / g2 belong to the data-gradient chain; everything in `Bwd` is per layer because the
   // weight-gradient work of layer l runs on a side stream while the main stream already works on layer l-1
   float *g0, *g2;
@@ -65,7 +66,7 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
   for (int l = 0; l < c.n_layer; ++l) {
     auto& y = w.layer[l];
     y.qkv = take(T * 3 * D); y.attn = take(T * D); y.z1 = take(T * D); y.st1 = take(T * 2); y.x1 = take(T * D);
-    y.pre = take(T * F); y.z2 = take(T * D); y.st2 = take(T * 2); y.x2 = take(T * D);
+    y.pre = take(T * F); y.hm = take(T * F); y.z2 = take(T * D); y.st2 = take(T * 2); y.x2 = take(T * D);
   }
   w.g0 = take(T * D); w.g2 = take(T * D);
   for (int l = 0; l < c.n_layer; ++l) {
@@ -260,7 +261,7 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
       auto& y = w.layer[l];
       const auto& m = w.img[l];
       FusedLayerHost& d = h.layer[l];
-      d.qkv = y.qkv; d.attn = y.attn; d.z1 = y.z1; d.st1 = y.st1; d.x1 = y.x1; d.pre = y.pre; d.z2 = y.z2; d.st2 = y.st2;
+      d.qkv = y.qkv; d.attn = y.attn; d.z1 = y.z1; d.st1 = y.st1; d.x1 = y.x1; d.pre = y.pre; d.hm = y.hm; d.z2 = y.z2; d.st2 = y.st2;
       d.x2 = (l == c->n_layer - 1 && q_packed) ? q_packed : y.x2;
       d.img[0] = m.in_f.hi; d.img[1] = m.in_f.lo; d.img[2] = m.out_f.hi; d.img[3] = m.out_f.lo;
       d.img[4] = m.w1_f.hi; d.img[5] = m.w1_f.lo; d.img[6] = m.w2_f.hi; d.img[7] = m.w2_f.lo;
@@ -287,6 +288,8 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
   DR4SR_TRY(build_weight_images(*c, params, w, lo, st));
   const bool attn_tc = attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head);
   if (attn_tc) DR4SR_TRY(launch_attn_tiles(tok_off, c->B, c->L, w.tile_first, st));
+  if (attn_bwd_tc2_enabled() && attn_tc_supported(c->L, D, c->n_head) && D == 128 && c->n_head == 2)   // its backward runs on the greedy tiles
+    DR4SR_TRY(launch_fused_tiles(tok_off, c->B, w.fused_tiles, st));
   const float* x = w.x0;
   for (int l = 0; l < c->n_layer; ++l) {
     const float* lp = params + (size_t)c->L * D + (size_t)l * lo.total;
@@ -346,6 +349,9 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
   const size_t pw_in = 0, pw_out = (size_t)kSplit * 3 * D * D, pw_w1 = pw_out + (size_t)kSplit * D * D,
                pw_w2 = pw_w1 + (size_t)kSplit * F * D;
 
+  // hm = dropout(gelu(pre)) was written by the fused forward (same predicate as in dr4sr_sasrec_fwd); the per-operator
+  // forward does not materialise it, its FFN-down weight gradient recomputes GELU + dropout from `pre`
+  const bool have_hm = fused_enabled() && fused_fwd_supported(c->L, D, F, c->n_head);
   SideStream& side = side_stream();
   cudaStream_t sw = side.ok ? side.s : st;            // weight-gradient stream (falls back to in-order if creation failed)
   float* gin = dq_packed;   // gradient w.r.t. the current layer's output
@@ -382,13 +388,17 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
       DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
       {
         tc::WgradTable tab{};
-        tab.job[0] = tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
+        tab.job[0] = have_hm ? tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.hm, F, PRO_NONE, none, D, F, s.part_w + pw_w2, 0}
+                             : tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
         tab.job[1] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
         tab.job[2] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
         tab.count = 3; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
         DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
       }
-      if (attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head))
+      if (attn_bwd_tc2_enabled() && attn_tc_supported(c->L, D, c->n_head) && D == 128 && c->n_head == 2)
+        DR4SR_TRY(launch_attn_bwd_tc2(y.qkv, w.g2, in_item_id, tok_off, row_seq, w.fused_tiles, fused_tiles_cap(c->B, c->L), s.dqkv, c->B,
+                                      c->L, D, c->n_head, d_attn_p, st));
+      else if (attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head))
         DR4SR_TRY(launch_attn_tc_bwd(y.qkv, w.g2, in_item_id, tok_off, row_seq, w.tile_first, s.dqkv, c->B, c->L, D, c->n_head,
                                      d_attn_p, st));
       else
@@ -437,29 +447,44 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
     const bool wg_tc = tc_enabled() && tc::wgrad_supported(D, F) && tc::wgrad_supported(F, D) && tc::wgrad_supported(D, D) &&
                        tc::wgrad_supported(3 * D, D);
     const Dropout none = no_dropout();
-    if (side.ok) {   // dz2, dpre, dz1 are final: the weight gradients that do not need dqkv start now (side stream)
-      if (cudaEventRecord(side.fork[2 * l], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[2 * l], 0) != cudaSuccess) {
-        set_cuda_error(cudaGetLastError(), "backward fork");
-        return DR4SR_ECUDA;
+    // Weight gradients that do not need dqkv (dW2, dW1, dWo, db1).  The attention backward holds a whole SM per CTA
+    // (192 KB of shared memory, all 512 TMEM columns), so weight-gradient CTAs already resident on an SM keep it from
+    // starting there: by default this work is queued on the side stream BEHIND the attention backward (it then overlaps
+    // the dx GEMM and the next layer's position-wise kernels, which share SMs with it happily).
+    static const bool early_fork = getenv("DR4SR_WGRAD_EARLY") != nullptr;
+    auto side_A = [&]() -> int {
+      DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
+      //   dW2[d,f]  = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]      dW1[f,d]  = sum_m dpre[m,f] * x1[m,d]
+      //   dWo[n,k]  = sum_m (dz1*mask)[m,n] * attn[m,k]                     dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
+      if (wg_tc) {
+        tc::WgradTable tab{};
+        tab.job[0] = have_hm ? tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.hm, F, PRO_NONE, none, D, F, s.part_w + pw_w2, 0}
+                             : tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
+        tab.job[1] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
+        tab.job[2] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
+        tab.count = 3; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
+        DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
       }
-    }
-    DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
-    //   dW2[d,f]  = sum_m (dz2*mask_out)[m,d] * drop(gelu(pre))[m,f]      dW1[f,d]  = sum_m dpre[m,f] * x1[m,d]
-    //   dWo[n,k]  = sum_m (dz1*mask)[m,n] * attn[m,k]                     dWin[j,d] = sum_m dqkv[m,j] * x[m,d]
-    if (wg_tc) {
-      tc::WgradTable tab{};
-      tab.job[0] = tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
-      tab.job[1] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
-      tab.job[2] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
-      tab.count = 3; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
-      DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
+      return DR4SR_OK;
+    };
+    if (early_fork) {
+      if (side.ok) {   // dz2, dpre, dz1 are final
+        if (cudaEventRecord(side.fork[2 * l], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[2 * l], 0) != cudaSuccess) {
+          set_cuda_error(cudaGetLastError(), "backward fork");
+          return DR4SR_ECUDA;
+        }
+      }
+      DR4SR_TRY(side_A());
     }
     {  // d(attn) = (dz1 * mask) Wo -> g2
       GemmArgs g = gemm_args(s.g1, D, lp + lo.out_w, D, w.g2, D, T, D, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_attn_out; g.tag = "gemm_bwd_dattn";
       DR4SR_TRY(gemm_nn(g, w.img[l].out_b, st));
     }
-    if (attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head))   // tiles were built by the forward (same workspace)
+    if (attn_bwd_tc2_enabled() && attn_tc_supported(c->L, D, c->n_head) && D == 128 && c->n_head == 2)   // tiles were built by the forward
+      DR4SR_TRY(launch_attn_bwd_tc2(y.qkv, w.g2, in_item_id, tok_off, row_seq, w.fused_tiles, fused_tiles_cap(c->B, c->L), s.dqkv, c->B,
+                                    c->L, D, c->n_head, d_attn_p, st));
+    else if (attn_tc_enabled() && attn_tc_supported(c->L, D, c->n_head))   // tiles were built by the forward (same workspace)
       DR4SR_TRY(launch_attn_tc_bwd(y.qkv, w.g2, in_item_id, tok_off, row_seq, w.tile_first, s.dqkv, c->B, c->L, D, c->n_head,
                                    d_attn_p, st));
     else
@@ -470,6 +495,7 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
         return DR4SR_ECUDA;
       }
     }
+    if (!early_fork) DR4SR_TRY(side_A());
     {  // dx = dz1 + dqkv Win  (layer 0: times the embedding-dropout mask) -> g0 / dx0
       float* dst = l == 0 ? dx0_packed : w.g0;
       GemmArgs g = gemm_args(s.dqkv, 3 * D, lp + lo.in_w, D, dst, D, T, D, 3 * D, counts);

@@ -105,9 +105,10 @@ typedef struct {
  * fp32 accumulate) wherever the shape allows (N % 128 == 0, K % 64 == 0), 1 = exact-fp32 FFMA kernels
  * everywhere.  Process-wide; used by the parity tests to check both. */
 DR4SR_API int dr4sr_set_gemm_backend(int backend);
-/* Attention backend (head_dim 64 only): 0 (default) = register-tiled FFMA kernel, one CTA per (sequence, head);
- * 1 = tcgen05 tiles of whole sequences (<= 128 rows) with bf16 hi/lo split operands.  Both are parity-tested; the
- * FFMA kernel is the faster one at L = 50 today (profiles/r1_ncu_full_notes.md). */
+/* Attention backend: 0 = register-tiled FFMA kernels, one CTA per (sequence, head); 1 = tcgen05 tiles of whole sequences
+ * (<= 128 rows, fixed windows) with bf16 hi/lo split operands, forward and backward; 2 (default) = the persistent tcgen05
+ * backward over the fused forward's greedy tiles (csrc/attention_bwd_tc.cu; D = 128, 2 heads -- other shapes fall back to
+ * the FFMA kernels), forward as in 0 when the per-operator schedule runs.  All are parity-tested. */
 DR4SR_API int dr4sr_set_attn_backend(int backend);
 /* Encoder schedule: 1 (default) = persistent fused forward (one CTA carries a group of whole sequences, <= 128
  * packed rows, through every layer: gather, QKV, attention, out-proj+LN, FFN+LN on tcgen05) where the shape allows

@@ -21,21 +21,23 @@ DEV = 'cuda:0'
 # losses / logits); the FFMA path is additionally held to fp32 round-off.
 TOL = {'tc': dict(fwd=1e-4, loss=1e-4, grad=1e-3, adam=1e-4), 'ffma': dict(fwd=1e-5, loss=1e-5, grad=1e-4, adam=2e-5)}
 TOL['tc_attn'] = TOL['tc']          # tcgen05 dense layers + tcgen05 attention tiles
+TOL['tc_attn2'] = TOL['tc']         # per-op tcgen05 dense layers + persistent tcgen05 attention backward (greedy tiles)
+TOL['fused_attn2'] = TOL['tc']      # fused forward + persistent tcgen05 attention backward
 TOL['fused'] = TOL['tc']            # persistent fused encoder kernels (default schedule)
 TOL['fused_bwd'] = TOL['tc']        # + fused backward FFN block
 
 
-@pytest.fixture(params=['fused', 'fused_bwd', 'tc', 'tc_attn', 'ffma'], autouse=True)
+@pytest.fixture(params=['fused', 'fused_attn2', 'fused_bwd', 'tc', 'tc_attn', 'tc_attn2', 'ffma'], autouse=True)
 def backend(request):
     if not torch.cuda.is_available():
         pytest.skip('no CUDA device')
     from dr4sr_b200 import _lib
     _lib.check(_lib.lib().dr4sr_set_gemm_backend(1 if request.param == 'ffma' else 0), 'set_gemm_backend')
-    _lib.check(_lib.lib().dr4sr_set_attn_backend(1 if request.param == 'tc_attn' else 0), 'set_attn_backend')
-    _lib.check(_lib.lib().dr4sr_set_fused_backend({'fused': 1, 'fused_bwd': 2}.get(request.param, 0)), 'set_fused_backend')
+    _lib.check(_lib.lib().dr4sr_set_attn_backend({'tc_attn': 1, 'tc_attn2': 2, 'fused_attn2': 2}.get(request.param, 0)), 'set_attn_backend')
+    _lib.check(_lib.lib().dr4sr_set_fused_backend({'fused': 1, 'fused_attn2': 1, 'fused_bwd': 2}.get(request.param, 0)), 'set_fused_backend')
     yield request.param
     _lib.lib().dr4sr_set_gemm_backend(0)
-    _lib.lib().dr4sr_set_attn_backend(0)
+    _lib.lib().dr4sr_set_attn_backend(2)
     _lib.lib().dr4sr_set_fused_backend(1)
 
 
