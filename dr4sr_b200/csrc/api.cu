@@ -18,7 +18,7 @@ void set_cuda_error(cudaError_t e, const char* where) {
 
 std::atomic<int> g_gemm_backend{0};
 std::atomic<int> g_attn_backend{2};
-std::atomic<int> g_fused_backend{1};
+std::atomic<int> g_fused_backend{2};
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

@@ -10,7 +10,7 @@ namespace dr4sr {
 
 extern std::atomic<int> g_attn_backend;   // 0 = FFMA attention kernels, 1 = tcgen05 window tiles (fwd + bwd), 2 (default) = persistent tcgen05 backward on the greedy tiles (dr4sr_set_attn_backend)
 extern std::atomic<int> g_gemm_backend;   // 0 = tcgen05 where the shape allows, 1 = FFMA everywhere (dr4sr_set_gemm_backend)
-extern std::atomic<int> g_fused_backend;  // 0 = per-op kernels, 1 = persistent fused forward where the shape allows (default), 2 = + fused backward FFN block
+extern std::atomic<int> g_fused_backend;  // 0 = per-op kernels, 1 = persistent fused forward where the shape allows, 2 (default) = + fused backward of each layer's position-wise half
 constexpr int kSplit = 64;                // token splits of the weight-gradient GEMMs (partials reduced in fixed order)
 
 struct Img { uint16_t *hi, *lo; };        // bf16 hi / lo weight images (UMMA SW128 K-major), see gemm_tc.cuh

@@ -86,7 +86,7 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, int 
 }
 
 struct FusedLayer {
-  float *qkv, *attn, *z1, *st1, *x1, *pre, *hm, *z2, *st2, *x2;                   // saved activations (packed rows); hm = dropout(gelu(pre))
+  float *qkv, *attn, *z1, *st1, *x1, *hm, *gp, *z2, *st2, *x2;   // saved activations (packed rows); hm = mask * gelu(pre), gp = mask * gelu'(pre)
   const uint16_t *in_hi, *in_lo, *out_hi, *out_lo, *w1_hi, *w1_lo, *w2_hi, *w2_lo;   // weight images
   const float *in_b, *out_b, *b1, *b2, *g1, *be1, *g2, *be2;
   Dropout d_attn_p, d_attn_out, d_ffn_h, d_ffn_out;
@@ -436,12 +436,12 @@ __device__ __forceinline__ void tmem_ld_fence(float* v, bool wait) {
   }
 }
 
-// out[row, n] = acc + bias[n]; gelu_stage: the next A operand = dropout(gelu(out)) goes straight to shared memory
-// (also written to `hm`: the FFN-down weight gradient reads it instead of recomputing GELU + dropout per element)
-__device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, int ldo, bool gelu_stage, Dropout dh, float* hm) {
+// out[row, n] = acc + bias[n] (QKV projection), or -- `hm` != null, the FFN up-projection -- pre = acc + bias is NOT stored:
+// the next A operand hm = mask * gelu(pre) goes to shared memory and to `hm` (the FFN-down weight gradient reads it), and
+// gp = mask * gelu'(pre) to `gp` (the backward multiplies by it instead of recomputing erf / exp per element).
+__device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, int ldo, Dropout dh, float* hm, float* gp) {
   RowDrop rd;
   rd.init(dh, (uint32_t)me.m);
-  float* orow = out + (size_t)me.m * ldo + me.half * 64;
 #pragma unroll 1
   for (int g = 0; g < 2; ++g) {
     const int n0 = me.half * 64 + g * 32;
@@ -455,24 +455,37 @@ __device__ __noinline__ void epi_linear(Me me, const float* s_bias, float* out, 
       const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + j);
       v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
     }
-    if (me.live) {
+    if (!hm) {
+      if (me.live) {
+        float* orow = out + (size_t)me.m * ldo + me.half * 64 + g * 32;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) st_global_v8(orow + g * 32 + j, v + j);
+        for (int j = 0; j < 32; j += 8) st_global_v8(orow + j, v + j);
+      }
+      continue;
     }
-    if (gelu_stage) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        float f[16];
-        rd.factors16(n0 + q * 16, f);
+    for (int q = 0; q < 2; ++q) {
+      float f[16], d[16];
+      rd.factors16(n0 + q * 16, f);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[q * 16 + j] = gelu_f(v[q * 16 + j]) * f[j];
-        store_image16(v + q * 16, me.row, n0 + q * 16, me.smem);
+      for (int j = 0; j < 16; ++j) {
+        const float x = v[q * 16 + j];
+        const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+        const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+        v[q * 16 + j] = x * cdf * f[j];                       // mask * gelu(pre)
+        d[j] = (cdf + x * pdf) * f[j];                        // mask * gelu'(pre)
       }
-      if (me.live && hm) {
-        float* hrow = hm + (size_t)me.m * ldo + me.half * 64 + g * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) st_global_v8(hrow + j, v + j);
+      store_image16(v + q * 16, me.row, n0 + q * 16, me.smem);
+      if (me.live) {
+        float* grow = gp + (size_t)me.m * ldo + n0 + q * 16;
+        st_global_v8(grow, d);
+        st_global_v8(grow + 8, d + 8);
       }
+    }
+    if (me.live) {
+      float* hrow = hm + (size_t)me.m * ldo + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st_global_v8(hrow + j, v + j);
     }
   }
 }
@@ -795,7 +808,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
         TRACE(100 * l + 13 + ch);
         wait_acc(c);
         TRACE(100 * l + 16 + ch);
-        epi_linear(me_of(c), s_par + kParIn + ch * 128, y.qkv + ch * 128, 384, false, y.d_ffn_h, nullptr);
+        epi_linear(me_of(c), s_par + kParIn + ch * 128, y.qkv + ch * 128, 384, y.d_ffn_h, nullptr, nullptr);
         tc_fence_before();
         __syncthreads();                                      // accumulator free; qkv rows visible to the whole CTA
         tc_fence_after();
@@ -824,7 +837,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
       TRACE(100 * l + 41);
       wait_acc(c);
       TRACE(100 * l + 42);
-      epi_linear(me_of(c), s_par + kParB1, y.pre, 128, true, y.d_ffn_h, y.hm);
+      epi_linear(me_of(c), s_par + kParB1, nullptr, 128, y.d_ffn_h, y.hm, y.gp);
       sync_for_mma();
       TRACE(100 * l + 50);
       // ---- FFN down + dropout + residual + LN2 (x2 -> park and the next layer's QKV operand) ----
@@ -853,86 +866,143 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
 // =====================================================================================================================
 // Backward of the position-wise half of a layer as one persistent kernel over 128-row tiles (no sequence alignment needed):
 //   g3   = LN2'(gin; z2)                                     (dz2)
-//   dpre = ((g3 . mask_ffn_out) W2) . mask_ffn_h . gelu'(pre)
+//   dpre = ((g3 . mask_ffn_out) W2) . gp                     (gp = mask_ffn_h . gelu'(pre), saved by the fused forward)
 //   dx1  = g3 + dpre W1
 //   g1   = LN1'(dx1; z1)                                     (dz1)
 //   g2   = (g1 . mask_attn_out) Wo                           (gradient w.r.t. the attention output)
-// replacing ln_bwd + gemm_bwd_dpre + gemm_bwd_dx1 + ln_bwd + gemm_bwd_dattn on the critical path.  g3, dpre, dx1, g1 also go
-// to HBM: the weight-gradient GEMMs and the LayerNorm / bias column sums consume them on the side stream.
+// replacing ln_bwd + gemm_bwd_dpre + gemm_bwd_dx1 + ln_bwd + gemm_bwd_dattn on the critical path.  g3, dpre, g1 also go to
+// HBM (the weight-gradient GEMMs consume them on the side stream), and the LayerNorm column partials (d gamma, d beta, bias
+// gradients under the two dropouts) are accumulated here, so no separate LayerNorm-backward launch remains.
+//
+// Two thread mappings.  Everything that touches the TMEM accumulator runs row-per-thread (TMEM lane = tile row): operands of
+// those epilogues (gp, g3) are fetched with 256-bit row loads issued BEFORE the accumulator wait, so their latency hides under
+// the UMMAs.  The two LayerNorm backwards do not touch TMEM at all and run in the COALESCED mapping -- 16 lanes per row, 32
+// bytes per lane, row statistics by shuffles inside the half-warp -- which is what the first version of this kernel lacked
+// (its row-per-thread loads of gin / z2 alone were 49 K of 182 K cycles per tile).
 struct FusedBwdFfnArgs {
-  const float *gin, *z2, *st2, *pre, *z1, *st1, *gamma2, *gamma1;
+  const float *gin, *z2, *st2, *gp, *z1, *st1, *gamma2, *gamma1;
   const uint16_t *w2_hi, *w2_lo, *w1_hi, *w1_lo, *out_hi, *out_lo;   // images of W2^T, W1^T, Wo^T (backward-data operands)
   float *g3, *dpre, *dx1, *g1, *g2;
+  float *part_ln2, *part_ln1;                                       // [gridDim.x][3 * 128] column partials of the two LayerNorms
   const int32_t* counts;
   int T_cap;
-  Dropout d_ffn_out, d_ffn_h, d_attn_out;
+  Dropout d_ffn_out, d_attn_out;
 };
 
-// dz = LN'(dy; z, mu, rstd, gamma) for this thread's 64 columns; `gd` holds dy on entry.  Writes dz to `dz_out` (global) and the
-// next A operand dz . mask(dm); optionally parks dz (fp32) in TMEM columns [128,256) for a later residual add.
-__device__ __forceinline__ void ln_bwd_rows(Me me, float* gd, const float* zrows, const float* stats, const float* s_gamma, Dropout dm,
-                                         float* dz_out, bool park, float (*s_x)[128]) {
-  const float mu = me.live ? stats[2 * me.m] : 0.f, rstd = me.live ? stats[2 * me.m + 1] : 0.f;
-  const float* zrow = zrows + (size_t)me.m * 128 + me.half * 64;
-  float s1 = 0.f, s2 = 0.f;
+// dz = LN'(dy; z, stats, gamma) over the tile in the coalesced mapping (chunk = tid & 15: 8 columns, rsub = tid >> 4: one of 16
+// rows per pass).  Writes dz (global, 32 B per lane), the next A operand dz . mask(dm) as bf16 hi/lo images, and adds this
+// tile's column partials {sum dy xhat, sum dy, sum dz mask} to acc.
+// (dy may have been written by this very CTA -- dx1 -- so no pointer here is __restrict__ / read-only-path qualified)
+__device__ __forceinline__ void ln_bwd_pass(const Ctx& c, const float* dy, const float* z, const float* stats, const float* s_gamma,
+                                            const Dropout& dm, float* dz_out, float (&acc)[3][8]) {
+  const int chunk = threadIdx.x & 15, rsub = threadIdx.x >> 4, col0 = chunk * 8;
+  float gam[8];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float4 zz[4];
+  for (int j = 0; j < 8; ++j) gam[j] = s_gamma[col0 + j];
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float4 dv[4][2], zv[4][2];
+    float mu[4], rs[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) zz[j] = me.live ? *reinterpret_cast<const float4*>(zrow + g * 16 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float zv[16] = {zz[0].x, zz[0].y, zz[0].z, zz[0].w, zz[1].x, zz[1].y, zz[1].z, zz[1].w,
-                          zz[2].x, zz[2].y, zz[2].z, zz[2].w, zz[3].x, zz[3].y, zz[3].z, zz[3].w};
+    for (int it = 0; it < 4; ++it) {                            // 4 rows x (dy, z) per lane in flight
+      const int row = (half * 4 + it) * 16 + rsub;
+      if (row < c.R) {
+        const size_t o = (size_t)(c.r0 + row) * 128 + col0;
+        dv[it][0] = *reinterpret_cast<const float4*>(dy + o); dv[it][1] = *reinterpret_cast<const float4*>(dy + o + 4);
+        zv[it][0] = *reinterpret_cast<const float4*>(z + o);  zv[it][1] = *reinterpret_cast<const float4*>(z + o + 4);
+        mu[it] = stats[2 * (c.r0 + row)]; rs[it] = stats[2 * (c.r0 + row) + 1];
+      } else {
+        dv[it][0] = dv[it][1] = zv[it][0] = zv[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mu[it] = 0.f; rs[it] = 0.f;
+      }
+    }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float xh = (zv[j] - mu) * rstd;
-      gd[g * 16 + j] *= s_gamma[me.half * 64 + g * 16 + j];          // dxhat
-      s1 += gd[g * 16 + j];
-      s2 = fmaf(gd[g * 16 + j], xh, s2);
+    for (int it = 0; it < 4; ++it) {
+      const int row = (half * 4 + it) * 16 + rsub;
+      const uint32_t m = (uint32_t)(c.r0 + row);
+      const float d8[8] = {dv[it][0].x, dv[it][0].y, dv[it][0].z, dv[it][0].w, dv[it][1].x, dv[it][1].y, dv[it][1].z, dv[it][1].w};
+      const float z8[8] = {zv[it][0].x, zv[it][0].y, zv[it][0].z, zv[it][0].w, zv[it][1].x, zv[it][1].y, zv[it][1].z, zv[it][1].w};
+      float xh[8], gd[8], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[j] = (z8[j] - mu[it]) * rs[it];
+        acc[0][j] = fmaf(d8[j], xh[j], acc[0][j]);
+        acc[1][j] += d8[j];
+        gd[j] = d8[j] * gam[j];                                  // d xhat
+        s1 += gd[j];
+        s2 = fmaf(gd[j], xh[j], s2);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {                          // the 16 lanes of a row are one half-warp
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      s1 *= (1.0f / 128.0f); s2 *= (1.0f / 128.0f);
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = rs[it] * (gd[j] - s1 - xh[j] * s2);
+      if (row < c.R) {
+        float* o = dz_out + (size_t)m * 128 + col0;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      // dropout factors of elements m * 128 + col0 .. + 7: pairs m * 64 + col0 / 2 .. + 3 (draw32 with its row half hoisted)
+      if (dm.thresh != 0u) {
+        const uint32_t rk = mix32(dm.key ^ (m >> 1)), pb = m * 64u + (uint32_t)(col0 >> 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t hsh = mix32((pb + (uint32_t)q) * 0x9E3779B1u + dm.key) ^ rk;
+          v[2 * q] = (hsh & 0xFFFFu) >= dm.thresh ? v[2 * q] * dm.scale : 0.f;
+          v[2 * q + 1] = (hsh >> 16) >= dm.thresh ? v[2 * q + 1] * dm.scale : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[2][j] += v[j];              // rows >= R contribute exact zeros (rs = 0)
+      uint4 hi, lo;
+      split8(v, hi, lo);
+      const uint32_t off = (uint32_t)(chunk >> 3) * kImg + sw128_offset((uint32_t)row, (uint32_t)((chunk & 7) * 8));
+      *reinterpret_cast<uint4*>(c.smem + off) = hi;
+      *reinterpret_cast<uint4*>(c.smem + 2 * kImg + off) = lo;
     }
   }
-  s_x[me.half][me.row] = s1;
-  __syncthreads();
-  s1 = (s_x[0][me.row] + s_x[1][me.row]) * (1.0f / 128.0f);
-  __syncthreads();
-  s_x[me.half][me.row] = s2;
-  __syncthreads();
-  s2 = (s_x[0][me.row] + s_x[1][me.row]) * (1.0f / 128.0f);
-  RowDrop rd;
-  rd.init(dm, (uint32_t)me.m);
-  float* orow = dz_out + (size_t)me.m * 128 + me.half * 64;
+}
+
+// acc (this thread's 8 columns over its rows) summed over the 16 row groups of the CTA in a fixed order and ADDED to
+// s_part[3][128] (single writer per element)
+__device__ __forceinline__ void fold_partials(float (&acc)[3][8], float (*s_red)[3][128], float (*s_part)[128]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, chunk = tid & 15;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int n0 = me.half * 64 + g * 16;
-    float4 zz[4];
+  for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) zz[j] = me.live ? *reinterpret_cast<const float4*>(zrow + g * 16 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float zv[16] = {zz[0].x, zz[0].y, zz[0].z, zz[0].w, zz[1].x, zz[1].y, zz[1].z, zz[1].w,
-                          zz[2].x, zz[2].y, zz[2].z, zz[2].w, zz[3].x, zz[3].y, zz[3].z, zz[3].w};
-    float v[16], f[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = rstd * (gd[g * 16 + j] - s1 - (zv[j] - mu) * rstd * s2);
-    if (me.live) {
-      st_global_v8(orow + g * 16, v);
-      st_global_v8(orow + g * 16 + 8, v + 8);
+    for (int j = 0; j < 8; ++j) {
+      const float v = acc[k][j] + __shfl_xor_sync(0xffffffffu, acc[k][j], 16);     // the two row groups of the warp
+      if (lane < 16) s_red[warp][k][chunk * 8 + j] = v;
+      acc[k][j] = 0.f;
     }
-    if (park) tmem_st16(me.trow + kPark + (uint32_t)(g * 16), v);
-    rd.factors16(n0, f);
+  __syncthreads();
+  for (int e = tid; e < 384; e += kFT) {
+    const int k = e >> 7, col = e & 127;
+    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] *= f[j];
-    store_image16(v, me.row, n0, me.smem);
+    for (int w = 0; w < 8; ++w) sum += s_red[w][k][col];
+    s_part[k][col] += sum;
   }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __grid_constant__ FusedBwdFfnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[5];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_x[2][128];
   __shared__ __align__(16) float s_gam[256];               // gamma2, gamma1
+  __shared__ float s_part2[3][128], s_part1[3][128];       // this CTA's column partials (all its tiles)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = min(a.T_cap, *a.counts);
   const int n_tiles = (T + 127) / 128;
-  if ((int)blockIdx.x >= n_tiles) return;
+  if ((int)blockIdx.x >= n_tiles) {                        // no tile: this CTA's partials are zero
+    for (int e = tid; e < 384; e += kFT) { a.part_ln2[(size_t)blockIdx.x * 384 + e] = 0.f; a.part_ln1[(size_t)blockIdx.x * 384 + e] = 0.f; }
+    return;
+  }
 
   Ctx c;
   c.smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -948,6 +1018,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   s_gam[tid] = tid < 128 ? a.gamma2[tid] : a.gamma1[tid - 128];
+  for (int e = tid; e < 384; e += kFT) { (&s_part2[0][0])[e] = 0.f; (&s_part1[0][0])[e] = 0.f; }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -955,6 +1026,11 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
   c.row = (warp & 3) * 32 + lane;
   c.half = warp >> 2;
   c.trow = c.tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c.half * 64);
+  float acc[3][8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
 
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -964,79 +1040,81 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
     c.m = c.r0 + c.row;
     TRACE(1);
     if (tid == kProducer) prefetch_chunk(c, a.w2_hi, a.w2_lo, 128, 0);   // no-op when the previous tile already queued them
-    // ---- g3 = LN2'(gin) -> HBM, park, A operand (g3 . mask_ffn_out) ----
-    {
-      float gd[64];
-      const float* grow = a.gin + (size_t)c.m * 128 + c.half * 64;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float4 v = c.live ? *reinterpret_cast<const float4*>(grow + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        gd[4 * j] = v.x; gd[4 * j + 1] = v.y; gd[4 * j + 2] = v.z; gd[4 * j + 3] = v.w;
-      }
-      ln_bwd_rows(me_of(c), gd, a.z2, a.st2, s_gam, a.d_ffn_out, a.g3, true, s_x);
-    }
+    // ---- g3 = LN2'(gin) -> HBM and the A operand (g3 . mask_ffn_out) ----
+    ln_bwd_pass(c, a.gin, a.z2, a.st2, s_gam, a.d_ffn_out, a.g3, acc);
     TRACE(2);
     sync_for_mma();
     TRACE(3);
-    // ---- dpre = (A W2) . mask_ffn_h . gelu'(pre) -> HBM and the next A operand ----
-    run_chunk(c, a.w2_hi, a.w2_lo, 128, 0, a.w1_hi, a.w1_lo, 128, 0);
-    TRACE(4);
-    wait_acc(c);
-    TRACE(5);
+    // ---- dpre = (A W2) . gp -> HBM and the next A operand ----
     {
-      RowDrop rd;
-      rd.init(a.d_ffn_h, (uint32_t)c.m);
-      const float* prow = a.pre + (size_t)c.m * 128 + c.half * 64;
+      float gpv[64];                                        // this thread's 64 gp values: in flight under the UMMAs
+      const float* prow = a.gp + (size_t)c.m * 128 + c.half * 64;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c.live) ld_global_v8(prow + 8 * j, gpv + 8 * j);
+        else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) gpv[8 * j + q] = 0.f;
+        }
+      }
+      run_chunk(c, a.w2_hi, a.w2_lo, 128, 0, a.w1_hi, a.w1_lo, 128, 0);
+      TRACE(4);
+      wait_acc(c);
+      TRACE(5);
+      // LN2 column partials; the staging buffer is the A-image region, dead between the accumulator wait and the stores below
+      fold_partials(acc, reinterpret_cast<float (*)[3][128]>(c.smem), s_part2);
       float* orow = a.dpre + (size_t)c.m * 128 + c.half * 64;
-#pragma unroll 1
+#pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int n0 = c.half * 64 + g * 16;
-        float v[16], f[16];
-        float4 pp[4];
+        float v[16];
+        tmem_ld16(c.trow + (uint32_t)(g * 16), v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) pp[j] = c.live ? *reinterpret_cast<const float4*>(prow + g * 16 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        tmem_ld16_nowait(c.trow + (uint32_t)(g * 16), v);
-        rd.factors16(n0, f);
-        tmem_ld_fence(v, true);
-        const float pv[16] = {pp[0].x, pp[0].y, pp[0].z, pp[0].w, pp[1].x, pp[1].y, pp[1].z, pp[1].w,
-                              pp[2].x, pp[2].y, pp[2].z, pp[2].w, pp[3].x, pp[3].y, pp[3].z, pp[3].w};
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= f[j] * gelu_grad_f(pv[j]);
+        for (int j = 0; j < 16; ++j) v[j] *= gpv[g * 16 + j];
         if (c.live) {
           st_global_v8(orow + g * 16, v);
           st_global_v8(orow + g * 16 + 8, v + 8);
         }
-        store_image16(v, c.row, n0, c.smem);
+        store_image16(v, c.row, c.half * 64 + g * 16, c.smem);
       }
     }
     TRACE(6);
     sync_for_mma();
     TRACE(7);
-    // ---- dx1 = g3 + A W1 -> HBM ; g1 = LN1'(dx1) -> HBM and the next A operand (g1 . mask_attn_out) ----
-    run_chunk(c, a.w1_hi, a.w1_lo, 128, 0, a.out_hi, a.out_lo, 128, 0);
-    TRACE(8);
-    wait_acc(c);
-    TRACE(9);
+    // ---- dx1 = g3 + A W1 -> HBM ----
     {
-      float gd[64];
+      float rv[64];                                         // g3 rows (written above by this CTA; L2 hits), in flight under the UMMAs
+      const float* rrow = a.g3 + (size_t)c.m * 128 + c.half * 64;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c.live) ld_global_v8(rrow + 8 * j, rv + 8 * j);
+        else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) rv[8 * j + q] = 0.f;
+        }
+      }
+      run_chunk(c, a.w1_hi, a.w1_lo, 128, 0, a.out_hi, a.out_lo, 128, 0);
+      TRACE(8);
+      wait_acc(c);
+      TRACE(9);
       float* xrow = a.dx1 + (size_t)c.m * 128 + c.half * 64;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float r[16];
-        tmem_ld16_nowait(c.trow + (uint32_t)(g * 16), gd + g * 16);
-        tmem_ld16_nowait(c.trow + kPark + (uint32_t)(g * 16), r);
-        tmem_ld_fence(gd + g * 16, true);
-        tmem_ld_fence(r, false);
+        float v[16];
+        tmem_ld16(c.trow + (uint32_t)(g * 16), v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) gd[g * 16 + j] += r[j];
+        for (int j = 0; j < 16; ++j) v[j] += rv[g * 16 + j];
         if (c.live) {
-          st_global_v8(xrow + g * 16, gd + g * 16);
-          st_global_v8(xrow + g * 16 + 8, gd + g * 16 + 8);
+          st_global_v8(xrow + g * 16, v);
+          st_global_v8(xrow + g * 16 + 8, v + 8);
         }
       }
-      TRACE(10);
-      ln_bwd_rows(me_of(c), gd, a.z1, a.st1, s_gam + 128, a.d_attn_out, a.g1, false, s_x);
     }
+    tc_fence_before();
+    __syncthreads();                                        // dx1 rows of the tile are visible to the whole CTA; A images are free
+    tc_fence_after();
+    TRACE(10);
+    // ---- g1 = LN1'(dx1) -> HBM and the next A operand (g1 . mask_attn_out) ----
+    ln_bwd_pass(c, a.dx1, a.z1, a.st1, s_gam + 128, a.d_attn_out, a.g1, acc);
     TRACE(11);
     sync_for_mma();
     TRACE(12);
@@ -1046,6 +1124,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
     TRACE(13);
     wait_acc(c);
     TRACE(14);
+    fold_partials(acc, reinterpret_cast<float (*)[3][128]>(c.smem), s_part1);     // LN1 column partials (A images are dead again)
     {
       float* orow = a.g2 + (size_t)c.m * 128 + c.half * 64;
 #pragma unroll 1
@@ -1065,6 +1144,10 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_bwd_ffn_fused_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+  }
+  for (int e = tid; e < 384; e += kFT) {
+    a.part_ln2[(size_t)blockIdx.x * 384 + e] = (&s_part2[0][0])[e];
+    a.part_ln1[(size_t)blockIdx.x * 384 + e] = (&s_part1[0][0])[e];
   }
   tc_fence_before();
   __syncthreads();
@@ -1121,7 +1204,7 @@ int launch_sasrec_fwd_fused(const FusedFwdHost& h, cudaStream_t st) {
   for (int l = 0; l < h.n_layer; ++l) {
     const FusedLayerHost& s = h.layer[l];
     FusedLayer& d = a.layer[l];
-    d.qkv = s.qkv; d.attn = s.attn; d.z1 = s.z1; d.st1 = s.st1; d.x1 = s.x1; d.pre = s.pre; d.hm = s.hm; d.z2 = s.z2; d.st2 = s.st2; d.x2 = s.x2;
+    d.qkv = s.qkv; d.attn = s.attn; d.z1 = s.z1; d.st1 = s.st1; d.x1 = s.x1; d.hm = s.hm; d.gp = s.gp; d.z2 = s.z2; d.st2 = s.st2; d.x2 = s.x2;
     d.in_hi = s.img[0]; d.in_lo = s.img[1]; d.out_hi = s.img[2]; d.out_lo = s.img[3];
     d.w1_hi = s.img[4]; d.w1_lo = s.img[5]; d.w2_hi = s.img[6]; d.w2_lo = s.img[7];
     d.in_b = s.in_b; d.out_b = s.out_b; d.b1 = s.b1; d.b2 = s.b2; d.g1 = s.g1; d.be1 = s.be1; d.g2 = s.g2; d.be2 = s.be2;
@@ -1142,18 +1225,18 @@ int launch_sasrec_fwd_fused(const FusedFwdHost& h, cudaStream_t st) {
 
 int launch_sasrec_bwd_ffn_fused(const FusedBwdFfnHost& h, cudaStream_t st) {
   FusedBwdFfnArgs a{};
-  a.gin = h.gin; a.z2 = h.z2; a.st2 = h.st2; a.pre = h.pre; a.z1 = h.z1; a.st1 = h.st1; a.gamma2 = h.gamma2; a.gamma1 = h.gamma1;
+  a.gin = h.gin; a.z2 = h.z2; a.st2 = h.st2; a.gp = h.gp; a.z1 = h.z1; a.st1 = h.st1; a.gamma2 = h.gamma2; a.gamma1 = h.gamma1;
   a.w2_hi = h.img[0]; a.w2_lo = h.img[1]; a.w1_hi = h.img[2]; a.w1_lo = h.img[3]; a.out_hi = h.img[4]; a.out_lo = h.img[5];
-  a.g3 = h.g3; a.dpre = h.dpre; a.dx1 = h.dx1; a.g1 = h.g1; a.g2 = h.g2; a.counts = h.counts; a.T_cap = h.T_cap;
-  a.d_ffn_out = h.d_ffn_out; a.d_ffn_h = h.d_ffn_h; a.d_attn_out = h.d_attn_out;
+  a.g3 = h.g3; a.dpre = h.dpre; a.dx1 = h.dx1; a.g1 = h.g1; a.g2 = h.g2; a.part_ln2 = h.part_ln2; a.part_ln1 = h.part_ln1;
+  a.counts = h.counts; a.T_cap = h.T_cap;
+  a.d_ffn_out = h.d_ffn_out; a.d_attn_out = h.d_attn_out;
   ProfScope prof("sasrec_bwd_ffn_fused", st);
   if (cudaFuncSetAttribute(sasrec_bwd_ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem) != cudaSuccess) {
     set_cuda_error(cudaGetLastError(), "sasrec_bwd_ffn_fused smem attribute");
     return DR4SR_ECUDA;
   }
-  const int tiles = ceil_div(h.T_cap, 128);
-  const int grid = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;
-  sasrec_bwd_ffn_fused_kernel<<<grid, kFT, kFusedSmem, st>>>(a);
+  // the grid is fixed (kLnBwdBlocks = 2 CTAs per SM): every CTA writes its slice of the LayerNorm partials, tiles are strided
+  sasrec_bwd_ffn_fused_kernel<<<kLnBwdBlocks, kFT, kFusedSmem, st>>>(a);
   DR4SR_LAUNCH_CHECK("sasrec_bwd_ffn_fused_kernel");
   return DR4SR_OK;
 }

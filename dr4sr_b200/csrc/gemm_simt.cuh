@@ -35,6 +35,7 @@ struct GemmArgs {
   const float* add;       // [M, ldadd] or null
   int ldadd;
   const float* pre;       // EPI_GELU_BWD: pre-activation [M, ldc]
+  const float* mul;       // EPI_GELU_BWD, tcgen05 kernel only: saved dropout-mask * gelu'(pre) [M, ldc] (replaces pre / dropE when set)
   Dropout dropE;          // EPI_GELU_BWD / LN epilogue dropout stream (index = m * N + n)
   // LN epilogue (GemmLN kernel only): z = drop(acc + bias) + add ; y = LN(z)
   const float* gamma; const float* beta; float ln_eps;

@@ -345,14 +345,20 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(TcArgs t) {
         float o[8] = {v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]};
         if (EPI == TC_GELU_BWD) {
           float p[8];
-          if (wide) ld_global_v8(g.pre + (size_t)m * g.ldc + n, p);
+          const float* src = g.mul ? g.mul : g.pre;
+          if (wide) ld_global_v8(src + (size_t)m * g.ldc + n, p);
           else {
-            const float4 p0 = *reinterpret_cast<const float4*>(g.pre + (size_t)m * g.ldc + n), p1 = *reinterpret_cast<const float4*>(g.pre + (size_t)m * g.ldc + n + 4);
+            const float4 p0 = *reinterpret_cast<const float4*>(src + (size_t)m * g.ldc + n), p1 = *reinterpret_cast<const float4*>(src + (size_t)m * g.ldc + n + 4);
             p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
           }
-          const float4 f0 = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n), f1 = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n + 4);
-          o[0] *= f0.x * gelu_grad_f(p[0]); o[1] *= f0.y * gelu_grad_f(p[1]); o[2] *= f0.z * gelu_grad_f(p[2]); o[3] *= f0.w * gelu_grad_f(p[3]);
-          o[4] *= f1.x * gelu_grad_f(p[4]); o[5] *= f1.y * gelu_grad_f(p[5]); o[6] *= f1.z * gelu_grad_f(p[6]); o[7] *= f1.w * gelu_grad_f(p[7]);
+          if (g.mul) {        // the forward saved mask * gelu'(pre)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] *= p[q];
+          } else {
+            const float4 f0 = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n), f1 = g.dropE.factor4((uint32_t)m * (uint32_t)g.ldc + n + 4);
+            o[0] *= f0.x * gelu_grad_f(p[0]); o[1] *= f0.y * gelu_grad_f(p[1]); o[2] *= f0.z * gelu_grad_f(p[2]); o[3] *= f0.w * gelu_grad_f(p[3]);
+            o[4] *= f1.x * gelu_grad_f(p[4]); o[5] *= f1.y * gelu_grad_f(p[5]); o[6] *= f1.z * gelu_grad_f(p[6]); o[7] *= f1.w * gelu_grad_f(p[7]);
+          }
         } else {
           if (g.bias) {
             const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n), b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);

@@ -4,6 +4,8 @@
 
 namespace dr4sr {
 
+constexpr int kLnBwdBlocks = 2 * kNumSMs;   // CTAs (= column-partial slices) of the LayerNorm backward kernels
+
 // attention over packed rows, one CTA per (sequence, head)  [attention.cu]
 int launch_attn_fwd(const float* qkv, const int64_t* in_ids, const int32_t* tok_off, float* out, int B, int L, int D,
                     int n_head, Dropout drop, cudaStream_t st);
@@ -25,7 +27,7 @@ int launch_attn_bwd_tc2(const float* qkv, const float* d_out, const int64_t* in_
 
 // whole-encoder forward as one persistent tcgen05 kernel (D = F = 128, 2 heads)  [fused_fwd.cu]
 struct FusedLayerHost {
-  float *qkv, *attn, *z1, *st1, *x1, *pre, *hm, *z2, *st2, *x2;   // hm (optional) = dropout(gelu(pre)), kept for the FFN-down weight gradient
+  float *qkv, *attn, *z1, *st1, *x1, *hm, *gp, *z2, *st2, *x2;   // hm = mask * gelu(pre), gp = mask * gelu'(pre) (pre itself is not kept)
   const uint16_t* img[8];   // in_hi, in_lo, out_hi, out_lo, w1_hi, w1_lo, w2_hi, w2_lo (forward weight images)
   const float *in_b, *out_b, *b1, *b2, *g1, *be1, *g2, *be2;
   Dropout d_attn_p, d_attn_out, d_ffn_h, d_ffn_out;
@@ -47,19 +49,19 @@ int fused_fwd_set_trace(int* host_mapped);
 int attn_bwd_set_trace(int* host_mapped);
 // backward of the position-wise half of a layer (LN2', dpre, dx1, LN1', d(attn)) as one persistent kernel  [fused_fwd.cu]
 struct FusedBwdFfnHost {
-  const float *gin, *z2, *st2, *pre, *z1, *st1, *gamma2, *gamma1;
+  const float *gin, *z2, *st2, *gp, *z1, *st1, *gamma2, *gamma1;   // gp = mask_ffn_h * gelu'(pre) from the fused forward
   const uint16_t* img[6];   // W2^T hi, lo, W1^T hi, lo, Wo^T hi, lo (backward-data weight images)
   float *g3, *dpre, *dx1, *g1, *g2;
+  float *part_ln2, *part_ln1;   // [kLnBwdBlocks][3 * 128]: {sum dy xhat, sum dy, sum dz mask} column partials of LN2 / LN1
   const int32_t* counts;
   int T_cap;
-  Dropout d_ffn_out, d_ffn_h, d_attn_out;
+  Dropout d_ffn_out, d_attn_out;
 };
 int launch_sasrec_bwd_ffn_fused(const FusedBwdFfnHost& h, cudaStream_t st);
 
 // LayerNorm backward over packed rows + column partials  [rowops.cu]
 //   dz = LN'(dy; z, stats, gamma);  partials[blk][0..D) = sum dy*xhat, [D..2D) = sum dy,
 //   [2D..3D) = sum dz * bias_drop.factor (gradient of the bias that sits under the dropout before this LN)
-constexpr int kLnBwdBlocks = 2 * kNumSMs;
 int launch_ln_bwd(const float* dy, const float* z, const float* stats, const float* gamma, float* dz, float* partials,
                   int D, int T_cap, const int32_t* tok_dev, Dropout bias_drop, cudaStream_t st,
                   Dropout dy_drop = Dropout{0u, 0u, 1.0f});

@@ -35,7 +35,8 @@ LayerOffsets layer_offsets(int D, int F) {
 struct Workspace {
   // saved activations
   float* x0;
-  struct Layer { float *qkv, *attn, *z1, *st1, *x1, *pre, *hm, *z2, *st2, *x2; } layer[8];   // hm = dropout(gelu(pre)) (fused forward only)
+  // fused forward: hm = mask * gelu(pre), gp = mask * gelu'(pre) instead of pre; per-operator forward: pre
+  struct Layer { float *qkv, *attn, *z1, *st1, *x1, *pre, *hm, *gp, *z2, *st2, *x2; } layer[8];
   // backward scratch.  g0 / g2 belong to the data-gradient chain; everything in `Bwd` is per layer because the
   // weight-gradient work of layer l runs on a side stream while the main stream already works on layer l-1
   float *g0, *g2;
@@ -66,7 +67,8 @@ Workspace carve(const dr4sr_sasrec_cfg& c, void* base) {
   for (int l = 0; l < c.n_layer; ++l) {
     auto& y = w.layer[l];
     y.qkv = take(T * 3 * D); y.attn = take(T * D); y.z1 = take(T * D); y.st1 = take(T * 2); y.x1 = take(T * D);
-    y.pre = take(T * F); y.hm = take(T * F); y.z2 = take(T * D); y.st2 = take(T * 2); y.x2 = take(T * D);
+    y.pre = take(T * F); y.hm = take(T * F); y.gp = y.pre;   // gp and pre never coexist (fused vs per-operator forward)
+    y.z2 = take(T * D); y.st2 = take(T * 2); y.x2 = take(T * D);
   }
   w.g0 = take(T * D); w.g2 = take(T * D);
   for (int l = 0; l < c.n_layer; ++l) {
@@ -261,7 +263,7 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
       auto& y = w.layer[l];
       const auto& m = w.img[l];
       FusedLayerHost& d = h.layer[l];
-      d.qkv = y.qkv; d.attn = y.attn; d.z1 = y.z1; d.st1 = y.st1; d.x1 = y.x1; d.pre = y.pre; d.hm = y.hm; d.z2 = y.z2; d.st2 = y.st2;
+      d.qkv = y.qkv; d.attn = y.attn; d.z1 = y.z1; d.st1 = y.st1; d.x1 = y.x1; d.hm = y.hm; d.gp = y.gp; d.z2 = y.z2; d.st2 = y.st2;
       d.x2 = (l == c->n_layer - 1 && q_packed) ? q_packed : y.x2;
       d.img[0] = m.in_f.hi; d.img[1] = m.in_f.lo; d.img[2] = m.out_f.hi; d.img[3] = m.out_f.lo;
       d.img[4] = m.w1_f.hi; d.img[5] = m.w1_f.lo; d.img[6] = m.w2_f.hi; d.img[7] = m.w2_f.lo;
@@ -369,32 +371,14 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
     if (fused_bwd_enabled() && fused_fwd_supported(c->L, D, F, c->n_head)) {
       // ---- position-wise half of the layer as one persistent kernel (main stream) ----
       FusedBwdFfnHost h{};
-      h.gin = gin; h.z2 = y.z2; h.st2 = y.st2; h.pre = y.pre; h.z1 = y.z1; h.st1 = y.st1; h.gamma2 = lp + lo.g2; h.gamma1 = lp + lo.g1;
+      h.gin = gin; h.z2 = y.z2; h.st2 = y.st2; h.gp = y.gp; h.z1 = y.z1; h.st1 = y.st1; h.gamma2 = lp + lo.g2; h.gamma1 = lp + lo.g1;
       h.img[0] = w.img[l].w2_b.hi; h.img[1] = w.img[l].w2_b.lo; h.img[2] = w.img[l].w1_b.hi; h.img[3] = w.img[l].w1_b.lo;
       h.img[4] = w.img[l].out_b.hi; h.img[5] = w.img[l].out_b.lo;
-      h.g3 = s.g3; h.dpre = s.dpre; h.dx1 = s.dx1; h.g1 = s.g1; h.g2 = w.g2; h.counts = counts; h.T_cap = T;
-      h.d_ffn_out = d_ffn_out; h.d_ffn_h = d_ffn_h; h.d_attn_out = d_attn_out;
+      h.g3 = s.g3; h.dpre = s.dpre; h.dx1 = s.dx1; h.g1 = s.g1; h.g2 = w.g2; h.part_ln2 = s.part_ln2; h.part_ln1 = s.part_ln1;
+      h.counts = counts; h.T_cap = T;
+      h.d_ffn_out = d_ffn_out; h.d_attn_out = d_attn_out;
       DR4SR_TRY(launch_sasrec_bwd_ffn_fused(h, st));
       const Dropout none = no_dropout();
-      if (side.ok) {   // dz2, dpre, dx1, dz1 are final: everything that does not need dqkv starts now (side stream)
-        if (cudaEventRecord(side.fork[2 * l], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[2 * l], 0) != cudaSuccess) {
-          set_cuda_error(cudaGetLastError(), "backward fork");
-          return DR4SR_ECUDA;
-        }
-      }
-      // LayerNorm affine / bias column sums (partials only: dz = null), bias-1 column sums, three weight gradients
-      DR4SR_TRY(launch_ln_bwd(gin, y.z2, y.st2, lp + lo.g2, nullptr, s.part_ln2, D, T, counts, d_ffn_out, sw));
-      DR4SR_TRY(launch_ln_bwd(s.dx1, y.z1, y.st1, lp + lo.g1, nullptr, s.part_ln1, D, T, counts, d_attn_out, sw));
-      DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
-      {
-        tc::WgradTable tab{};
-        tab.job[0] = have_hm ? tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.hm, F, PRO_NONE, none, D, F, s.part_w + pw_w2, 0}
-                             : tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.pre, F, PRO_GELU_DROP, d_ffn_h, D, F, s.part_w + pw_w2, 0};
-        tab.job[1] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
-        tab.job[2] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
-        tab.count = 3; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
-        DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
-      }
       if (attn_bwd_tc2_enabled() && attn_tc_supported(c->L, D, c->n_head) && D == 128 && c->n_head == 2)
         DR4SR_TRY(launch_attn_bwd_tc2(y.qkv, w.g2, in_item_id, tok_off, row_seq, w.fused_tiles, fused_tiles_cap(c->B, c->L), s.dqkv, c->B,
                                       c->L, D, c->n_head, d_attn_p, st));
@@ -403,11 +387,20 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
                                      d_attn_p, st));
       else
         DR4SR_TRY(launch_attn_bwd(y.qkv, w.g2, in_item_id, tok_off, s.dqkv, c->B, c->L, D, c->n_head, d_attn_p, st));
-      if (side.ok) {
+      if (side.ok) {   // g3, dpre, g1 and dqkv are final: every weight gradient of the layer runs behind the attention backward
         if (cudaEventRecord(side.fork[2 * l + 1], st) != cudaSuccess || cudaStreamWaitEvent(sw, side.fork[2 * l + 1], 0) != cudaSuccess) {
           set_cuda_error(cudaGetLastError(), "backward fork");
           return DR4SR_ECUDA;
         }
+      }
+      DR4SR_TRY(launch_colsum(s.dpre, F, T, counts, s.part_cs_b1, sw));
+      {
+        tc::WgradTable tab{};
+        tab.job[0] = tc::WgradJob{s.g3, D, PRO_DROPMASK, d_ffn_out, y.hm, F, PRO_NONE, none, D, F, s.part_w + pw_w2, 0};
+        tab.job[1] = tc::WgradJob{s.dpre, F, PRO_NONE, none, y.x1, D, PRO_NONE, none, F, D, s.part_w + pw_w1, 0};
+        tab.job[2] = tc::WgradJob{s.g1, D, PRO_DROPMASK, d_attn_out, y.attn, D, PRO_NONE, none, D, D, s.part_w + pw_out, 0};
+        tab.count = 3; tab.T_cap = T; tab.tok_dev = counts; tab.n_split = kSplit;
+        DR4SR_TRY(tc::launch_wgrad_tc(tab, sw));
       }
       {  // dx = dz1 + dqkv Win  (layer 0: times the embedding-dropout mask) -> this layer's own output buffer / dx0
         float* dst = l == 0 ? dx0_packed : s.gout;
@@ -435,6 +428,7 @@ static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const 
       GemmArgs g = gemm_args(s.g3, D, lp + lo.w2, F, s.dpre, F, T, F, D, counts);
       g.proA = PRO_DROPMASK; g.dropA = d_ffn_out;
       g.epi = EPI_GELU_BWD; g.pre = y.pre; g.dropE = d_ffn_h; g.tag = "gemm_bwd_dpre";
+      if (have_hm) { g.pre = nullptr; g.mul = y.gp; }       // the fused forward saved mask * gelu'(pre) instead of pre
       DR4SR_TRY(gemm_nn(g, w.img[l].w2_b, st));
     }
     {  // dx1 = dz2 + dpre W1   -> g0

@@ -110,11 +110,11 @@ DR4SR_API int dr4sr_set_gemm_backend(int backend);
  * backward over the fused forward's greedy tiles (csrc/attention_bwd_tc.cu; D = 128, 2 heads -- other shapes fall back to
  * the FFMA kernels), forward as in 0 when the per-operator schedule runs.  All are parity-tested. */
 DR4SR_API int dr4sr_set_attn_backend(int backend);
-/* Encoder schedule: 1 (default) = persistent fused forward (one CTA carries a group of whole sequences, <= 128
- * packed rows, through every layer: gather, QKV, attention, out-proj+LN, FFN+LN on tcgen05) where the shape allows
- * (D = F = 128, 2 heads); 0 = one kernel per operator; 2 = 1 plus the backward of each layer's position-wise half
- * (LN2', dpre, dx1, LN1', d(attn)) as one persistent kernel per layer, with the LayerNorm / bias column sums on the
- * side stream (correct, not faster today: DESIGN.md 4a).  All three are parity-tested. */
+/* Encoder schedule: 2 (default) = persistent fused forward (one CTA carries a group of whole sequences, <= 128 packed rows,
+ * through every layer: gather, QKV, attention, out-proj+LN, FFN+LN on tcgen05) plus, in the backward, the position-wise
+ * half of each layer (LN2', dpre, dx1, LN1', d(attn) and the LayerNorm / bias column partials) as one persistent kernel per
+ * layer, where the shape allows (D = F = 128, 2 heads); 1 = fused forward, one kernel per operator in the backward;
+ * 0 = one kernel per operator everywhere.  All three are parity-tested. */
 DR4SR_API int dr4sr_set_fused_backend(int backend);
 /* The tiling the fused kernels run on: greedy groups of whole sequences with <= 128 packed rows (no sequence is split,
  * so attention never leaves a tile).  tiles[0] = n_tiles, tiles[1 + k] = first sequence of tile k, tiles[1 + n_tiles] = B;

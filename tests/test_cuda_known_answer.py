@@ -74,8 +74,10 @@ def test_shipped_checkpoint_known_answer_on_cuda(name):
     print(f'   near-tie swaps: {bad_rows} users, largest score gap between swapped ids {worst_gap:.3e} (max |score| {smax:.2f})')
     assert bad_rows <= max(2, n // 2000), f'{bad_rows} users whose top-20 ids differ from the reference'
     assert worst_gap <= 4e-6 * smax, f'ids differ across a score gap of {worst_gap:.3e}: not a round-off tie'
-    assert abs(ndcg - float(fx['metric']['ndcg@20'])) < 5e-7
-    assert abs(recall - float(fx['metric']['recall@20'])) < 5e-7
+    # the stored metrics to 5e-7, plus at most one rank position per user whose ids differ across a round-off tie
+    slack = 5e-7 + bad_rows / n
+    assert abs(ndcg - float(fx['metric']['ndcg@20'])) < slack
+    assert abs(recall - float(fx['metric']['recall@20'])) < slack
 
 
 def test_checkpoint_roundtrip_keys_and_save(tmp_path):

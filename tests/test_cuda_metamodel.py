@@ -119,7 +119,7 @@ def test_meta_inner_step_matches_reference_golden(name, backend):
                 worst = max(worst, (k, e), key=lambda t: t[1])
         mworst = max(rel_err(p.grad.cpu(), fx['inner_meta_grad'][k]) for k, p in m.meta_module.named_parameters())
         print(f'[{name} {backend}] inner loss rel err {lerr:.2e}; worst sub-model grad {worst[0]} {worst[1]:.2e}; meta grad {mworst:.2e}')
-        tol = 2e-5 if backend == 'ffma' or fx['param']['item_embedding.weight'].shape[1] == 64 else 3e-4
+        tol = 1.5e-5 if backend == 'ffma' or fx['param']['item_embedding.weight'].shape[1] == 64 else 2e-5    # measured 4.0e-6 / 5.0e-6
         assert lerr < 1e-5
         assert worst[1] < tol, worst
         assert mworst < tol
@@ -142,6 +142,6 @@ def test_meta_outer_step_matches_reference_golden(name):
     errs = {k: rel_err(g.cpu(), fx['outer_hypergrad'][k]) for (k, _), g in zip(m.meta_module.named_parameters(), grads)}
     perr = {k: rel_err(v.cpu(), fx['meta_after'][k]) for k, v in m.meta_module.state_dict().items()}
     print(f'[{name}] hypergradient rel err {errs}; meta params after the step {perr}')
-    assert max(errs.values()) < 1e-3, errs
-    assert max(perr.values()) < 1e-5, perr
+    assert max(errs.values()) < 1e-5, errs          # measured 1.1e-6
+    assert max(perr.values()) < 1e-6, perr          # measured 1.5e-8
     assert torch.equal(sub_before, m.sub_model._flat)         # the outer step never touches the sub-model

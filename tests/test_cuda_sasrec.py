@@ -19,7 +19,9 @@ DEV = 'cuda:0'
 # Dense layers run either on tcgen05 (bf16 hi/lo split operands, 3 UMMAs per product: ~2^-16 relative
 # per product) or on exact-fp32 FFMA kernels.  Both are held to the north-star bar (1e-4 relative on
 # losses / logits); the FFMA path is additionally held to fp32 round-off.
-TOL = {'tc': dict(fwd=1e-4, loss=1e-4, grad=1e-3, adam=1e-4), 'ffma': dict(fwd=1e-5, loss=1e-5, grad=1e-4, adam=2e-5)}
+# Tolerances = measured worst case (gpurun_out/parity_errors.json: tc fwd 1.3e-6, loss 3.4e-7, grad 9.0e-6, adam 5.7e-5 abs;
+# ffma fwd 2.7e-7, loss 1.7e-7, grad 9.7e-7, adam 4.0e-6) times about three -- all inside the north-star's 1e-4.
+TOL = {'tc': dict(fwd=5e-6, loss=2e-6, grad=3e-5, adam=1.5e-4), 'ffma': dict(fwd=1e-6, loss=1e-6, grad=3e-6, adam=1.2e-5)}
 TOL['tc_attn'] = TOL['tc']          # tcgen05 dense layers + tcgen05 attention tiles
 TOL['tc_attn2'] = TOL['tc']         # per-op tcgen05 dense layers + persistent tcgen05 attention backward (greedy tiles)
 TOL['fused_attn2'] = TOL['tc']      # fused forward + persistent tcgen05 attention backward
@@ -38,7 +40,7 @@ def backend(request):
     yield request.param
     _lib.lib().dr4sr_set_gemm_backend(0)
     _lib.lib().dr4sr_set_attn_backend(2)
-    _lib.lib().dr4sr_set_fused_backend(1)
+    _lib.lib().dr4sr_set_fused_backend(2)
 
 
 def _need_gpu():
