@@ -25,6 +25,12 @@ int launch_attn_tc_bwd(const float* qkv, const float* d_out, const int64_t* in_i
 int launch_attn_bwd_tc2(const float* qkv, const float* d_out, const int64_t* in_ids, const int32_t* tok_off, const int32_t* row_seq,
                         const int32_t* tiles, int tiles_cap, float* d_qkv, int B, int L, int D, int n_head, Dropout drop, cudaStream_t st);
 
+// full-catalog scoring q @ E^T on tcgen05 with the top-k selection fused into the epilogue (no B x N logits)  [logits_tc.cu]
+bool logits_tc_supported(int D, int32_t k);
+size_t logits_tc_workspace_bytes(int B, int64_t N, int D, int H);
+int launch_logits_topk_tc(const float* q, const float* table, const uint8_t* item_dead, const int64_t* user_hist, int B, int D, int64_t N,
+                          int H, int k, float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // whole-encoder forward as one persistent tcgen05 kernel (D = F = 128, 2 heads)  [fused_fwd.cu]
 struct FusedLayerHost {
   float *qkv, *attn, *z1, *st1, *x1, *hm, *gp, *z2, *st2, *x2;   // hm = mask * gelu(pre), gp = mask * gelu'(pre) (pre itself is not kept)

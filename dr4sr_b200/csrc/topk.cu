@@ -1,12 +1,16 @@
 // topk.cu -- full-catalog scoring + top-k, replaces BaseModel.topk (reference model/basemodel.py:354-365).
 //
 //   scores = q @ E[:N].T ; -inf at ids outside the eval domain and at the user's history ; top-k.
-// Round-1 structure: exact-fp32 FFMA GEMM with the domain mask folded in as a column bias (0 / -inf),
+// Default path (D in {64, 128}, k <= 128): logits_tc.cu -- tcgen05 scoring with the selection fused into the epilogue,
+// exact fp32 re-scoring of the survivors; no B x N buffer.  This file keeps the exact-fp32 reference path of the library
+// (dr4sr_set_gemm_backend(1), other shapes): FFMA GEMM with the domain mask folded in as a column bias (0 / -inf),
 // a scatter of -inf at the history ids, then one CTA per row doing an 8-bit MSD radix select for the
 // k-th key followed by an index-ordered gather and a bitonic sort of the k survivors.
 // Ties are broken by the lower item id (deterministic; torch.topk leaves tie order unspecified).
+#include <atomic>
 #include "gemm_simt.cuh"
 #include "internal.cuh"
+namespace dr4sr { extern std::atomic<int> g_gemm_backend; }
 
 namespace dr4sr {
 namespace {
@@ -139,10 +143,14 @@ __global__ void __launch_bounds__(kSelThreads) topk_select_kernel(const float* _
 
 using namespace dr4sr;
 
+static bool topk_use_tc(int32_t D, int32_t k) { return g_gemm_backend.load(std::memory_order_relaxed) == 0 && logits_tc_supported(D, k); }
+
 extern "C" size_t dr4sr_topk_workspace_bytes(int32_t B, int64_t N, int32_t k) {
-  (void)k;
+  // tcgen05 path: bf16 hi/lo images of the table + per-row candidate lists -- O(N D + B), independent of B x N.  The
+  // signature carries neither D nor H: sized for D = 128 and H = 64 (the reference's max_seq_len is 50).
+  if (topk_use_tc(128, k)) return logits_tc_workspace_bytes(B, N, 128, 64);
   const size_t n_al = ((size_t)N + 127) & ~(size_t)127;
-  return sizeof(float) * ((size_t)B * n_al + n_al) + 256;
+  return sizeof(float) * ((size_t)B * n_al + n_al) + 256;      // exact-fp32 FFMA path: materialised logits
 }
 
 extern "C" int dr4sr_topk(const float* q, const float* table, const uint8_t* item_dead, const int64_t* user_hist, int32_t B,
@@ -150,8 +158,13 @@ extern "C" int dr4sr_topk(const float* q, const float* table, const uint8_t* ite
                           size_t ws_bytes, dr4sr_stream_t stream) {
   if (!q || !table || !out_scores || !out_ids || !ws || B <= 0 || D % 4 || N <= 0 || N > 0x7fffff00) return DR4SR_EINVAL;
   if (k <= 0 || k > 1024 || k > N) return DR4SR_EINVAL;
-  if (ws_bytes < dr4sr_topk_workspace_bytes(B, N, k)) return DR4SR_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
+  if (topk_use_tc(D, k) && H <= 64)
+    return launch_logits_topk_tc(q, table, item_dead, user_hist, B, D, N, H, k, out_scores, out_ids, ws, ws_bytes, st);
+  {
+    const size_t n_al0 = ((size_t)N + 127) & ~(size_t)127;
+    if (ws_bytes < sizeof(float) * ((size_t)B * n_al0 + n_al0) + 256) return DR4SR_EWORKSPACE;
+  }
   const size_t n_al = ((size_t)N + 127) & ~(size_t)127;   // padded row stride: 16-byte stores, whole tiles
   float* bias = reinterpret_cast<float*>(ws);
   float* scores = bias + n_al;

@@ -150,7 +150,11 @@ class BaseModel(nn.Module):
             raise _engine._lib.Dr4srError(f'flat layout mismatch: python {n} vs C {self.engine.param_count}')
         dev = self.item_embedding.weight.device
         self._flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self._flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        # every gradient lives in ONE buffer [table gradient | encoder gradient | loss slot], so that a data-parallel step
+        # needs a single all-reduce (replicated table) or one over the tail (row-sharded table)
+        tn = self.item_embedding.weight.numel()
+        self._comm = torch.zeros(tn + n + 1, dtype=torch.float32, device=dev)
+        self._flat_grad = self._comm[tn:tn + n]
         self._grad_views = []
         off = 0
         for p in params:
@@ -160,7 +164,7 @@ class BaseModel(nn.Module):
             self._grad_views.append(self._flat_grad[off:off + k].view(p.shape))
             off += k
         self._flat_params = params
-        self._table_grad = torch.zeros_like(self.item_embedding.weight.data)
+        self._table_grad = self._comm[:tn].view_as(self.item_embedding.weight.data)
         old_table = getattr(self, '_table_group', None)
         self._table_group: Optional[FlatGroup] = None
         opt = getattr(self, 'optimizer', None)
@@ -250,6 +254,34 @@ class BaseModel(nn.Module):
             self._dp_sum(tg)
         else:
             self._shard.push_grads(self._table_grad_buffer())
+
+    def _dp_count_async(self, counts_slot: torch.Tensor):
+        """Global number of valid targets: summed over ranks on NCCL's stream while the encoder forward runs; the
+        returned handle's wait() orders the scoring kernel behind it (None when not data parallel)."""
+        grp = getattr(self, '_dp_group', None)
+        if grp is None:
+            return None
+        import torch.distributed as dist
+        return dist.all_reduce(counts_slot, op=dist.ReduceOp.SUM, group=grp, async_op=True)
+
+    def _reduce_grads(self, tg: torch.Tensor, loss: Optional[torch.Tensor]) -> None:
+        """End of a data-parallel backward: ONE all-reduce over [table gradient | encoder gradient | loss] (replicated
+        table), or the row push of the sharded table plus one all-reduce over [encoder gradient | loss].  `loss` (the
+        forward's local partial sum, divided by the global n) becomes the global loss in place."""
+        grp = getattr(self, '_dp_group', None)
+        if grp is None:
+            return
+        import torch.distributed as dist
+        tn = self._table_grad.numel()
+        if loss is not None:
+            self._comm[-1:].copy_(loss.detach().view(1))
+        if self._shard is None and tg is self._table_grad:
+            dist.all_reduce(self._comm, op=dist.ReduceOp.SUM, group=grp)
+        else:
+            self._finish_table_grad(tg)
+            dist.all_reduce(self._comm[tn:], op=dist.ReduceOp.SUM, group=grp)
+        if loss is not None:
+            loss.detach().view(1).copy_(self._comm[-1:])
 
     def _dp_sum(self, *tensors) -> None:
         grp = getattr(self, '_dp_group', None)

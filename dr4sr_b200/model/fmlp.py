@@ -122,7 +122,8 @@ class FMLP(BaseModel):
         eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad)
         tg = self._table_grad_buffer()
         eng.table_grad(b, in_ids, item_id, neg, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
-        self._dp_sum(self._flat_grad, tg)
+        if getattr(self, '_dp_group', None) is not None:
+            self._reduce_grads(tg, None)
 
     def composite_forward(self, batch):
         """Twice-differentiable torch evaluation (MetaModel's outer step only), model/fmlp.py:18-39."""

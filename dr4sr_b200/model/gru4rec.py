@@ -44,7 +44,7 @@ class GRU4Rec(BaseModel):
 
     def _step_backward(self, state, reduce, dloss, dquery) -> None:
         eng = self.engine
-        b, table, in_ids, item_id, neg, fused_grad = state
+        b, table, in_ids, item_id, neg, fused_grad, late_loss = state
         if fused_grad:
             eng.scale_grads(b, dloss)
         elif reduce:
@@ -58,8 +58,8 @@ class GRU4Rec(BaseModel):
         eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad)
         tg = self._scatter_target()
         eng.table_grad(b, in_ids, item_id, neg, tg, None)          # no positional table in GRU4Rec
-        self._dp_sum(self._flat_grad)
-        self._finish_table_grad(tg)
+        if getattr(self, '_dp_group', None) is not None:
+            self._reduce_grads(tg, late_loss)
 
     def composite_forward(self, batch):
         """Twice-differentiable torch evaluation (MetaModel's outer step only), model/gru4rec.py:23-31."""

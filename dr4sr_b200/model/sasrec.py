@@ -86,8 +86,7 @@ class SASRec(BaseModel):
         in_ids, item_id, neg = batch['in_' + self.fiid], batch[self.fiid], batch['neg_item']
         neg = neg.view(item_id.shape)
         b = eng.prep(batch['seqlen'], item_id)
-        if getattr(self, '_dp_group', None) is not None:
-            self._dp_sum(b.counts[1:2])       # data parallel: normalise by the global number of valid targets
+        n_work = self._dp_count_async(b.counts[1:2])   # data parallel: normalise by the global number of valid targets
         if self.training:
             eng.step += 1
         q_dense = None
@@ -98,15 +97,20 @@ class SASRec(BaseModel):
         # training with the mean loss: ds, dq come out of the same sweep as the loss (scaled by autograd's grad_output
         # in the backward); the weighted / per-position variants recompute them there
         fused_grad = bool(reduce and self.training)
+        if n_work is not None:
+            n_work.wait()                     # (stream-side wait: the count's all-reduce ran under the encoder forward)
         eng.score_bce(b, table, item_id, neg, want_grad=fused_grad)
         loss = eng.reduce_loss(b) if reduce else b.loss_pos.clone()
-        if reduce and getattr(self, '_dp_group', None) is not None:
+        # data parallel, mean loss in training: the rank-local partial becomes the global loss inside the backward's single
+        # gradient all-reduce (BaseModel._reduce_grads); any other use sums it right away
+        late = bool(reduce and fused_grad and getattr(self, '_dp_group', None) is not None)
+        if reduce and not late:
             self._dp_sum(loss)
-        return loss, q_dense, (b, table, in_ids, item_id, neg, fused_grad)
+        return loss, q_dense, (b, table, in_ids, item_id, neg, fused_grad, loss if late else None)
 
     def _step_backward(self, state, reduce, dloss, dquery) -> None:
         eng = self.engine
-        b, table, in_ids, item_id, neg, fused_grad = state
+        b, table, in_ids, item_id, neg, fused_grad, late_loss = state
         if fused_grad:
             eng.scale_grads(b, dloss)
         elif reduce:
@@ -121,8 +125,8 @@ class SASRec(BaseModel):
         tg = self._scatter_target()
         eng.table_grad(b, in_ids, item_id, neg, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
         eng.join_bwd()
-        self._dp_sum(self._flat_grad)
-        self._finish_table_grad(tg)
+        if getattr(self, '_dp_group', None) is not None:
+            self._reduce_grads(tg, late_loss)
 
     def composite_forward(self, batch):
         """Twice-differentiable torch evaluation of the same parameters (MetaModel's outer step only):

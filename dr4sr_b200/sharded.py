@@ -47,32 +47,50 @@ class ShardedTable:
         self.send_ids = torch.zeros(cap, dtype=torch.int64, device=dev)
         self.loc = torch.zeros(1 + cap, self.D, dtype=torch.float32, device=dev)
         self.gloc = torch.zeros(1 + cap, self.D, dtype=torch.float32, device=dev)
-        self.in_loc = self.item_loc = self.neg_loc = None
+        # everything the step needs is allocated once: remapped ids, the id / row / gradient exchange buffers (their used
+        # prefixes change per step, their capacity does not: a rank receives at most `world` x cap requests in the worst
+        # case, sized lazily on first overflow), the count exchange
+        self._loc_ids = torch.zeros(3, B * L, dtype=torch.int64, device=dev)
+        self.counts2 = torch.zeros(2, self.world, dtype=torch.int64, device=dev)
+        self.counts_host = torch.zeros(2, self.world, dtype=torch.int64).pin_memory()
+        self._recv_cap = 0
+        self.bytes_last_step = 0
+
+    def _ensure_recv(self, n_recv: int) -> None:
+        if n_recv <= self._recv_cap:
+            return
+        self._recv_cap = int(n_recv * 1.25) + 1024
+        dev = self.device
+        self.recv_ids = torch.zeros(self._recv_cap, dtype=torch.int64, device=dev)
+        self.rows_out = torch.zeros(self._recv_cap, self.D, dtype=torch.float32, device=dev)
+        self.grad_in = torch.zeros(self._recv_cap, self.D, dtype=torch.float32, device=dev)
 
     def fetch(self, shard: torch.Tensor, bufs, in_ids: torch.Tensor, item_id: Optional[torch.Tensor], neg: Optional[torch.Tensor]
               ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
         """-> (local table, in_loc, item_loc, neg_loc).  `shard` = this rank's rows [lo, hi) of E."""
         B, L = in_ids.shape
         self._ensure(B, L)
-        dev = self.device
-        in_loc = torch.empty(B, L, dtype=torch.int64, device=dev)
-        item_loc = torch.empty(B, L, dtype=torch.int64, device=dev) if item_id is not None else None
-        neg_loc = torch.empty(B, L, dtype=torch.int64, device=dev) if item_id is not None else None
+        in_loc = self._loc_ids[0, :B * L].view(B, L)
+        item_loc = self._loc_ids[1, :B * L].view(B, L) if item_id is not None else None
+        neg_loc = self._loc_ids[2, :B * L].view(B, L) if item_id is not None else None
         check(self.lib.dr4sr_shard_plan(_p(in_ids), _p(item_id), _p(neg), _p(bufs.tok_off), _p(bufs.row_seq), _p(bufs.counts), B, L,
                                         self.N, self.world, _p(self.send_counts), _p(self.scratch), _p(self.send_ids), _p(in_loc),
                                         _p(item_loc), _p(neg_loc), _stream()), 'dr4sr_shard_plan')
-        sc_dev = self.send_counts.to(torch.int64)
-        rc_dev = torch.empty_like(sc_dev)
-        dist.all_to_all_single(rc_dev, sc_dev, group=self.group)
-        both = torch.stack([sc_dev, rc_dev]).cpu()             # the step's one host sync
-        sc, rc = both[0].tolist(), both[1].tolist()
+        self.counts2[0].copy_(self.send_counts)
+        dist.all_to_all_single(self.counts2[1], self.counts2[0], group=self.group)
+        self.counts_host.copy_(self.counts2, non_blocking=True)
+        torch.cuda.current_stream().synchronize()              # the step's one host sync (sizes the two variable all-to-alls)
+        sc, rc = self.counts_host[0].tolist(), self.counts_host[1].tolist()
         n_send, n_recv = sum(sc), sum(rc)
-        recv_ids = torch.empty(n_recv, dtype=torch.int64, device=dev)
+        self._ensure_recv(n_recv)
+        recv_ids = self.recv_ids[:n_recv]
         dist.all_to_all_single(recv_ids, self.send_ids[:n_send], rc, sc, group=self.group)
-        rows_out = torch.empty(n_recv, self.D, dtype=torch.float32, device=dev)
+        rows_out = self.rows_out[:n_recv]
         check(self.lib.dr4sr_gather_rows(_p(shard), _p(recv_ids), self.lo, n_recv, self.D, _p(rows_out), _stream()), 'dr4sr_gather_rows')
         dist.all_to_all_single(self.loc[1:1 + n_send], rows_out, sc, rc, group=self.group)
         self._state = (sc, rc, recv_ids, n_send, n_recv)
+        # all-to-all payload this rank sends + receives per step: ids out, rows back, gradient rows out (for the bench line)
+        self.bytes_last_step = (n_send + n_recv) * (8 + 2 * 4 * self.D)
         return self.loc, in_loc, item_loc, neg_loc
 
     def local_grad(self) -> torch.Tensor:
@@ -84,7 +102,7 @@ class ShardedTable:
     def push_grads(self, shard_grad: torch.Tensor) -> None:
         """Send the rows of the local gradient table to their owners and accumulate them into `shard_grad`."""
         sc, rc, recv_ids, n_send, n_recv = self._state
-        grad_in = torch.empty(n_recv, self.D, dtype=torch.float32, device=self.device)
+        grad_in = self.grad_in[:n_recv]
         dist.all_to_all_single(grad_in, self.gloc[1:1 + n_send], rc, sc, group=self.group)
         check(self.lib.dr4sr_scatter_add_rows(_p(shard_grad), _p(recv_ids), self.lo, n_recv, self.D, _p(grad_in), _stream()),
               'dr4sr_scatter_add_rows')
