@@ -41,6 +41,37 @@ ProfScope::~ProfScope() {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   cudaEventRecord(g_prof[slot].end, st);
 }
+// Auxiliary stream for short independent kernels (fork / join with events; legal inside a CUDA-graph capture of the main
+// stream).  One per device, created on first use, never destroyed.  aux_fork: work queued on the returned stream starts
+// once everything enqueued on `st` so far has finished; aux_join: `st` continues after that work.  Falls back to `st` itself.
+struct AuxStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+static AuxStream& aux_stream() {
+  static AuxStream per_dev[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  AuxStream& x = per_dev[dev & 63];
+  if (!x.ok) {
+    bool good = cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+    x.ok = good;
+  }
+  return x;
+}
+cudaStream_t aux_fork(cudaStream_t st) {
+  AuxStream& x = aux_stream();
+  if (!x.ok || cudaEventRecord(x.fork, st) != cudaSuccess || cudaStreamWaitEvent(x.s, x.fork, 0) != cudaSuccess) return st;
+  return x.s;
+}
+int aux_join(cudaStream_t aux, cudaStream_t st) {
+  if (aux == st) return DR4SR_OK;
+  AuxStream& x = aux_stream();
+  if (cudaEventRecord(x.join, aux) != cudaSuccess || cudaStreamWaitEvent(st, x.join, 0) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "aux join");
+    return DR4SR_ECUDA;
+  }
+  return DR4SR_OK;
+}
 }  // namespace dr4sr
 
 using namespace dr4sr;

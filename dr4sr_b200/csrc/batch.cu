@@ -5,9 +5,10 @@ namespace dr4sr {
 namespace {
 
 // tok_off = exclusive scan of clamp(seqlen, 0, L); row_seq[row] = b.  One CTA (B is a few thousand).
+// counts = {live tokens, non-pad targets among item_id[0, n_tgt) (0 when item_id is null), 0, 0}.
 __global__ void __launch_bounds__(1024) prep_scan_kernel(const int64_t* __restrict__ seqlen, int B, int L,
                                                          int32_t* __restrict__ tok_off, int32_t* __restrict__ row_seq,
-                                                         int32_t* __restrict__ counts) {
+                                                         int32_t* __restrict__ counts, const int64_t* __restrict__ item_id, int64_t n_tgt) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
   __shared__ int s_before[1024], s_len[1024];
@@ -52,21 +53,21 @@ __global__ void __launch_bounds__(1024) prep_scan_kernel(const int64_t* __restri
     if (tid == blockDim.x - 1) carry = before + len;
     __syncthreads();
   }
-  if (tid == 0) {
-    tok_off[B] = carry;
-    counts[0] = carry;
-    counts[1] = 0; counts[2] = 0; counts[3] = 0;
-  }
-}
-
-__global__ void __launch_bounds__(256) count_targets_int_kernel(const int64_t* __restrict__ item_id, int64_t n,
-                                                                int32_t* __restrict__ counts) {
-  int c = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    c += item_id[i] != 0;
+  int c = 0;                                   // valid targets: same CTA, no second launch (integer sum: order-independent)
+  if (item_id)
+    for (int64_t i = tid; i < n_tgt; i += blockDim.x) c += item_id[i] != 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counts[1], c);   // integer atomics: order-independent result
+  __syncthreads();
+  if (lane == 0) warp_tot[warp] = c;
+  __syncthreads();
+  if (tid == 0) {
+    int tot = 0;
+    for (int w = 0; w < 32; ++w) tot += warp_tot[w];
+    tok_off[B] = carry;
+    counts[0] = carry;
+    counts[1] = tot; counts[2] = 0; counts[3] = 0;
+  }
 }
 
 __global__ void __launch_bounds__(256) neg_sample_kernel(int64_t* __restrict__ out, int64_t n, uint32_t range, uint32_t key) {
@@ -134,14 +135,8 @@ extern "C" int dr4sr_prep_batch(const int64_t* seqlen, const int64_t* item_id, i
   if (!seqlen || !tok_off || !row_seq || !counts || B <= 0 || L <= 0) return DR4SR_EINVAL;
   cudaStream_t st = as_stream(stream);
   ProfScope prof("prep_batch", st);
-  prep_scan_kernel<<<1, 1024, 0, st>>>(seqlen, B, L, tok_off, row_seq, counts);
+  prep_scan_kernel<<<1, 1024, 0, st>>>(seqlen, B, L, tok_off, row_seq, counts, item_id, target_is_1d ? (int64_t)B : (int64_t)B * L);
   DR4SR_LAUNCH_CHECK("prep_scan_kernel");
-  if (item_id) {
-    const int64_t n = target_is_1d ? (int64_t)B : (int64_t)B * L;
-    const int blocks = ceil_div(n, 256 * 4) < kNumSMs ? ceil_div(n, 256 * 4) : kNumSMs;
-    count_targets_int_kernel<<<blocks, 256, 0, st>>>(item_id, n, counts);
-    DR4SR_LAUNCH_CHECK("count_targets_kernel");
-  }
   return DR4SR_OK;
 }
 

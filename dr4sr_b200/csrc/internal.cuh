@@ -4,6 +4,10 @@
 
 namespace dr4sr {
 
+// auxiliary stream for short independent kernels  [api.cu]
+cudaStream_t aux_fork(cudaStream_t st);
+int aux_join(cudaStream_t aux, cudaStream_t st);
+
 constexpr int kLnBwdBlocks = 2 * kNumSMs;   // CTAs (= column-partial slices) of the LayerNorm backward kernels
 
 // attention over packed rows, one CTA per (sequence, head)  [attention.cu]

@@ -283,30 +283,36 @@ extern "C" int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, 
   cudaStream_t st = as_stream(stream);
   const int T_cap = B * L;
   const int blocks = ceil_div(T_cap, 8) < 8 * kNumSMs ? ceil_div(T_cap, 8) : 8 * kNumSMs;
+  // the positional gradient (a deterministic column reduction of dx0) shares nothing with the scatter-add but its input:
+  // it runs on the auxiliary stream, beside the scatter
+  const bool with_pos = pos_grad && dx0_packed;
+  cudaStream_t sa = st;
+  if (with_pos) {
+    if (!ws || ws_bytes < dr4sr_table_grad_workspace_bytes(L, D)) return DR4SR_EWORKSPACE;
+    sa = aux_fork(st);
+    float* partial = reinterpret_cast<float*>(ws);
+    const size_t smem = sizeof(float) * (size_t)L * D;
+    {
+      ProfScope prof("pos_grad", sa);
+      if (cudaFuncSetAttribute(pos_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_cuda_error(cudaGetLastError(), "pos_grad smem attribute");
+        return DR4SR_ECUDA;
+      }
+      pos_grad_kernel<<<kPosChunks, 256, smem, sa>>>(dx0_packed, tok_off, B, L, D, partial);
+      DR4SR_LAUNCH_CHECK("pos_grad_kernel");
+    }
+    ReduceTable tab{};
+    tab.seg[0] = ReduceSeg{partial, pos_grad, kPosChunks, (int64_t)L * D, L * D};
+    tab.count = 1;
+    DR4SR_TRY(launch_reduce_segments(tab, sa));
+  }
   {
   ProfScope prof("table_grad_scatter", st);
   table_grad_kernel<<<blocks, 256, 0, st>>>(dx0_packed, q_packed, dscore, in_item_id, item_id, neg_item, tok_off, row_seq,
                                             counts, L, D, table_grad);
   DR4SR_LAUNCH_CHECK("table_grad_kernel");
   }
-  if (pos_grad && dx0_packed) {
-    if (!ws || ws_bytes < dr4sr_table_grad_workspace_bytes(L, D)) return DR4SR_EWORKSPACE;
-    float* partial = reinterpret_cast<float*>(ws);
-    const size_t smem = sizeof(float) * (size_t)L * D;
-    {
-      ProfScope prof("pos_grad", st);
-      if (cudaFuncSetAttribute(pos_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        set_cuda_error(cudaGetLastError(), "pos_grad smem attribute");
-        return DR4SR_ECUDA;
-      }
-      pos_grad_kernel<<<kPosChunks, 256, smem, st>>>(dx0_packed, tok_off, B, L, D, partial);
-      DR4SR_LAUNCH_CHECK("pos_grad_kernel");
-    }
-    ReduceTable tab{};
-    tab.seg[0] = ReduceSeg{partial, pos_grad, kPosChunks, (int64_t)L * D, L * D};
-    tab.count = 1;
-    DR4SR_TRY(launch_reduce_segments(tab, st));
-  }
+  if (with_pos) DR4SR_TRY(aux_join(sa, st));
   return DR4SR_OK;
 }
 

@@ -251,9 +251,12 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
   const float* pos = params;
 
   if (fused_enabled() && fused_fwd_supported(c->L, D, F, c->n_head)) {
-    // one persistent kernel: gather + positions + dropout and every layer, per group of whole sequences
-    DR4SR_TRY(build_weight_images(*c, params, w, lo, st));
+    // one persistent kernel: gather + positions + dropout and every layer, per group of whole sequences.  Its two small
+    // preparation kernels (weight images: parameters only; tiles: tok_off only) run side by side
+    cudaStream_t sa = aux_fork(st);
+    DR4SR_TRY(build_weight_images(*c, params, w, lo, sa));
     DR4SR_TRY(launch_fused_tiles(tok_off, c->B, w.fused_tiles, st));
+    DR4SR_TRY(aux_join(sa, st));
     FusedFwdHost h{};
     h.table = table; h.pos = pos; h.in_ids = in_item_id; h.tok_off = tok_off; h.row_seq = row_seq; h.tiles = w.fused_tiles;
     h.x0 = w.x0; h.B = c->B; h.L = c->L; h.n_layer = c->n_layer; h.ln_eps = c->ln_eps;
