@@ -17,7 +17,7 @@ def test_kernel_work_model_matches_design_table():
     T, B = 26_400, 1024
     U = T * c['embed_dim'] * 4
     w = bench.kernel_work('sasrec_fwd_fused', T, B, c)
-    assert w == dict(bound='hbm', work=(2 + 9 * c['layer_num']) * U, unit='GB/s')
+    assert w == dict(bound='hbm', work=(2 + 10 * c['layer_num']) * U, unit='GB/s')
     assert bench.kernel_work('attn_bwd', T, B, c)['work'] == 7 * U
     assert bench.kernel_work('adam_table', T, B, c)['work'] == 24 * c['num_items'] * c['embed_dim']
     g = bench.kernel_work('wgrad_tc', T, B, c)
@@ -28,9 +28,9 @@ def test_kernel_work_model_matches_design_table():
 
 def test_ncu_traffic_table_is_committed_and_names_profiled_kernels():
     t = bench.ncu_traffic()
-    assert {'attn_bwd', 'sasrec_fwd_fused'} <= set(t)
+    assert {'attn_bwd_tc', 'sasrec_fwd_fused', 'sasrec_bwd_ffn_fused', 'adam_table'} <= set(t)
     assert all(isinstance(v, (int, float)) and v > 0 for v in t.values())
-    src = json.load(open(os.path.join(REPO, 'profiles', 'r1_ncu_traffic.json')))['source']
+    src = json.load(open(os.path.join(REPO, 'profiles', 'r2_ncu_traffic.json')))['source']
     assert 'ncu --set full' in src
 
 
