@@ -29,6 +29,15 @@ class GruCfg(C.Structure):
                 ('seed', c_u64), ('step', c_u64)]
 
 
+MAX_SHARDS = 8
+
+
+class ShardMap(C.Structure):
+    """Mirror of dr4sr_shard_map (row-sharded item table over peer memory)."""
+    _fields_ = [('table', c_p * MAX_SHARDS), ('grad', c_p * MAX_SHARDS), ('lo', c_i64 * (MAX_SHARDS + 1)), ('world', c_i32),
+                ('rank', c_i32)]
+
+
 class SasrecCfg(C.Structure):
     """Mirror of dr4sr_sasrec_cfg."""
     _fields_ = [('B', c_i32), ('L', c_i32), ('D', c_i32), ('F', c_i32), ('n_head', c_i32), ('n_layer', c_i32),
@@ -39,6 +48,7 @@ class SasrecCfg(C.Structure):
 SIGNATURES = {
     'dr4sr_abi_version': (c_i32, []),
     'dr4sr_last_cuda_error': (C.c_char_p, []),
+    'dr4sr_enable_peer_access': (c_i32, [c_i32]),
     'dr4sr_launch_count': (C.c_longlong, []),
     'dr4sr_prof_enable': (c_i32, [c_i32]),
     'dr4sr_prof_collect': (c_sz, [C.c_char_p, c_sz]),
@@ -53,6 +63,9 @@ SIGNATURES = {
     'dr4sr_sasrec_param_count': (c_sz, [C.POINTER(SasrecCfg)]),
     'dr4sr_sasrec_workspace_bytes': (c_sz, [C.POINTER(SasrecCfg)]),
     'dr4sr_sasrec_fwd': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p, c_p, c_p]),
+    'dr4sr_sasrec_fwd_sharded': (c_i32, [C.POINTER(SasrecCfg), C.POINTER(ShardMap), c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_i32, c_p, c_p, c_p, c_p]),
+    'dr4sr_score_loss_sharded': (c_i32, [c_i32, c_p, C.POINTER(ShardMap), c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_p, c_p, c_p, c_p, c_p, c_p]),
+    'dr4sr_table_grad_sharded': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, C.POINTER(ShardMap), c_p, c_p, c_sz, c_p]),
     'dr4sr_sasrec_bwd': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
     'dr4sr_sasrec_bwd_async': (c_i32, [C.POINTER(SasrecCfg), c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p, c_p, c_p]),
     'dr4sr_sasrec_bwd_join': (c_i32, [c_p]),

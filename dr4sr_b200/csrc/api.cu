@@ -77,6 +77,16 @@ int aux_join(cudaStream_t aux, cudaStream_t st) {
 using namespace dr4sr;
 
 extern "C" int dr4sr_abi_version(void) { return DR4SR_ABI_VERSION; }
+extern "C" int dr4sr_enable_peer_access(int peer_device) {
+  int cur = 0, can = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) { set_cuda_error(cudaGetLastError(), "peer access"); return DR4SR_ECUDA; }
+  if (peer_device == cur) return DR4SR_OK;
+  if (cudaDeviceCanAccessPeer(&can, cur, peer_device) != cudaSuccess || !can) { cudaGetLastError(); return DR4SR_EINVAL; }
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_cuda_error(e, "cudaDeviceEnablePeerAccess"); return DR4SR_ECUDA; }
+  cudaGetLastError();
+  return DR4SR_OK;
+}
 extern "C" const char* dr4sr_last_cuda_error(void) { return g_err; }
 extern "C" int dr4sr_set_gemm_backend(int backend) {
   if (backend != 0 && backend != 1) return DR4SR_EINVAL;

@@ -91,6 +91,47 @@ inline Dropout make_dropout(float p, uint64_t seed, uint64_t step, uint32_t site
 enum : uint32_t { SITE_EMBED = 1, SITE_ATTN_P = 16, SITE_ATTN_OUT = 17, SITE_FFN_H = 18, SITE_FFN_OUT = 19 };
 inline uint32_t layer_site(uint32_t site, int layer) { return site + 8u * (uint32_t)layer; }
 
+// ---- row-sharded table over peer memory (include/dr4sr.h, dr4sr_shard_map) ---------------------------------------------
+// Kernel-side copy of the map; world == 1 is the single-GPU case (one compare-free path: lo[1] = N).
+struct ShardView {
+  const float* table[DR4SR_MAX_SHARDS];
+  float* grad[DR4SR_MAX_SHARDS];
+  long long lo[DR4SR_MAX_SHARDS + 1];
+  int world, rank;
+  // owner of a row id: ranges are few and sorted -> branch-free count of the boundaries at or below id
+  __device__ __forceinline__ int owner(long long id) const {
+    int o = 0;
+#pragma unroll
+    for (int r = 1; r < DR4SR_MAX_SHARDS; ++r) o += (r < world && id >= lo[r]) ? 1 : 0;
+    return o;
+  }
+  __device__ __forceinline__ const float* row(long long id, int D) const {
+    if (world == 1) return table[0] + (size_t)id * D;
+    const int o = owner(id);
+    return table[o] + (size_t)(id - lo[o]) * D;
+  }
+  __device__ __forceinline__ float* grad_row(long long id, int D) const {
+    if (world == 1) return grad[0] + (size_t)id * D;
+    const int o = owner(id);
+    return grad[o] + (size_t)(id - lo[o]) * D;
+  }
+  __device__ __forceinline__ bool is_local(long long id) const { return world == 1 || (id >= lo[rank] && id < lo[rank + 1]); }
+};
+inline ShardView shard_view_local(const float* table, float* grad, long long N) {
+  ShardView v{};
+  v.table[0] = table; v.grad[0] = grad; v.lo[0] = 0; v.lo[1] = N; v.world = 1; v.rank = 0;
+  return v;
+}
+inline bool shard_view_from(const dr4sr_shard_map* m, ShardView* out) {
+  if (!m || m->world < 1 || m->world > DR4SR_MAX_SHARDS || m->rank < 0 || m->rank >= m->world) return false;
+  ShardView v{};
+  for (int r = 0; r < m->world; ++r) { v.table[r] = m->table[r]; v.grad[r] = m->grad[r]; v.lo[r] = m->lo[r]; }
+  v.lo[m->world] = m->lo[m->world];
+  v.world = m->world; v.rank = m->rank;
+  *out = v;
+  return true;
+}
+
 // ---- warp helpers -------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -92,7 +92,7 @@ struct FusedLayer {
   Dropout d_attn_p, d_attn_out, d_ffn_h, d_ffn_out;
 };
 struct FusedFwdArgs {
-  const float* table; const float* pos;
+  ShardView table; const float* pos;
   const int64_t* in_ids; const int32_t* tok_off; const int32_t* row_seq; const int32_t* tiles;
   float* x0;
   int n_layer, L;
@@ -735,7 +735,8 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
         pd = id == 0;
         // pull the whole 512 B table row into L2 as ONE contiguous request: the row-per-thread gather below would
         // otherwise reach DRAM as scattered 32 B sectors
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.table + (size_t)id * 128), "r"(512) : "memory");
+        if (a.table.is_local(id))       // (rows of other ranks come over NVLink: nothing to prefetch into this GPU's L2)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.table.row(id, 128)), "r"(512) : "memory");
       }
       s_start[tid] = st; s_seq[tid] = sq; s_id[tid] = id;
       const uint32_t real = __ballot_sync(0xffffffffu, !pd);        // warps 0..3 are complete: 32 keys each
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(kFT, 2) sasrec_fwd_fused_kernel(const __grid_c
     {
       RowDrop rd;
       rd.init(a.d_embed, (uint32_t)c.m);
-      const float* e = a.table + (size_t)s_id[c.row] * 128 + c.half * 64;
+      const float* e = a.table.row(s_id[c.row], 128) + c.half * 64;     // local HBM, or the owner's HBM through peer memory
       const float* p = a.pos + (size_t)(c.row - s_start[c.row]) * 128 + c.half * 64;
       float ev[64];                                             // the thread's 64 table floats: every (256-bit) load in flight at once
 #pragma unroll

@@ -43,7 +43,7 @@ struct FusedLayerHost {
   Dropout d_attn_p, d_attn_out, d_ffn_h, d_ffn_out;
 };
 struct FusedFwdHost {
-  const float* table; const float* pos;
+  ShardView table; const float* pos;
   const int64_t* in_ids; const int32_t* tok_off; const int32_t* row_seq; const int32_t* tiles;
   float* x0;
   int B, L, n_layer;

@@ -15,7 +15,7 @@ namespace {
 // intends it, l = -logsig(s+ - s-) / n with one negative (unreachable through the reference's training_step, which
 // passes `reduce` to a two-argument forward -- the "fixed BPR" extension of SURVEY.md Appendix C.6).
 template <int KIND>
-__global__ void __launch_bounds__(256) score_bce_kernel(const float* __restrict__ q, const float* __restrict__ table,
+__global__ void __launch_bounds__(256) score_bce_kernel(const float* __restrict__ q, const __grid_constant__ ShardView table,
                                                         const int64_t* __restrict__ item_id, const int64_t* __restrict__ neg_item,
                                                         const int32_t* __restrict__ tok_off, const int32_t* __restrict__ counts,
                                                         int B, int L, int D, const float* __restrict__ loss_weight,
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256) score_bce_kernel(const float* __restrict_
     }
     const int64_t nid = neg_item[slot];
     const float* qr = q + (size_t)row * D;
-    const float* ep = table + (size_t)pid * D;
-    const float* en = table + (size_t)nid * D;
+    const float* ep = table.row(pid, D);          // local HBM, or the owner's HBM through peer memory
+    const float* en = table.row(nid, D);
     float sp = 0.f, sn = 0.f;
     float4 qv[2], pv[2], nv[2];   // D <= 256
     int k = 0;
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) table_grad_kernel(const float* __restrict
                                                          const float* __restrict__ dscore, const int64_t* __restrict__ in_ids,
                                                          const int64_t* __restrict__ item_id, const int64_t* __restrict__ neg_item,
                                                          const int32_t* __restrict__ tok_off, const int32_t* __restrict__ row_seq,
-                                                         const int32_t* __restrict__ counts, int L, int D, float* __restrict__ tg) {
+                                                         const int32_t* __restrict__ counts, int L, int D, const __grid_constant__ ShardView tg) {
   const int T = counts[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int row = blockIdx.x * 8 + warp; row < T; row += gridDim.x * 8) {
@@ -123,16 +123,18 @@ __global__ void __launch_bounds__(256) table_grad_kernel(const float* __restrict
     const int64_t iid = in_ids[slot];
     if (dx0 && iid != 0) {   // padding_idx = 0 receives no gradient (nn.Embedding)
       for (int c = lane * 4; c < D; c += 128)
-        red_add_v4(tg + (size_t)iid * D + c, *reinterpret_cast<const float4*>(dx0 + (size_t)row * D + c));
+        red_add_v4(tg.grad_row(iid, D) + c, *reinterpret_cast<const float4*>(dx0 + (size_t)row * D + c));
     }
     const int64_t pid = item_id ? item_id[slot] : 0;
     if (pid != 0) {
       const float dsp = dscore[2 * (size_t)row], dsn = dscore[2 * (size_t)row + 1];
       const int64_t nid = neg_item[slot];
+      float* gp_row = tg.grad_row(pid, D);           // red.global.add into the owner's accumulator (NVLink atomics for remote rows)
+      float* gn_row = tg.grad_row(nid, D);
       for (int c = lane * 4; c < D; c += 128) {
         const float4 v = *reinterpret_cast<const float4*>(q + (size_t)row * D + c);
-        red_add_v4(tg + (size_t)pid * D + c, make_float4(dsp * v.x, dsp * v.y, dsp * v.z, dsp * v.w));
-        red_add_v4(tg + (size_t)nid * D + c, make_float4(dsn * v.x, dsn * v.y, dsn * v.z, dsn * v.w));
+        red_add_v4(gp_row + c, make_float4(dsp * v.x, dsp * v.y, dsp * v.z, dsp * v.w));
+        red_add_v4(gn_row + c, make_float4(dsn * v.x, dsn * v.y, dsn * v.z, dsn * v.w));
       }
     }
   }
@@ -234,24 +236,43 @@ extern "C" int dr4sr_scale_grads(const float* upstream, const int32_t* counts, i
   return DR4SR_OK;
 }
 
-extern "C" int dr4sr_score_loss(int32_t kind, const float* q_packed, const float* table, const int64_t* item_id,
-                                const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts,
-                                int32_t B, int32_t L, int32_t D, const float* loss_weight, const float* upstream, float* loss_pos,
-                                float* dscore, float* dq_packed, dr4sr_stream_t stream) {
-  (void)row_seq;
-  if (!q_packed || !table || !item_id || !neg_item || !tok_off || !counts || !loss_pos || !dscore) return DR4SR_EINVAL;
+static int score_loss_impl(int32_t kind, const float* q_packed, const ShardView& tv, const int64_t* item_id,
+                           const int64_t* neg_item, const int32_t* tok_off, const int32_t* counts,
+                           int32_t B, int32_t L, int32_t D, const float* loss_weight, const float* upstream, float* loss_pos,
+                           float* dscore, float* dq_packed, dr4sr_stream_t stream) {
+  if (!q_packed || !tv.table[0] || !item_id || !neg_item || !tok_off || !counts || !loss_pos || !dscore) return DR4SR_EINVAL;
   if (D % 4 || D > 256 || (kind != DR4SR_LOSS_BCE && kind != DR4SR_LOSS_BPR)) return DR4SR_EINVAL;
   const int total = B * L;
   const int blocks = ceil_div(total, 8) < 8 * kNumSMs ? ceil_div(total, 8) : 8 * kNumSMs;
   ProfScope prof(kind == DR4SR_LOSS_BCE ? "score_bce" : "score_bpr", as_stream(stream));
   if (kind == DR4SR_LOSS_BCE)
-    score_bce_kernel<0><<<blocks, 256, 0, as_stream(stream)>>>(q_packed, table, item_id, neg_item, tok_off, counts, B, L, D,
+    score_bce_kernel<0><<<blocks, 256, 0, as_stream(stream)>>>(q_packed, tv, item_id, neg_item, tok_off, counts, B, L, D,
                                                                 loss_weight, upstream, loss_pos, dscore, dq_packed);
   else
-    score_bce_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(q_packed, table, item_id, neg_item, tok_off, counts, B, L, D,
+    score_bce_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(q_packed, tv, item_id, neg_item, tok_off, counts, B, L, D,
                                                                 loss_weight, upstream, loss_pos, dscore, dq_packed);
   DR4SR_LAUNCH_CHECK("score_bce_kernel");
   return DR4SR_OK;
+}
+
+extern "C" int dr4sr_score_loss(int32_t kind, const float* q_packed, const float* table, const int64_t* item_id,
+                                const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts,
+                                int32_t B, int32_t L, int32_t D, const float* loss_weight, const float* upstream, float* loss_pos,
+                                float* dscore, float* dq_packed, dr4sr_stream_t stream) {
+  (void)row_seq;
+  return score_loss_impl(kind, q_packed, shard_view_local(table, nullptr, 0), item_id, neg_item, tok_off, counts, B, L, D, loss_weight,
+                         upstream, loss_pos, dscore, dq_packed, stream);
+}
+
+extern "C" int dr4sr_score_loss_sharded(int32_t kind, const float* q_packed, const dr4sr_shard_map* map, const int64_t* item_id,
+                                        const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts,
+                                        int32_t B, int32_t L, int32_t D, const float* loss_weight, const float* upstream,
+                                        float* loss_pos, float* dscore, float* dq_packed, dr4sr_stream_t stream) {
+  (void)row_seq;
+  ShardView tv;
+  if (!shard_view_from(map, &tv)) return DR4SR_EINVAL;
+  return score_loss_impl(kind, q_packed, tv, item_id, neg_item, tok_off, counts, B, L, D, loss_weight, upstream, loss_pos, dscore,
+                         dq_packed, stream);
 }
 
 extern "C" int dr4sr_score_bce(const float* q_packed, const float* table, const int64_t* item_id, const int64_t* neg_item,
@@ -272,12 +293,12 @@ extern "C" int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t s
 
 extern "C" size_t dr4sr_table_grad_workspace_bytes(int32_t L, int32_t D) { return sizeof(float) * (size_t)kPosChunks * L * D; }
 
-extern "C" int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, const float* dscore,
-                                const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
-                                const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
-                                int32_t D, int64_t N, float* table_grad, float* pos_grad, void* ws, size_t ws_bytes,
-                                dr4sr_stream_t stream) {
-  (void)N;
+static int table_grad_impl(const float* dx0_packed, const float* q_packed, const float* dscore,
+                           const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
+                           const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                           int32_t D, const ShardView& gv, float* pos_grad, void* ws, size_t ws_bytes,
+                           dr4sr_stream_t stream) {
+  float* table_grad = gv.grad[0];
   if (!in_item_id || !tok_off || !row_seq || !counts || !table_grad || D % 4) return DR4SR_EINVAL;
   if (item_id && (!q_packed || !dscore || !neg_item)) return DR4SR_EINVAL;
   cudaStream_t st = as_stream(stream);
@@ -309,11 +330,31 @@ extern "C" int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, 
   {
   ProfScope prof("table_grad_scatter", st);
   table_grad_kernel<<<blocks, 256, 0, st>>>(dx0_packed, q_packed, dscore, in_item_id, item_id, neg_item, tok_off, row_seq,
-                                            counts, L, D, table_grad);
+                                            counts, L, D, gv);
   DR4SR_LAUNCH_CHECK("table_grad_kernel");
   }
   if (with_pos) DR4SR_TRY(aux_join(sa, st));
   return DR4SR_OK;
+}
+
+extern "C" int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, const float* dscore,
+                                const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
+                                const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                                int32_t D, int64_t N, float* table_grad, float* pos_grad, void* ws, size_t ws_bytes,
+                                dr4sr_stream_t stream) {
+  return table_grad_impl(dx0_packed, q_packed, dscore, in_item_id, item_id, neg_item, tok_off, row_seq, counts, B, L, D,
+                         shard_view_local(nullptr, table_grad, N), pos_grad, ws, ws_bytes, stream);
+}
+
+extern "C" int dr4sr_table_grad_sharded(const float* dx0_packed, const float* q_packed, const float* dscore,
+                                        const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
+                                        const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                                        int32_t D, const dr4sr_shard_map* map, float* pos_grad, void* ws, size_t ws_bytes,
+                                        dr4sr_stream_t stream) {
+  ShardView gv;
+  if (!shard_view_from(map, &gv)) return DR4SR_EINVAL;
+  return table_grad_impl(dx0_packed, q_packed, dscore, in_item_id, item_id, neg_item, tok_off, row_seq, counts, B, L, D, gv, pos_grad,
+                         ws, ws_bytes, stream);
 }
 
 extern "C" int dr4sr_adam(float* p, float* g, float* m, float* v, int64_t n, int64_t step, float lr, float beta1, float beta2,

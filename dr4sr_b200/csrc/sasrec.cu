@@ -235,16 +235,19 @@ extern "C" size_t dr4sr_sasrec_workspace_bytes(const dr4sr_sasrec_cfg* c) {
   return carve(*c, nullptr).bytes;
 }
 
-extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, const float* params,
-                                const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
-                                const int32_t* counts, void* ws, size_t ws_bytes, int32_t train, float* q_packed,
-                                float* q_last, float* q_dense, dr4sr_stream_t stream) {
+static int sasrec_fwd_impl(const dr4sr_sasrec_cfg* c, const ShardView& tv, const float* params,
+                           const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                           const int32_t* counts, void* ws, size_t ws_bytes, int32_t train, float* q_packed,
+                           float* q_last, float* q_dense, dr4sr_stream_t stream) {
+  const float* table = tv.table[0];
   DR4SR_TRY(check_cfg(c));
   if (!table || !params || !in_item_id || !tok_off || !row_seq || !counts || !ws) return DR4SR_EINVAL;
   Workspace w = carve(*c, ws);
   if (ws_bytes < w.bytes) return DR4SR_EWORKSPACE;
   cudaStream_t st = as_stream(stream);
   const int T = c->B * c->L, D = c->D, F = c->F;
+  // a peer-sharded table is gathered by the fused forward only (the per-operator embedding kernel reads one local table)
+  if (tv.world > 1 && !(fused_enabled() && fused_fwd_supported(c->L, D, F, c->n_head))) return DR4SR_EINVAL;
   const bool tr = train != 0;
   const float p = c->dropout_p;
   const LayerOffsets lo = layer_offsets(D, F);
@@ -258,7 +261,7 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
     DR4SR_TRY(launch_fused_tiles(tok_off, c->B, w.fused_tiles, st));
     DR4SR_TRY(aux_join(sa, st));
     FusedFwdHost h{};
-    h.table = table; h.pos = pos; h.in_ids = in_item_id; h.tok_off = tok_off; h.row_seq = row_seq; h.tiles = w.fused_tiles;
+    h.table = tv; h.pos = pos; h.in_ids = in_item_id; h.tok_off = tok_off; h.row_seq = row_seq; h.tiles = w.fused_tiles;
     h.x0 = w.x0; h.B = c->B; h.L = c->L; h.n_layer = c->n_layer; h.ln_eps = c->ln_eps;
     h.d_embed = make_dropout(p, c->seed, c->step, SITE_EMBED, tr);
     for (int l = 0; l < c->n_layer; ++l) {
@@ -335,6 +338,24 @@ extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, c
   }
   DR4SR_TRY(dr4sr_unpack_rows(x, tok_off, c->B, c->L, D, q_last, q_dense, stream));
   return DR4SR_OK;
+}
+
+extern "C" int dr4sr_sasrec_fwd(const dr4sr_sasrec_cfg* c, const float* table, const float* params,
+                                const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                                const int32_t* counts, void* ws, size_t ws_bytes, int32_t train, float* q_packed,
+                                float* q_last, float* q_dense, dr4sr_stream_t stream) {
+  if (!c || !table) return DR4SR_EINVAL;
+  return sasrec_fwd_impl(c, shard_view_local(table, nullptr, c->N), params, in_item_id, tok_off, row_seq, counts, ws, ws_bytes, train,
+                         q_packed, q_last, q_dense, stream);
+}
+
+extern "C" int dr4sr_sasrec_fwd_sharded(const dr4sr_sasrec_cfg* c, const dr4sr_shard_map* map, const float* params,
+                                        const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                                        const int32_t* counts, void* ws, size_t ws_bytes, int32_t train, float* q_packed,
+                                        float* q_last, float* q_dense, dr4sr_stream_t stream) {
+  ShardView tv;
+  if (!c || !shard_view_from(map, &tv) || tv.lo[tv.world] != c->N) return DR4SR_EINVAL;
+  return sasrec_fwd_impl(c, tv, params, in_item_id, tok_off, row_seq, counts, ws, ws_bytes, train, q_packed, q_last, q_dense, stream);
 }
 
 static int sasrec_bwd_impl(const dr4sr_sasrec_cfg* c, const float* table, const float* params,

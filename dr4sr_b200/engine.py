@@ -125,6 +125,14 @@ class SASRecEngine:
         cfg = self.cfg(B)
         b.fwd_train, b.fwd_step = bool(train), self.step
         self.fwd_token += 1                 # the workspace now holds THIS forward's activations (stale backwards are refused)
+        if hasattr(table, 'cmap'):          # row-sharded table over peer memory (dr4sr_b200/peer.py)
+            if self._name != 'dr4sr_sasrec':
+                raise _lib.Dr4srError('the peer-sharded table is implemented for SASRec; use enable_sharded_table for ' + self._name)
+            check(self.lib.dr4sr_sasrec_fwd_sharded(C.byref(cfg), table.ref(), _p(_req(flat, torch.float32, 'params')), _p(in_ids),
+                                                    _p(b.tok_off), _p(b.row_seq), _p(b.counts), _p(b.ws), b.ws.numel(),
+                                                    1 if train else 0, _p(b.q_packed), _p(b.q_last) if want_last else None,
+                                                    _p(q_dense), _stream()), 'dr4sr_sasrec_fwd_sharded')
+            return b.q_packed
         check(self._fn_fwd(C.byref(cfg), _p(_req(table, torch.float32, 'table')),
                                         _p(_req(flat, torch.float32, 'params')), _p(in_ids), _p(b.tok_off), _p(b.row_seq),
                                         _p(b.counts), _p(b.ws), b.ws.numel(), 1 if train else 0, _p(b.q_packed),
@@ -138,6 +146,12 @@ class SASRecEngine:
         neg_item = _req(neg_item, torch.int64, 'neg_item')
         B = item_id.size(0)
         q = b.q_packed if q_packed is None else q_packed
+        if hasattr(table, 'cmap'):
+            check(self.lib.dr4sr_score_loss_sharded(self.loss_kind, _p(q), table.ref(), _p(item_id), _p(neg_item), _p(b.tok_off),
+                                                    _p(b.row_seq), _p(b.counts), B, self.L, self.D, _p(loss_weight), _p(upstream),
+                                                    _p(b.loss_pos), _p(b.dscore), _p(b.dq) if want_grad else None, _stream()),
+                  'dr4sr_score_loss_sharded')
+            return b.loss_pos
         check(self.lib.dr4sr_score_loss(self.loss_kind, _p(q), _p(table), _p(item_id), _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
                                        B, self.L, self.D, _p(loss_weight), _p(upstream), _p(b.loss_pos), _p(b.dscore),
                                        _p(b.dq) if want_grad else None, _stream()), 'dr4sr_score_loss')
@@ -166,7 +180,8 @@ class SASRecEngine:
             cfg.dropout_p = 0.0
         dq = b.dq if dq is None else dq
         fn = self._fn_bwd_async if (defer_join and getattr(self, '_fn_bwd_async', None) is not None) else self._fn_bwd
-        check(fn(C.byref(cfg), _p(table), _p(flat), _p(in_ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
+        tptr = None if hasattr(table, 'cmap') else _p(table)       # (the backward never reads the table)
+        check(fn(C.byref(cfg), tptr, _p(flat), _p(in_ids), _p(b.tok_off), _p(b.row_seq), _p(b.counts),
                                         _p(b.ws), b.ws.numel(), _p(dq), _p(grads_flat), _p(b.dx0), _stream()), self._name + '_bwd')
         return b.dx0
 
@@ -177,6 +192,12 @@ class SASRecEngine:
     def table_grad(self, b: _Buffers, in_ids: torch.Tensor, item_id: Optional[torch.Tensor], neg_item: Optional[torch.Tensor],
                    table_grad: torch.Tensor, pos_grad: Optional[torch.Tensor], with_dx0: bool = True) -> None:
         B = in_ids.size(0)
+        if hasattr(table_grad, 'cmap'):     # peer-sharded accumulator: gradient rows are added in the owner's HBM
+            check(self.lib.dr4sr_table_grad_sharded(_p(b.dx0) if with_dx0 else None, _p(b.q_packed), _p(b.dscore), _p(in_ids),
+                                                    _p(item_id), _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L,
+                                                    self.D, table_grad.ref(), _p(pos_grad), _p(self._tg_ws), self._tg_ws.numel(),
+                                                    _stream()), 'dr4sr_table_grad_sharded')
+            return
         check(self.lib.dr4sr_table_grad(_p(b.dx0) if with_dx0 else None, _p(b.q_packed), _p(b.dscore), _p(in_ids), _p(item_id),
                                         _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L, self.D, self.N,
                                         _p(table_grad), _p(pos_grad), _p(self._tg_ws), self._tg_ws.numel(), _stream()),

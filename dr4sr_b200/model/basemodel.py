@@ -93,6 +93,7 @@ class BaseModel(nn.Module):
         # config['train']['table_shard'] = (rank, world): this process holds rows [lo, hi) of the item table only
         # (multi-GPU, see dr4sr_b200/sharded.py); absent => the whole table, as in the reference (basemodel.py:42)
         self._shard = None
+        self._peer = None
         self._shard_rows = None
         ts = config['train'].get('table_shard')
         if ts is not None:
@@ -240,13 +241,37 @@ class BaseModel(nn.Module):
         assert (self._shard.lo, self._shard.hi) == tuple(self._shard_rows)
         self._sync_replicas(group, table=False)           # the encoder is replicated; each rank keeps its own table rows
 
+    def enable_peer_table(self, group) -> None:
+        """Row-sharded item table over peer memory (config['train']['table_shard'] must have sized the embedding as this
+        rank's shard): kernels read rows / add gradient rows directly in the owner's HBM over NVLink, Adam runs on the shard;
+        the encoder stays data parallel.  See dr4sr_b200/peer.py.  One backward per optimizer step."""
+        from ..peer import PeerTable
+        from ..sharded import ShardedTable
+        if self._shard_rows is None:
+            raise _engine._lib.Dr4srError("enable_peer_table needs config['train']['table_shard'] = (rank, world)")
+        self._dp_group = group
+        self._sync_replicas(group, table=False)
+        self._table_grad.zero_()
+        if self._table_group is not None:
+            self._table_group.dirty = False
+        self._peer = PeerTable(self.num_items, self.embed_dim, group, self.item_embedding.weight.data, self._table_grad)
+        self._peer_eval = ShardedTable(self.num_items, self.embed_dim, group, self.item_embedding.weight.device)   # top-k merge only
+
     def _rows_for(self, bufs, in_ids, item_id, neg):
-        """(table, in_ids, item_id, neg) the kernels run on: the parameter itself, or the staged local rows."""
+        """(table, in_ids, item_id, neg) the kernels run on: the parameter itself, the peer-sharded table, or the staged
+        local rows of the all-to-all variant."""
+        if self._peer is not None:
+            self._peer.check_unmoved(self.item_embedding.weight.data, self._table_grad)
+            return self._peer, in_ids, item_id, neg
         if self._shard is None:
             return self.item_embedding.weight.data, in_ids, item_id, neg
         return self._shard.fetch(self.item_embedding.weight.data, bufs, in_ids, item_id, neg)
 
-    def _scatter_target(self) -> torch.Tensor:
+    def _scatter_target(self):
+        if self._peer is not None:            # cleared by the Adam pass only: other ranks add to this shard at any time of the step
+            if self._table_group is not None:
+                self._table_group.dirty = True
+            return self._peer
         return self._table_grad_buffer() if self._shard is None else self._shard.local_grad()
 
     def _finish_table_grad(self, tg: torch.Tensor) -> None:
@@ -275,7 +300,11 @@ class BaseModel(nn.Module):
         tn = self._table_grad.numel()
         if loss is not None:
             self._comm[-1:].copy_(loss.detach().view(1))
-        if self._shard is None and tg is self._table_grad:
+        if self._peer is not None:
+            # the rows were added in their owners' HBM by the scatter kernel; this all-reduce is also the barrier
+            # "every rank's scatter has finished" that the Adam pass on the shard needs
+            dist.all_reduce(self._comm[tn:], op=dist.ReduceOp.SUM, group=grp)
+        elif self._shard is None and tg is self._table_grad:
             dist.all_reduce(self._comm, op=dist.ReduceOp.SUM, group=grp)
         else:
             self._finish_table_grad(tg)
@@ -346,9 +375,10 @@ class BaseModel(nn.Module):
     def topk(self, batch, k, user_h=None):
         query = self.forward(batch)
         dead = self._item_dead(self.eval_domain)
-        if self._shard is not None:
+        sh = self._shard if self._shard is not None else getattr(self, '_peer_eval', None) if self._peer is not None else None
+        if sh is not None:
             lo, hi = self._shard_rows
-            return self._shard.topk(_engine.topk, query, self.item_embedding.weight.data, dead[lo:hi].contiguous(), user_h, k)
+            return sh.topk(_engine.topk, query, self.item_embedding.weight.data, dead[lo:hi].contiguous(), user_h, k)
         return _engine.topk(query, self.item_embedding.weight.data, dead, user_h, k)
 
     def set_eval_domain(self, domain):

@@ -73,6 +73,8 @@ class SASRec(BaseModel):
         eng = self.engine
         in_ids = batch['in_' + self.fiid]
         b = eng.prep(batch['seqlen'], None)
+        if self._peer is not None:
+            self._peer.barrier()              # rows are read from the other ranks' shards: every rank's last update is done
         table, in_ids, _, _ = self._rows_for(b, in_ids, None, None)
         if self.training or not need_pooling:
             q_dense = torch.empty(in_ids.size(0), eng.L, eng.D, dtype=torch.float32, device=in_ids.device)
@@ -87,6 +89,9 @@ class SASRec(BaseModel):
         neg = neg.view(item_id.shape)
         b = eng.prep(batch['seqlen'], item_id)
         n_work = self._dp_count_async(b.counts[1:2])   # data parallel: normalise by the global number of valid targets
+        if n_work is not None and self._peer is not None:
+            n_work.wait()                     # peer-sharded table: also the barrier "every rank's Adam pass is done" for the gathers
+            n_work = None
         if self.training:
             eng.step += 1
         q_dense = None

@@ -20,7 +20,7 @@ def _rel(a: torch.Tensor, b: torch.Tensor) -> float:
 
 
 def sharded_parity_check(group, dev: torch.device, model_name: str = 'SASRec', N: int = 5003, D: int = 128, B: int = 24,
-                         k: int = 100) -> Dict[str, float]:
+                         k: int = 100, mode: str = 'a2a') -> Dict[str, float]:
     """-> {'loss_rel', 'grad_rel', 'table_grad_rel', 'table_after_adam_abs', 'flat_after_adam_abs', 'topk_scores_rel',
     'topk_ids_equal'} maximised (minimised for topk_ids_equal) over the ranks of `group`."""
     from .data.synthetic import synthetic_batch
@@ -48,7 +48,10 @@ def sharded_parity_check(group, dev: torch.device, model_name: str = 'SASRec', N
     sh = build(True)
     lo, hi = sh._shard_rows
     sh.item_embedding.weight.data.copy_(ref.item_embedding.weight.data[lo:hi])
-    sh.enable_sharded_table(group)                   # broadcasts rank 0's encoder (identical on every rank: same seed)
+    if mode == 'peer':                               # rows read / gradient rows added directly in the owner's HBM (peer memory)
+        sh.enable_peer_table(group)
+    else:                                            # rows exchanged by all-to-all
+        sh.enable_sharded_table(group)               # (both broadcast rank 0's encoder: identical on every rank, same seed)
     sh._flat.copy_(ref._flat)
     sh.train()
     mine = split_batch(full, rank, world)
@@ -83,7 +86,7 @@ def sharded_parity_check(group, dev: torch.device, model_name: str = 'SASRec', N
     t = torch.tensor([errs[k_] if k_ != 'topk_ids_equal' else -errs[k_] for k_ in keys], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     out = {k_: (float(v) if k_ != 'topk_ids_equal' else -float(v)) for k_, v in zip(keys, t.tolist())}
-    out.update(model=model_name, world=world, num_items=N, batch_per_rank=B)
+    out.update(model=model_name, world=world, num_items=N, batch_per_rank=B, mode=mode)
     del ref, sh
     torch.cuda.empty_cache()
     return out

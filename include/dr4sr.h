@@ -46,6 +46,10 @@ DR4SR_API int dr4sr_abi_version(void);
 /* last CUDA error string seen by this thread's most recent failing call ("" if none) */
 DR4SR_API const char* dr4sr_last_cuda_error(void);
 
+/* Multi-GPU, peer memory: lets kernels launched on the CURRENT device dereference memory of `peer_device` (item-table
+ * shards of the other ranks, mapped through CUDA IPC) over NVLink.  Idempotent; DR4SR_EINVAL when the pair has no P2P path. */
+DR4SR_API int dr4sr_enable_peer_access(int peer_device);
+
 /* Measurement hooks (bench / profiling only; not on the product path).
  * dr4sr_launch_count: kernels launched by this library since load.
  * dr4sr_prof_enable(1): bracket every launcher with CUDA events on its stream; dr4sr_prof_collect waits
@@ -257,7 +261,42 @@ DR4SR_API int dr4sr_table_grad(const float* dx0_packed, const float* q_packed, c
                      dr4sr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Row-sharded item table (multi-GPU; no reference counterpart -- the reference is single-device).
+ * Row-sharded item table over PEER MEMORY (multi-GPU, one process per GPU; no reference counterpart -- the reference is
+ * single-device).  Rank r owns rows [lo[r], lo[r+1]) of E and of its gradient accumulator G; every rank maps the other
+ * ranks' shards into its address space (CUDA IPC opened in the local device's context + dr4sr_enable_peer_access) and
+ * passes the resulting pointers here.  The kernels then read E rows and `red.global.add` gradient rows directly in the
+ * owner's HBM over NVLink / NVSwitch: the row exchange is part of the gather / scatter kernels themselves, there is no
+ * collective, no request planning and no host synchronisation (measured on 2 x B200: 550 GB/s of 512-byte row gathers
+ * and 530 GB/s of 512-byte vector atomics per direction, profiles/r2_p2p_probe.md).  The caller orders the steps
+ * across ranks (gathers after every rank's Adam, Adam after every rank's scatter) with stream-ordered barriers.
+ *   world <= 8;  table[r] / grad[r]: base of rank r's shard (row lo[r] at offset 0);  lo[world] = N.
+ * A null map (or world == 1) everywhere below means "the whole table is local". */
+#define DR4SR_MAX_SHARDS 8
+typedef struct {
+  const float* table[DR4SR_MAX_SHARDS];
+  float* grad[DR4SR_MAX_SHARDS];
+  int64_t lo[DR4SR_MAX_SHARDS + 1];
+  int32_t world;
+  int32_t rank;
+} dr4sr_shard_map;
+/* dr4sr_sasrec_fwd / dr4sr_score_loss / dr4sr_table_grad with the table (resp. its gradient) given as a shard map. */
+DR4SR_API int dr4sr_sasrec_fwd_sharded(const dr4sr_sasrec_cfg* cfg, const dr4sr_shard_map* map, const float* params,
+                     const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
+                     const int32_t* counts, void* ws, size_t ws_bytes, int32_t train,
+                     float* q_packed, float* q_last, float* q_dense, dr4sr_stream_t stream);
+DR4SR_API int dr4sr_score_loss_sharded(int32_t kind, const float* q_packed, const dr4sr_shard_map* map, const int64_t* item_id,
+                     const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B,
+                     int32_t L, int32_t D, const float* loss_weight, const float* upstream, float* loss_pos, float* dscore,
+                     float* dq_packed, dr4sr_stream_t stream);
+DR4SR_API int dr4sr_table_grad_sharded(const float* dx0_packed, const float* q_packed, const float* dscore,
+                     const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
+                     const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                     int32_t D, const dr4sr_shard_map* map, float* pos_grad, void* ws, size_t ws_bytes,
+                     dr4sr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Row-sharded item table, all-to-all variant (the rows travel through NCCL; kept for GRU4Rec and as the fallback when the
+ * GPUs have no peer path).
  * Rank r owns rows [lo_r, hi_r) of E (balanced contiguous ranges: the first num_rows % world ranks hold one
  * extra row).  dr4sr_shard_plan turns the live slots of a batch into row requests bucketed by owner:
  *   request 3*row+k of packed row `row`: k=0 input id, k=1 positive target, k=2 negative (targets only

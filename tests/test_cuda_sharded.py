@@ -24,7 +24,7 @@ def _rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
-def _worker(rank, world, port, model_name, out):
+def _worker(rank, world, port, model_name, mode, out):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
@@ -32,26 +32,26 @@ def _worker(rank, world, port, model_name, out):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     try:
         from dr4sr_b200.parity import sharded_parity_check
-        out[rank] = sharded_parity_check(dist.group.WORLD, dev, model_name)
+        out[rank] = sharded_parity_check(dist.group.WORLD, dev, model_name, mode=mode)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('model_name', ['SASRec', 'GRU4Rec'])
-def test_sharded_table_equals_single_process(model_name):
+@pytest.mark.parametrize('model_name,mode', [('SASRec', 'peer'), ('SASRec', 'a2a'), ('GRU4Rec', 'a2a')])
+def test_sharded_table_equals_single_process(model_name, mode):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip('needs >= 2 GPUs')
     world, port = 2, _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, model_name, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, model_name, mode, out), nprocs=world, join=True)
     res = dict(out)
     assert set(res) == {0, 1}
-    print(model_name, res[0])
+    print(model_name, mode, res[0])
     for r, e in res.items():
         assert e['loss_rel'] < 1e-5, (r, e)
-        assert e['grad_rel'] < 2e-4, (r, e)
-        assert e['table_grad_rel'] < 2e-4, (r, e)
+        assert e['grad_rel'] < 5e-6, (r, e)                 # measured 3e-7 (summation order of the all-reduce)
+        assert e['table_grad_rel'] < 5e-6, (r, e)            # measured 5e-7 (order of the row atomics)
         assert e['table_after_adam_abs'] < 1e-4 and e['flat_after_adam_abs'] < 1e-4, (r, e)
         assert e['topk_scores_rel'] < 1e-6, (r, e)
         assert e['topk_ids_equal'] == 1.0, (r, e)          # same parameters, same kernels: ids must be EQUAL
