@@ -111,7 +111,10 @@ class SASRec(BaseModel):
         late = bool(reduce and fused_grad and getattr(self, '_dp_group', None) is not None)
         if reduce and not late:
             self._dp_sum(loss)
-        return loss, q_dense, (b, table, in_ids, item_id, neg, fused_grad, loss if late else None)
+        # (a detached alias of the same storage: the returned tensor itself would close the cycle loss -> grad_fn -> ctx.state ->
+        # loss, and the step's tensors would then wait for the cyclic GC instead of being freed by reference count -- measured:
+        # sporadic cudaMallocs of the growing pool, 2 - 150 ms each with peer mappings enabled)
+        return loss, q_dense, (b, table, in_ids, item_id, neg, fused_grad, loss.detach() if late else None)
 
     def _step_backward(self, state, reduce, dloss, dquery) -> None:
         eng = self.engine

@@ -54,4 +54,5 @@ def test_sharded_table_equals_single_process(model_name, mode):
         assert e['table_grad_rel'] < 5e-6, (r, e)            # measured 5e-7 (order of the row atomics)
         assert e['table_after_adam_abs'] < 1e-4 and e['flat_after_adam_abs'] < 1e-4, (r, e)
         assert e['topk_scores_rel'] < 1e-6, (r, e)
-        assert e['topk_ids_equal'] == 1.0, (r, e)          # same parameters, same kernels: ids must be EQUAL
+        assert e['topk_ids_equal'] == 1.0, (r, e)          # same parameters, same kernels, same queries: ids must be EQUAL
+        assert e['step_freed_by_refcount'] == 1.0, (r, e)  # no reference cycle through the autograd node
