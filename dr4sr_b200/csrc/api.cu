@@ -72,6 +72,48 @@ int aux_join(cudaStream_t aux, cudaStream_t st) {
   }
   return DR4SR_OK;
 }
+// Background stream: one longer kernel that may run under everything the main stream does until bg_join (the scatter-add of
+// the target / negative gradient rows runs under the whole encoder backward).  Same fork / join protocol, its own stream, so
+// the short kernels of the auxiliary stream never queue behind it.
+struct BgStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false, pending = false; };
+static BgStream& bg_stream() {
+  static BgStream per_dev[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  BgStream& x = per_dev[dev & 63];
+  if (!x.ok) {
+    bool good = cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) == cudaSuccess;
+    x.ok = good;
+  }
+  return x;
+}
+cudaStream_t bg_fork(cudaStream_t st) {
+  BgStream& x = bg_stream();
+  if (!x.ok || cudaEventRecord(x.fork, st) != cudaSuccess || cudaStreamWaitEvent(x.s, x.fork, 0) != cudaSuccess) return st;
+  return x.s;
+}
+int bg_mark(cudaStream_t bg, cudaStream_t st) {
+  if (bg == st) return DR4SR_OK;
+  BgStream& x = bg_stream();
+  if (cudaEventRecord(x.join, bg) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "background stream record");
+    return DR4SR_ECUDA;
+  }
+  x.pending = true;
+  return DR4SR_OK;
+}
+int bg_join(cudaStream_t st) {
+  BgStream& x = bg_stream();
+  if (!x.ok || !x.pending) return DR4SR_OK;
+  x.pending = false;
+  if (cudaStreamWaitEvent(st, x.join, 0) != cudaSuccess) {
+    set_cuda_error(cudaGetLastError(), "background stream join");
+    return DR4SR_ECUDA;
+  }
+  return DR4SR_OK;
+}
 }  // namespace dr4sr
 
 using namespace dr4sr;

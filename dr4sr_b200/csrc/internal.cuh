@@ -7,6 +7,10 @@ namespace dr4sr {
 // auxiliary stream for short independent kernels  [api.cu]
 cudaStream_t aux_fork(cudaStream_t st);
 int aux_join(cudaStream_t aux, cudaStream_t st);
+// background stream for one longer kernel that overlaps the main stream until bg_join  [api.cu]
+cudaStream_t bg_fork(cudaStream_t st);
+int bg_mark(cudaStream_t bg, cudaStream_t st);
+int bg_join(cudaStream_t st);
 
 constexpr int kLnBwdBlocks = 2 * kNumSMs;   // CTAs (= column-partial slices) of the LayerNorm backward kernels
 

@@ -357,6 +357,40 @@ extern "C" int dr4sr_table_grad_sharded(const float* dx0_packed, const float* q_
                          ws, ws_bytes, stream);
 }
 
+// The target / negative rows of the scatter-add depend on the loss kernel only (ds, q), not on the encoder backward: queued on
+// the background stream they run under it; dr4sr_table_grad_targets_join makes `stream` wait for them.
+static int table_grad_targets_impl(const float* q_packed, const float* dscore, const int64_t* item_id, const int64_t* neg_item,
+                                   const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                                   int32_t D, const ShardView& gv, dr4sr_stream_t stream) {
+  if (!q_packed || !dscore || !item_id || !neg_item || !tok_off || !row_seq || !counts || !gv.grad[0] || D % 4) return DR4SR_EINVAL;
+  cudaStream_t st = as_stream(stream);
+  cudaStream_t sb = bg_fork(st);
+  const int T_cap = B * L;
+  const int blocks = ceil_div(T_cap, 8) < 8 * kNumSMs ? ceil_div(T_cap, 8) : 8 * kNumSMs;
+  {
+    ProfScope prof("table_grad_targets", sb);
+    table_grad_kernel<<<blocks, 256, 0, sb>>>(nullptr, q_packed, dscore, item_id, item_id, neg_item, tok_off, row_seq, counts, L, D, gv);
+    DR4SR_LAUNCH_CHECK("table_grad_kernel (targets)");
+  }
+  return bg_mark(sb, st);
+}
+extern "C" int dr4sr_table_grad_targets_async(const float* q_packed, const float* dscore, const int64_t* item_id,
+                                              const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq,
+                                              const int32_t* counts, int32_t B, int32_t L, int32_t D, int64_t N, float* table_grad,
+                                              dr4sr_stream_t stream) {
+  return table_grad_targets_impl(q_packed, dscore, item_id, neg_item, tok_off, row_seq, counts, B, L, D,
+                                 shard_view_local(nullptr, table_grad, N), stream);
+}
+extern "C" int dr4sr_table_grad_targets_async_sharded(const float* q_packed, const float* dscore, const int64_t* item_id,
+                                                      const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq,
+                                                      const int32_t* counts, int32_t B, int32_t L, int32_t D,
+                                                      const dr4sr_shard_map* map, dr4sr_stream_t stream) {
+  ShardView gv;
+  if (!shard_view_from(map, &gv)) return DR4SR_EINVAL;
+  return table_grad_targets_impl(q_packed, dscore, item_id, neg_item, tok_off, row_seq, counts, B, L, D, gv, stream);
+}
+extern "C" int dr4sr_table_grad_targets_join(dr4sr_stream_t stream) { return bg_join(as_stream(stream)); }
+
 extern "C" int dr4sr_adam(float* p, float* g, float* m, float* v, int64_t n, int64_t step, float lr, float beta1, float beta2,
                           float eps, float weight_decay, int32_t zero_grad, dr4sr_stream_t stream) {
   if (!p || !g || !m || !v || n < 0 || step < 1) return DR4SR_EINVAL;

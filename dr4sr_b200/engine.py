@@ -189,6 +189,22 @@ class SASRecEngine:
         if getattr(self, '_fn_bwd_async', None) is not None:
             check(self.lib.dr4sr_sasrec_bwd_join(_stream()), 'dr4sr_sasrec_bwd_join')
 
+    def table_grad_targets_async(self, b: _Buffers, item_id: torch.Tensor, neg_item: torch.Tensor, table_grad) -> None:
+        """dE[item_id] += ds+ q, dE[neg] += ds- q on the library's background stream (runs under the encoder backward); pair with
+        table_grad(..., item_id=None, neg_item=None) and table_grad_join()."""
+        B = item_id.size(0)
+        if hasattr(table_grad, 'cmap'):
+            check(self.lib.dr4sr_table_grad_targets_async_sharded(_p(b.q_packed), _p(b.dscore), _p(item_id), _p(neg_item), _p(b.tok_off),
+                                                                  _p(b.row_seq), _p(b.counts), B, self.L, self.D, table_grad.ref(),
+                                                                  _stream()), 'dr4sr_table_grad_targets_async_sharded')
+            return
+        check(self.lib.dr4sr_table_grad_targets_async(_p(b.q_packed), _p(b.dscore), _p(item_id), _p(neg_item), _p(b.tok_off), _p(b.row_seq),
+                                                      _p(b.counts), B, self.L, self.D, self.N, _p(table_grad), _stream()),
+              'dr4sr_table_grad_targets_async')
+
+    def table_grad_join(self) -> None:
+        check(self.lib.dr4sr_table_grad_targets_join(_stream()), 'dr4sr_table_grad_targets_join')
+
     def table_grad(self, b: _Buffers, in_ids: torch.Tensor, item_id: Optional[torch.Tensor], neg_item: Optional[torch.Tensor],
                    table_grad: torch.Tensor, pos_grad: Optional[torch.Tensor], with_dx0: bool = True) -> None:
         B = in_ids.size(0)

@@ -128,10 +128,14 @@ class SASRec(BaseModel):
         if dquery is not None:
             valid = torch.arange(eng.L, device=dquery.device).view(1, -1) < batch_len(b)
             b.dq[: int(b.counts[0])] += dquery[valid]
-        # the weight gradients finish on the library's side stream while the embedding scatter-add runs here
-        eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad, defer_join=True)
+        # the target / negative rows of the embedding gradient need ds and q only: their scatter-add (NVLink atomics into the
+        # owners' shards when the table is peer-sharded) runs on the background stream under the whole encoder backward; the
+        # weight gradients finish on the library's side stream while the input rows are scattered here
         tg = self._scatter_target()
-        eng.table_grad(b, in_ids, item_id, neg, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
+        eng.table_grad_targets_async(b, item_id, neg, tg)
+        eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad, defer_join=True)
+        eng.table_grad(b, in_ids, None, None, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
+        eng.table_grad_join()
         eng.join_bwd()
         if getattr(self, '_dp_group', None) is not None:
             self._reduce_grads(tg, late_loss)

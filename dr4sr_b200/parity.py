@@ -83,6 +83,10 @@ def sharded_parity_check(group, dev: torch.device, model_name: str = 'SASRec', N
     errs['flat_after_adam_abs'] = float((sh._flat - ref._flat).abs().max())
 
     ref.eval(); sh.eval()
+    # one set of parameters for everybody: the ranks' single-process models took their Adam step independently (float atomics
+    # in the scatter-add: equal to round-off only), and the sharded table is assembled from every rank's slice
+    dist.broadcast(ref.item_embedding.weight.data, src=dist.get_global_rank(group, 0), group=group)
+    dist.broadcast(ref._flat, src=dist.get_global_rank(group, 0), group=group)
     sh.item_embedding.weight.data.copy_(ref.item_embedding.weight.data[lo:hi])   # identical parameters for the id check
     sh._flat.copy_(ref._flat)
     ev = {k_: v.to(dev) for k_, v in synthetic_batch(world * B, 50, N, seed=4, eval_mode=True, with_neg=False).items()}

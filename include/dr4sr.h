@@ -279,6 +279,18 @@ typedef struct {
   int32_t world;
   int32_t rank;
 } dr4sr_shard_map;
+/* The target / negative part of dr4sr_table_grad (dE[item_id] += ds+ q, dE[neg] += ds- q), queued on the library's
+ * background stream behind everything enqueued on `stream` so far: it depends on the loss kernel only and runs under the
+ * encoder backward.  Follow with dr4sr_table_grad(dx0, NULL, NULL, in_item_id, NULL, NULL, ...) for the input rows and
+ * dr4sr_table_grad_targets_join(stream), after which `stream` is ordered behind the background kernel.  The sum of the
+ * two calls is dr4sr_table_grad's result (float atomics: equal to summation order).  Reference: the autograd scatter of
+ * nn.Embedding's backward, model/basemodel.py:204-214 through torch. */
+DR4SR_API int dr4sr_table_grad_targets_async(const float* q_packed, const float* dscore, const int64_t* item_id,
+                                             const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq,
+                                             const int32_t* counts, int32_t B, int32_t L, int32_t D, int64_t N, float* table_grad,
+                                             dr4sr_stream_t stream);
+DR4SR_API int dr4sr_table_grad_targets_join(dr4sr_stream_t stream);
+
 /* dr4sr_sasrec_fwd / dr4sr_score_loss / dr4sr_table_grad with the table (resp. its gradient) given as a shard map. */
 DR4SR_API int dr4sr_sasrec_fwd_sharded(const dr4sr_sasrec_cfg* cfg, const dr4sr_shard_map* map, const float* params,
                      const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
@@ -293,6 +305,10 @@ DR4SR_API int dr4sr_table_grad_sharded(const float* dx0_packed, const float* q_p
                      const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
                      int32_t D, const dr4sr_shard_map* map, float* pos_grad, void* ws, size_t ws_bytes,
                      dr4sr_stream_t stream);
+DR4SR_API int dr4sr_table_grad_targets_async_sharded(const float* q_packed, const float* dscore, const int64_t* item_id,
+                                                     const int64_t* neg_item, const int32_t* tok_off, const int32_t* row_seq,
+                                                     const int32_t* counts, int32_t B, int32_t L, int32_t D,
+                                                     const dr4sr_shard_map* map, dr4sr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Row-sharded item table, all-to-all variant (the rows travel through NCCL; kept for GRU4Rec and as the fallback when the

@@ -1,0 +1,67 @@
+"""GPU test of the embedding-gradient scatter-add through the C ABI: one call (dr4sr_table_grad) == the split the training
+step uses (dr4sr_table_grad_targets_async on the background stream + input rows + join) == a float64 index_add of the same
+rows (reference: nn.Embedding's backward under model/basemodel.py:204-214).  Float atomics: equal up to summation order."""
+import pytest
+import torch
+
+from tests.helpers import check_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('B,L,D,N', [(64, 50, 128, 5000), (7, 9, 64, 300), (1024, 50, 128, 100_000)])
+def test_split_scatter_equals_single_call_and_index_add(B, L, D, N):
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dr4sr_b200 import _lib
+    from dr4sr_b200.engine import _p, _stream
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(B * 31 + L)
+    seqlen = torch.randint(1, L + 1, (B,), generator=g)
+    tok_off = torch.zeros(B + 1, dtype=torch.int32)
+    tok_off[1:] = seqlen.cumsum(0).int()
+    T = int(tok_off[-1])
+    row_seq = torch.repeat_interleave(torch.arange(B, dtype=torch.int32), seqlen)
+    live = torch.arange(L).view(1, -1) < seqlen.view(-1, 1)
+    in_ids = torch.randint(1, N, (B, L), generator=g) * live
+    item_id = torch.randint(1, N, (B, L), generator=g) * live
+    item_id[:, 0] *= (torch.rand(B, generator=g) < 0.8)        # some live slots without a target (id 0): no gradient
+    neg = torch.randint(1, N, (B, L), generator=g)
+    dx0 = torch.randn(T, D, generator=g)
+    q = torch.randn(T, D, generator=g)
+    ds = torch.randn(T, 2, generator=g)
+    counts = torch.tensor([T, int((item_id != 0).sum())], dtype=torch.int32)
+    d = {k: v.to(DEV) for k, v in dict(tok_off=tok_off, row_seq=row_seq, in_ids=in_ids, item_id=item_id, neg=neg, dx0=dx0, q=q, ds=ds,
+                                        counts=counts).items()}
+    ws = torch.empty(lib.dr4sr_table_grad_workspace_bytes(L, D), dtype=torch.uint8, device=DEV)
+
+    one = torch.zeros(N, D, device=DEV)
+    pos1 = torch.zeros(L, D, device=DEV)
+    _lib.check(lib.dr4sr_table_grad(_p(d['dx0']), _p(d['q']), _p(d['ds']), _p(d['in_ids']), _p(d['item_id']), _p(d['neg']), _p(d['tok_off']),
+                                    _p(d['row_seq']), _p(d['counts']), B, L, D, N, _p(one), _p(pos1), _p(ws), ws.numel(), _stream()), 'table_grad')
+    two = torch.zeros(N, D, device=DEV)
+    pos2 = torch.zeros(L, D, device=DEV)
+    _lib.check(lib.dr4sr_table_grad_targets_async(_p(d['q']), _p(d['ds']), _p(d['item_id']), _p(d['neg']), _p(d['tok_off']), _p(d['row_seq']),
+                                                  _p(d['counts']), B, L, D, N, _p(two), _stream()), 'targets_async')
+    _lib.check(lib.dr4sr_table_grad(_p(d['dx0']), None, None, _p(d['in_ids']), None, None, _p(d['tok_off']), _p(d['row_seq']), _p(d['counts']),
+                                    B, L, D, N, _p(two), _p(pos2), _p(ws), ws.numel(), _stream()), 'table_grad inputs')
+    _lib.check(lib.dr4sr_table_grad_targets_join(_stream()), 'join')
+    torch.cuda.synchronize()
+
+    # float64 index_add of the same rows
+    want = torch.zeros(N, D, dtype=torch.float64)
+    flat_in, flat_tg, flat_ng = in_ids[live], item_id[live], neg[live]
+    want.index_add_(0, flat_in, dx0.double() * (flat_in != 0).view(-1, 1))
+    has = (flat_tg != 0).view(-1, 1)
+    want.index_add_(0, flat_tg, q.double() * ds[:, :1].double() * has)
+    want.index_add_(0, flat_ng, q.double() * ds[:, 1:].double() * has)
+    want[0] = 0
+    scale = float(want.abs().max())
+    check_err(f'table_grad one call vs f64 index_add (B={B})', float((one.cpu().double() - want).abs().max()) / scale, 2e-6)
+    check_err(f'table_grad split vs f64 index_add (B={B})', float((two.cpu().double() - want).abs().max()) / scale, 2e-6)
+    assert torch.equal(pos1, pos2)                                # the positional reduction is deterministic
+    t_of = (torch.arange(T) - tok_off[row_seq.long()].long())
+    pw = torch.zeros(L, D, dtype=torch.float64).index_add_(0, t_of, dx0.double())
+    check_err(f'pos_grad vs f64 (B={B})', float((pos1.cpu().double() - pw).abs().max()) / float(pw.abs().max()), 2e-6)
+    assert float(one[0].abs().max()) == 0.0 and float(two[0].abs().max()) == 0.0      # padding row untouched
