@@ -12,6 +12,9 @@ cudaStream_t bg_fork(cudaStream_t st);
 int bg_mark(cudaStream_t bg, cudaStream_t st);
 int bg_join(cudaStream_t st);
 
+// positional gradient (deterministic column reduction of dx0)  [loss_table.cu]
+int launch_pos_grad(const float* dx0_packed, const int32_t* tok_off, int B, int L, int D, float* pos_grad, void* ws, cudaStream_t sa);
+
 constexpr int kLnBwdBlocks = 2 * kNumSMs;   // CTAs (= column-partial slices) of the LayerNorm backward kernels
 
 // attention over packed rows, one CTA per (sequence, head)  [attention.cu]

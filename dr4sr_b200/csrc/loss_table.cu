@@ -293,6 +293,27 @@ extern "C" int dr4sr_sum(const float* x, int64_t n, float* out, dr4sr_stream_t s
 
 extern "C" size_t dr4sr_table_grad_workspace_bytes(int32_t L, int32_t D) { return sizeof(float) * (size_t)kPosChunks * L * D; }
 
+namespace dr4sr {
+// dP[t] = sum_b dx0[(b, t)]: per-CTA partials in `ws` (dr4sr_table_grad_workspace_bytes), summed in a fixed order
+int launch_pos_grad(const float* dx0_packed, const int32_t* tok_off, int B, int L, int D, float* pos_grad, void* ws, cudaStream_t sa) {
+  float* partial = reinterpret_cast<float*>(ws);
+  const size_t smem = sizeof(float) * (size_t)L * D;
+  {
+    ProfScope prof("pos_grad", sa);
+    if (cudaFuncSetAttribute(pos_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      set_cuda_error(cudaGetLastError(), "pos_grad smem attribute");
+      return DR4SR_ECUDA;
+    }
+    pos_grad_kernel<<<kPosChunks, 256, smem, sa>>>(dx0_packed, tok_off, B, L, D, partial);
+    DR4SR_LAUNCH_CHECK("pos_grad_kernel");
+  }
+  ReduceTable tab{};
+  tab.seg[0] = ReduceSeg{partial, pos_grad, kPosChunks, (int64_t)L * D, L * D};
+  tab.count = 1;
+  return launch_reduce_segments(tab, sa);
+}
+}  // namespace dr4sr
+
 static int table_grad_impl(const float* dx0_packed, const float* q_packed, const float* dscore,
                            const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
                            const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
@@ -311,21 +332,7 @@ static int table_grad_impl(const float* dx0_packed, const float* q_packed, const
   if (with_pos) {
     if (!ws || ws_bytes < dr4sr_table_grad_workspace_bytes(L, D)) return DR4SR_EWORKSPACE;
     sa = aux_fork(st);
-    float* partial = reinterpret_cast<float*>(ws);
-    const size_t smem = sizeof(float) * (size_t)L * D;
-    {
-      ProfScope prof("pos_grad", sa);
-      if (cudaFuncSetAttribute(pos_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        set_cuda_error(cudaGetLastError(), "pos_grad smem attribute");
-        return DR4SR_ECUDA;
-      }
-      pos_grad_kernel<<<kPosChunks, 256, smem, sa>>>(dx0_packed, tok_off, B, L, D, partial);
-      DR4SR_LAUNCH_CHECK("pos_grad_kernel");
-    }
-    ReduceTable tab{};
-    tab.seg[0] = ReduceSeg{partial, pos_grad, kPosChunks, (int64_t)L * D, L * D};
-    tab.count = 1;
-    DR4SR_TRY(launch_reduce_segments(tab, sa));
+    DR4SR_TRY(launch_pos_grad(dx0_packed, tok_off, B, L, D, pos_grad, ws, sa));
   }
   {
   ProfScope prof("table_grad_scatter", st);

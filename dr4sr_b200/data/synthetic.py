@@ -12,11 +12,17 @@ import torch
 
 
 def synthetic_batch(batch_size: int, max_seq_len: int, num_items: int, seed: int = 0, layout: str = 'post',
-                    min_len: int = 1, with_neg: bool = True, eval_mode: bool = False) -> Dict[str, torch.Tensor]:
-    """seqlen ~ U{min_len..L}; ids ~ U{1..N-1}; negatives ~ U{1..N-1} (one per target slot)."""
+                    min_len: int = 1, with_neg: bool = True, eval_mode: bool = False, mean_len: float = 0.0) -> Dict[str, torch.Tensor]:
+    """seqlen ~ U{min_len..L} (or, with mean_len > 0, 1 + Geometric with that mean, clipped to L: the shape of the shipped
+    amazon-toys train_regen.pth, mean 2.25); ids ~ U{1..N-1}; negatives ~ U{1..N-1} (one per target slot)."""
     g = torch.Generator().manual_seed(seed)
     B, L, N = batch_size, max_seq_len, num_items
-    seqlen = torch.randint(min_len, L + 1, (B,), generator=g, dtype=torch.int64)
+    if mean_len > 0.0:
+        p = 1.0 / max(mean_len, 1.0 + 1e-6)                     # P(len = k) = p (1-p)^(k-1), k >= 1
+        u = torch.rand(B, generator=g, dtype=torch.float64).clamp_min(1e-12)
+        seqlen = (1 + torch.floor(torch.log(u) / torch.log(torch.tensor(1.0 - p, dtype=torch.float64)))).clamp(1, L).to(torch.int64)
+    else:
+        seqlen = torch.randint(min_len, L + 1, (B,), generator=g, dtype=torch.int64)
     x = torch.randint(1, N, (B, L + 1), generator=g, dtype=torch.int64)
     t = torch.arange(L).view(1, L)
     if layout == 'post':

@@ -52,6 +52,7 @@ class _Buffers:
 class SASRecEngine:
     """Kernels + workspaces of one SASRec encoder (reference model/sasrec.py:10-75)."""
     loss_kind = 0                       # DR4SR_LOSS_BCE; BaseModel._init_model sets it from config['model']['loss_fn']
+    deterministic_scatter = False       # config['train']['deterministic_scatter']: sorted warp-segmented reduction instead of atomics
 
     def __init__(self, num_items: int, embed_dim: int, max_seq_len: int, hidden_size: int, head_num: int,
                  layer_num: int, dropout_rate: float, layer_norm_eps: float, seed: int, device: torch.device) -> None:
@@ -202,6 +203,14 @@ class SASRecEngine:
                                                       _p(b.counts), B, self.L, self.D, self.N, _p(table_grad), _stream()),
               'dr4sr_table_grad_targets_async')
 
+    def _sorted_ws(self, B: int, rows: int) -> torch.Tensor:
+        cache = self.__dict__.setdefault('_tg_sorted', {})
+        ws = cache.get((B, rows))
+        if ws is None:
+            ws = cache[(B, rows)] = torch.empty(self.lib.dr4sr_table_grad_sorted_workspace_bytes(B, self.L, self.D, rows),
+                                                dtype=torch.uint8, device=self.device)
+        return ws
+
     def table_grad_join(self) -> None:
         check(self.lib.dr4sr_table_grad_targets_join(_stream()), 'dr4sr_table_grad_targets_join')
 
@@ -213,6 +222,13 @@ class SASRecEngine:
                                                     _p(item_id), _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L,
                                                     self.D, table_grad.ref(), _p(pos_grad), _p(self._tg_ws), self._tg_ws.numel(),
                                                     _stream()), 'dr4sr_table_grad_sharded')
+            return
+        if self.deterministic_scatter:      # sort by id + fixed-order segment sums: bit-reproducible gradients
+            rows = table_grad.size(0)
+            ws = self._sorted_ws(B, rows)
+            check(self.lib.dr4sr_table_grad_sorted(_p(b.dx0) if with_dx0 else None, _p(b.q_packed), _p(b.dscore), _p(in_ids), _p(item_id),
+                                                   _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L, self.D, rows,
+                                                   _p(table_grad), _p(pos_grad), _p(ws), ws.numel(), _stream()), 'dr4sr_table_grad_sorted')
             return
         check(self.lib.dr4sr_table_grad(_p(b.dx0) if with_dx0 else None, _p(b.q_packed), _p(b.dscore), _p(in_ids), _p(item_id),
                                         _p(neg_item), _p(b.tok_off), _p(b.row_seq), _p(b.counts), B, self.L, self.D, self.N,

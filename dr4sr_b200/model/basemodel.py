@@ -141,6 +141,7 @@ class BaseModel(nn.Module):
         self.optimizer = self._get_optimizers()
         self.loss_fn = self._get_loss_func()
         self.engine.loss_kind = {'bce': 0, 'bpr': 1}[self.loss_fn.kind]      # DR4SR_LOSS_* of include/dr4sr.h
+        self.engine.deterministic_scatter = bool(self.config['train'].get('deterministic_scatter', False))
 
     def _flatten(self) -> None:
         """Re-home the encoder parameters as views of one flat fp32 buffer (the C ABI's layout) and
@@ -249,6 +250,9 @@ class BaseModel(nn.Module):
         from ..sharded import ShardedTable
         if self._shard_rows is None:
             raise _engine._lib.Dr4srError("enable_peer_table needs config['train']['table_shard'] = (rank, world)")
+        if self.engine.deterministic_scatter:
+            raise _engine._lib.Dr4srError('deterministic_scatter is not available with the peer-memory table (gradient rows of several '
+                                          'ranks meet in the owner\'s HBM through float atomics); use the all-to-all or replicated layout')
         self._dp_group = group
         self._sync_replicas(group, table=False)
         self._table_grad.zero_()

@@ -132,10 +132,16 @@ class SASRec(BaseModel):
         # owners' shards when the table is peer-sharded) runs on the background stream under the whole encoder backward; the
         # weight gradients finish on the library's side stream while the input rows are scattered here
         tg = self._scatter_target()
-        eng.table_grad_targets_async(b, item_id, neg, tg)
+        split = not eng.deterministic_scatter          # (the sorted, bit-reproducible reduction takes all three row sets at once)
+        if split:
+            eng.table_grad_targets_async(b, item_id, neg, tg)
         eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad, defer_join=True)
-        eng.table_grad(b, in_ids, None, None, tg, self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D))
-        eng.table_grad_join()
+        pos = self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D)
+        if split:
+            eng.table_grad(b, in_ids, None, None, tg, pos)
+            eng.table_grad_join()
+        else:
+            eng.table_grad(b, in_ids, item_id, neg, tg, pos)
         eng.join_bwd()
         if getattr(self, '_dp_group', None) is not None:
             self._reduce_grads(tg, late_loss)

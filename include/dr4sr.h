@@ -279,6 +279,19 @@ typedef struct {
   int32_t world;
   int32_t rank;
 } dr4sr_shard_map;
+/* Deterministic variant of dr4sr_table_grad: the (item id, source row) entries of the step are sorted by id (stable radix
+ * sort) and every run of equal ids is reduced by warps in a fixed order -- a warp-segmented reduction, no float atomics, every
+ * row of table_grad has one writer.  Same arguments and result contract; two calls on the same inputs give bit-identical
+ * gradients, and a hot id (Zipf catalogs) costs run/16 row adds instead of `run` atomics serialised on one L2 line.
+ * D <= 256.  `ws` needs dr4sr_table_grad_sorted_workspace_bytes(B, L, D, N) bytes.  Reference: the index_put / embedding
+ * backward torch runs under model/basemodel.py:198 (which sorts, too). */
+DR4SR_API size_t dr4sr_table_grad_sorted_workspace_bytes(int32_t B, int32_t L, int32_t D, int64_t N);
+DR4SR_API int dr4sr_table_grad_sorted(const float* dx0_packed, const float* q_packed, const float* dscore,
+                                      const int64_t* in_item_id, const int64_t* item_id, const int64_t* neg_item,
+                                      const int32_t* tok_off, const int32_t* row_seq, const int32_t* counts, int32_t B, int32_t L,
+                                      int32_t D, int64_t N, float* table_grad, float* pos_grad, void* ws, size_t ws_bytes,
+                                      dr4sr_stream_t stream);
+
 /* The target / negative part of dr4sr_table_grad (dE[item_id] += ds+ q, dE[neg] += ds- q), queued on the library's
  * background stream behind everything enqueued on `stream` so far: it depends on the loss kernel only and runs under the
  * encoder backward.  Follow with dr4sr_table_grad(dx0, NULL, NULL, in_item_id, NULL, NULL, ...) for the input rows and

@@ -120,7 +120,7 @@ def sampled_scores(query: Tensor, table: Tensor, item_id: Tensor, neg_item: Tens
 # ----------------------------------------------------------------------------------------------
 def pool_origin(x: Tensor, seqlen: Tensor) -> Tensor:
     L = x.size(1)
-    dead = torch.arange(L).view(1, L, 1) >= seqlen.view(-1, 1, 1)
+    dead = torch.arange(L, device=x.device).view(1, L, 1) >= seqlen.view(-1, 1, 1)
     return x.masked_fill(dead, 0.0)
 
 
@@ -156,7 +156,7 @@ class _OracleBase(nn.Module):
         includes id 0) and at the user's history ids, then top-k."""
         q = self.forward(batch)
         score = q @ self.item_embedding.weight[: self.num_items].T
-        dead = torch.ones(1, self.num_items, dtype=torch.bool)
+        dead = torch.ones(1, self.num_items, dtype=torch.bool, device=score.device)
         if domain_items is None:
             dead[:, 1:] = False
         else:
@@ -199,8 +199,8 @@ class OracleSASRec(_OracleBase):
         enc = self.query_encoder
         ids = batch['in_item_id']
         L = ids.size(1)
-        x = enc.item_encoder(ids) + enc.position_emb(torch.arange(L)).unsqueeze(0)      # :42-46,64
-        causal = torch.triu(torch.ones(L, L, dtype=torch.bool), 1)                       # :58
+        x = enc.item_encoder(ids) + enc.position_emb(torch.arange(L, device=ids.device)).unsqueeze(0)      # :42-46,64
+        causal = torch.triu(torch.ones(L, L, dtype=torch.bool, device=ids.device), 1)                       # :58
         return enc.transformer_layer(src=enc.dropout(x), mask=causal, src_key_padding_mask=ids == 0)  # :65-68
 
     def forward(self, batch: Batch) -> Tensor:
@@ -227,7 +227,7 @@ def sasrec_layer_explicit(x: Tensor, key_is_pad: Tensor, w: Dict[str, Tensor], n
     qkv = x @ w['self_attn.in_proj_weight'].T + w['self_attn.in_proj_bias']
     q, k, v = (t.view(B, L, nhead, dh).transpose(1, 2) for t in qkv.split(D, dim=-1))
     s = (q @ k.transpose(-1, -2)) / math.sqrt(dh)
-    dead = torch.triu(torch.ones(L, L, dtype=torch.bool), 1).view(1, 1, L, L) | key_is_pad.view(B, 1, 1, L)
+    dead = torch.triu(torch.ones(L, L, dtype=torch.bool, device=x.device), 1).view(1, 1, L, L) | key_is_pad.view(B, 1, 1, L)
     a = torch.softmax(s.masked_fill(dead, -torch.inf), dim=-1)
     o = (a @ v).transpose(1, 2).reshape(B, L, D)
     o = o @ w['self_attn.out_proj.weight'].T + w['self_attn.out_proj.bias']
@@ -370,7 +370,7 @@ class OracleFMLP(_OracleBase):
     def encode(self, batch: Batch) -> Tensor:
         ids = batch['in_item_id']
         L = ids.size(1)
-        x = self.item_embedding(ids) + self.position_embeddings(torch.arange(L)).unsqueeze(0)   # fmlp.py:18-24
+        x = self.item_embedding(ids) + self.position_embeddings(torch.arange(L, device=ids.device)).unsqueeze(0)   # fmlp.py:18-24
         x = self.dropout(self.LayerNorm(x))                                                    # fmlp.py:25-26
         for blk in self.item_encoder.layer:
             x = blk(x)
@@ -386,7 +386,7 @@ def fmlp_filter_explicit(x: Tensor, complex_weight: Tensor) -> Tensor:
     B, L, D = x.shape
     W = torch.view_as_complex(complex_weight.contiguous())[0]              # [L//2+1, D]
     h = torch.fft.irfft(W, n=L, dim=0, norm='backward')                    # [L, D]
-    idx = (torch.arange(L).view(L, 1) - torch.arange(L).view(1, L)) % L    # [t, s]
+    idx = ((torch.arange(L).view(L, 1) - torch.arange(L).view(1, L)) % L).to(x.device)    # [t, s]
     K = h[idx]                                                             # [t, s, D]
     return torch.einsum('tsd,bsd->btd', K, x)
 

@@ -65,3 +65,98 @@ def test_split_scatter_equals_single_call_and_index_add(B, L, D, N):
     pw = torch.zeros(L, D, dtype=torch.float64).index_add_(0, t_of, dx0.double())
     check_err(f'pos_grad vs f64 (B={B})', float((pos1.cpu().double() - pw).abs().max()) / float(pw.abs().max()), 2e-6)
     assert float(one[0].abs().max()) == 0.0 and float(two[0].abs().max()) == 0.0      # padding row untouched
+
+
+def _scatter_inputs(B, L, D, N, seed, zipf=False):
+    g = torch.Generator().manual_seed(seed)
+    seqlen = torch.randint(1, L + 1, (B,), generator=g)
+    tok_off = torch.zeros(B + 1, dtype=torch.int32)
+    tok_off[1:] = seqlen.cumsum(0).int()
+    T = int(tok_off[-1])
+    row_seq = torch.repeat_interleave(torch.arange(B, dtype=torch.int32), seqlen)
+    live = torch.arange(L).view(1, -1) < seqlen.view(-1, 1)
+
+    def ids():
+        if zipf:                                                # Zipf(1.0) over 1..N-1: id 1 takes ~1/H(N) of all slots
+            w = 1.0 / torch.arange(1, N, dtype=torch.float64)
+            return (torch.multinomial(w, B * L, replacement=True, generator=g) + 1).view(B, L)
+        return torch.randint(1, N, (B, L), generator=g)
+    in_ids, item_id, neg = ids() * live, ids() * live, ids()
+    item_id[:, 0] *= (torch.rand(B, generator=g) < 0.8)
+    dx0, q, ds = torch.randn(T, D, generator=g), torch.randn(T, D, generator=g), torch.randn(T, 2, generator=g)
+    counts = torch.tensor([T, int((item_id != 0).sum())], dtype=torch.int32)
+    host = dict(tok_off=tok_off, row_seq=row_seq, in_ids=in_ids, item_id=item_id, neg=neg, dx0=dx0, q=q, ds=ds, counts=counts)
+    want = torch.zeros(N, D, dtype=torch.float64)
+    fi, ft, fn = in_ids[live], item_id[live], neg[live]
+    has = (ft != 0).view(-1, 1)
+    want.index_add_(0, fi, dx0.double() * (fi != 0).view(-1, 1))
+    want.index_add_(0, ft, q.double() * ds[:, :1].double() * has)
+    want.index_add_(0, fn, q.double() * ds[:, 1:].double() * has)
+    want[0] = 0
+    return host, want
+
+
+@pytest.mark.parametrize('B,L,D,N,zipf', [(64, 50, 128, 5000, False), (7, 9, 64, 300, False), (1024, 50, 128, 100_000, False),
+                                          (1024, 50, 128, 100_000, True), (256, 50, 64, 11_925, True), (3, 50, 128, 17, False)])
+def test_sorted_segment_reduction_is_exact_and_bit_reproducible(B, L, D, N, zipf):
+    """dr4sr_table_grad_sorted == float64 index_add (tighter than the atomic path on hot rows: fixed-shape sums), twice the
+    same bits, and the padding row stays untouched; Zipf ids put thousands of entries on one row (runs crossing many chunks)."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dr4sr_b200 import _lib
+    from dr4sr_b200.engine import _p, _stream
+    lib = _lib.lib()
+    host, want = _scatter_inputs(B, L, D, N, seed=B * 7 + N, zipf=zipf)
+    d = {k: v.to(DEV) for k, v in host.items()}
+    ws = torch.empty(lib.dr4sr_table_grad_sorted_workspace_bytes(B, L, D, N), dtype=torch.uint8, device=DEV)
+    outs = []
+    for _ in range(2):
+        tg = torch.zeros(N, D, device=DEV)
+        pos = torch.zeros(L, D, device=DEV)
+        ws.random_(0, 255)                                      # no dependence on workspace contents
+        _lib.check(lib.dr4sr_table_grad_sorted(_p(d['dx0']), _p(d['q']), _p(d['ds']), _p(d['in_ids']), _p(d['item_id']), _p(d['neg']),
+                                               _p(d['tok_off']), _p(d['row_seq']), _p(d['counts']), B, L, D, N, _p(tg), _p(pos), _p(ws),
+                                               ws.numel(), _stream()), 'table_grad_sorted')
+        torch.cuda.synchronize()
+        outs.append((tg, pos))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), 'not bit-reproducible'
+    scale = float(want.abs().max())
+    check_err(f'sorted table_grad vs f64 index_add (B={B}, N={N}, zipf={zipf})', float((outs[0][0].cpu().double() - want).abs().max()) / scale, 1e-6)
+    assert float(outs[0][0][0].abs().max()) == 0.0
+    # too small a workspace is an error, not a silent overrun
+    rc = lib.dr4sr_table_grad_sorted(_p(d['dx0']), _p(d['q']), _p(d['ds']), _p(d['in_ids']), _p(d['item_id']), _p(d['neg']), _p(d['tok_off']),
+                                     _p(d['row_seq']), _p(d['counts']), B, L, D, N, _p(outs[0][0]), None, _p(ws), 16, _stream())
+    assert rc != 0
+
+
+def test_deterministic_training_step_repeats_bit_for_bit():
+    """config['train']['deterministic_scatter']: two identical SASRec steps give identical table gradients and parameters
+    (the default atomic scatter agrees with them to round-off)."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    from dr4sr_b200.model.sasrec import SASRec
+    from dr4sr_b200.utils.config import SyntheticCatalog, default_config
+    N, D, B = 3001, 128, 96
+    batch = {k: v.to(DEV) for k, v in synthetic_batch(B, 50, N, seed=5).items()}
+
+    def run(det):
+        cfg = default_config('SASRec', model__embed_dim=D, model__dropout_rate=0.3, train__device=DEV)
+        cfg['train']['deterministic_scatter'] = det
+        torch.manual_seed(11)
+        m = SASRec(cfg, [SyntheticCatalog(N)] * 3)
+        m._init_model()
+        m.train()
+        for _ in range(2):
+            m.optimizer.zero_grad()
+            loss = m.training_step(batch)
+            loss.backward()
+            g = m.item_embedding.weight.grad.clone()
+            m.optimizer.step()
+        return g, m.item_embedding.weight.data.clone(), float(loss.detach())
+
+    g1, w1, l1 = run(True)
+    g2, w2, l2 = run(True)
+    assert torch.equal(g1, g2) and torch.equal(w1, w2) and l1 == l2
+    g3, w3, _ = run(False)
+    check_err('deterministic vs atomic scatter, table gradient', float((g1 - g3).abs().max() / g1.abs().max()), 5e-6)
