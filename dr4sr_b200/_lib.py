@@ -86,6 +86,7 @@ SIGNATURES = {
     'dr4sr_table_grad_targets_async': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p]),
     'dr4sr_table_grad_targets_async_sharded': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, C.POINTER(ShardMap), c_p]),
     'dr4sr_table_grad_targets_join': (c_i32, [c_p]),
+    'dr4sr_rank_metrics': (c_i32, [c_p, c_p, c_i32, c_i32, C.POINTER(c_i32), c_i32, c_p, c_p]),
     'dr4sr_table_grad_sorted_workspace_bytes': (c_sz, [c_i32, c_i32, c_i32, c_i64]),
     'dr4sr_table_grad_sorted': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_sz, c_p]),
     'dr4sr_table_grad': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_sz, c_p]),

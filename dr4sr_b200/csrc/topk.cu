@@ -191,3 +191,57 @@ extern "C" int dr4sr_topk(const float* q, const float* table, const uint8_t* ite
   DR4SR_LAUNCH_CHECK("topk_select_kernel");
   return DR4SR_OK;
 }
+
+// ---- ranking metrics of an eval batch, accumulated on the device (reference evaluation/__init__.py:9-36,107-134 through
+// model/basemodel.py:337-352: one relevant item per user) ---------------------------------------------------------------
+// hit position r of `target` in the user's top-k ids -> ndcg@c += 1 / log2(r + 2), recall@c += 1 for every cutoff c > r.
+// One thread per user; block partials in double, one atomicAdd(double) per block and metric: the epoch's sums stay on the
+// device (no host read per batch) and are read once at the end.
+namespace dr4sr {
+struct Cutoffs { int32_t c[8]; int32_t n; };
+__global__ void __launch_bounds__(256) rank_metrics_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ target, int B, int k,
+                                                           const Cutoffs cut, double* __restrict__ sums) {
+  __shared__ double s_part[16][8];                            // [2 * n_cut][warps]
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = -1;
+  if (u < B) {
+    const int64_t t = target[u];
+    const int64_t* row = ids + (size_t)u * k;
+    for (int j = 0; j < k; ++j)
+      if (row[j] == t) { r = j; break; }
+  }
+  const float gain = r >= 0 ? 1.0f / log2f((float)r + 2.0f) : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = 0; i < cut.n; ++i) {
+    const bool in = r >= 0 && r < cut.c[i];
+    double nd = in ? (double)gain : 0.0, rc = in ? 1.0 : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      nd += __shfl_xor_sync(0xffffffffu, nd, o);
+      rc += __shfl_xor_sync(0xffffffffu, rc, o);
+    }
+    if (lane == 0) { s_part[2 * i][warp] = nd; s_part[2 * i + 1][warp] = rc; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * cut.n) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+}
+}  // namespace dr4sr
+
+extern "C" int dr4sr_rank_metrics(const int64_t* topk_ids, const int64_t* target, int32_t B, int32_t k, const int32_t* cutoffs,
+                                  int32_t n_cutoffs, double* sums, dr4sr_stream_t stream) {
+  if (!topk_ids || !target || !cutoffs || !sums || B <= 0 || k <= 0 || n_cutoffs <= 0 || n_cutoffs > 8) return DR4SR_EINVAL;
+  Cutoffs cut{};
+  cut.n = n_cutoffs;
+  for (int i = 0; i < n_cutoffs; ++i) {
+    if (cutoffs[i] <= 0 || cutoffs[i] > k) return DR4SR_EINVAL;
+    cut.c[i] = cutoffs[i];
+  }
+  cudaStream_t st = as_stream(stream);
+  ProfScope prof("rank_metrics", st);
+  rank_metrics_kernel<<<ceil_div(B, 256), 256, 0, st>>>(topk_ids, target, B, k, cut, sums);
+  DR4SR_LAUNCH_CHECK("rank_metrics_kernel");
+  return DR4SR_OK;
+}

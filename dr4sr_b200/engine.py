@@ -397,6 +397,19 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
                                 1 if zero_grad else 0, _stream()), 'dr4sr_adam')
 
 
+def rank_metrics(topk_ids: torch.Tensor, target: torch.Tensor, cutoffs, sums: torch.Tensor) -> None:
+    """sums[2i] += sum_u ndcg@cutoffs[i], sums[2i+1] += sum_u recall@cutoffs[i] (reference evaluation/__init__.py:9-36,107-134)."""
+    topk_ids = _req(topk_ids, torch.int64, 'topk_ids')
+    target = _req(target.reshape(-1), torch.int64, 'target')
+    if not (sums.is_cuda and sums.dtype == torch.float64 and sums.numel() == 2 * len(cutoffs) and sums.is_contiguous()):
+        raise _lib.Dr4srError('rank_metrics: sums must be a contiguous CUDA float64 tensor of 2 * len(cutoffs) elements')
+    if target.numel() != topk_ids.size(0) or not topk_ids.is_contiguous() or not target.is_contiguous():
+        raise _lib.Dr4srError('rank_metrics: one target per row of contiguous topk_ids')
+    arr = (C.c_int32 * len(cutoffs))(*[int(c) for c in cutoffs])
+    check(_lib.lib().dr4sr_rank_metrics(_p(topk_ids), _p(target), topk_ids.size(0), topk_ids.size(1), arr, len(cutoffs), _p(sums), _stream()),
+          'dr4sr_rank_metrics')
+
+
 _topk_ws: Dict[tuple, torch.Tensor] = {}
 
 

@@ -404,28 +404,23 @@ class BaseModel(nn.Module):
             outputs.append({'loss_0': loss.detach()})
         return [outputs]
 
-    @staticmethod
-    def _rank_metrics(hit: torch.Tensor, cutoffs) -> Dict[str, torch.Tensor]:
-        """ndcg@k / recall@k for one relevant item per user (reference evaluation/__init__.py:9-36,107-134)."""
-        out = {}
-        for k in cutoffs:
-            h = hit[:, :k].float()
-            disc = torch.log2(torch.arange(k, device=hit.device, dtype=torch.float32) + 2.0)
-            out[f'ndcg@{k}'] = (h / disc).sum(-1)
-            out[f'recall@{k}'] = h.sum(-1)
-        return out
-
     @torch.no_grad()
     def _eval_epoch(self, loader, cutoffs) -> Dict[str, float]:
-        sums, n = defaultdict(float), 0
+        """ndcg@c / recall@c over the loader: the hit position and the metric numerators are one kernel per batch
+        (dr4sr_rank_metrics) accumulating into a device buffer; the host reads it once per epoch."""
+        cutoffs = [int(c) for c in cutoffs]
+        sums = torch.zeros(2 * len(cutoffs), dtype=torch.float64, device=self.device)
+        n = 0
         for batch in loader:
             batch = {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
             _, ids = self.topk(batch, self.config['eval']['topk'], batch['user_hist'])
-            hit = batch[self.fiid].view(-1, 1) == ids
-            for name, v in self._rank_metrics(hit, cutoffs).items():
-                sums[name] += float(v.sum())
-            n += hit.size(0)
-        return {k: v / max(n, 1) for k, v in sums.items()}
+            _engine.rank_metrics(ids, batch[self.fiid], cutoffs, sums)
+            n += ids.size(0)
+        host = (sums / max(n, 1)).tolist()
+        out = {}
+        for i, c in enumerate(cutoffs):
+            out[f'ndcg@{c}'], out[f'recall@{c}'] = host[2 * i], host[2 * i + 1]
+        return out
 
     def fit(self):
         self._init_model(self.dataset_list[0])

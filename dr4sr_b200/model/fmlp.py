@@ -125,12 +125,13 @@ class FMLP(BaseModel):
         if getattr(self, '_dp_group', None) is not None:
             self._reduce_grads(tg, None)
 
-    def composite_forward(self, batch):
+    def composite_forward(self, batch, table=None):
         """Twice-differentiable torch evaluation (MetaModel's outer step only), model/fmlp.py:18-39."""
         import torch.nn.functional as F
         ids = batch['in_' + self.fiid]
         L = ids.size(1)
-        x = self.item_embedding(ids) + self.position_embeddings(torch.arange(L, device=ids.device)).unsqueeze(0)
+        emb = self.item_embedding(ids) if table is None else torch.nn.functional.embedding(ids, table, padding_idx=0)
+        x = emb + self.position_embeddings(torch.arange(L, device=ids.device)).unsqueeze(0)
         x = self.dropout(self.LayerNorm(x))
         for blk in self.item_encoder.layer:
             f, i = blk.filterlayer, blk.intermediate

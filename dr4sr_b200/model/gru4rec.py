@@ -61,11 +61,12 @@ class GRU4Rec(BaseModel):
         if getattr(self, '_dp_group', None) is not None:
             self._reduce_grads(tg, late_loss)
 
-    def composite_forward(self, batch):
+    def composite_forward(self, batch, table=None):
         """Twice-differentiable torch evaluation (MetaModel's outer step only), model/gru4rec.py:23-31."""
         ids = batch['in_' + self.fiid]
         seq = self.query_encoder[0]
-        h = seq[3].gru(seq[2](self.item_embedding(ids)))[0]
+        emb = self.item_embedding(ids) if table is None else torch.nn.functional.embedding(ids, table, padding_idx=0)
+        h = seq[3].gru(seq[2](emb))[0]
         out = self.query_encoder[1](h)
         ar = torch.arange(ids.size(1), device=ids.device)
         return out.masked_fill(ar.view(1, -1, 1) >= batch['seqlen'].view(-1, 1, 1), 0.0)

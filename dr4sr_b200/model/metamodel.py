@@ -162,12 +162,12 @@ class MetaModel(BaseModel):
         return self.dataset_list[0].get_loader()
 
     # ---- outer step (metamodel.py:123-166): composite, twice-differentiable evaluation ----------------
-    def _composite_losses(self, batch, weighted: bool):
+    def _composite_losses(self, batch, weighted: bool, table=None):
         """Per-slot BCE of the sub-model through the torch modules that hold its parameters (double-backward
         capable); same arithmetic as the reference's training_step (basemodel.py:204-214, loss_func.py:9-35)."""
         sm = self.sub_model
-        q = sm.composite_forward(batch)
-        E = sm.item_embedding.weight
+        q = sm.composite_forward(batch, table)
+        E = sm.item_embedding.weight if table is None else table
         item_id, neg = batch[self.fiid], batch['neg_item']
         pos = (q * E[item_id]).sum(-1)
         negs = (q.unsqueeze(-2) * E[neg]).sum(-1)
@@ -187,12 +187,27 @@ class MetaModel(BaseModel):
         """One hypergradient update of the meta module from a validation batch and a training batch (both with
         `neg_item`): the else-branch of the reference's _outter_loop (metamodel.py:149-166)."""
         from torch.nn.attention import SDPBackend, sdpa_kernel
+        # The item table enters both losses only through the rows the two batches touch: every other row has a zero gradient
+        # and a zero row / column in the Hessian, so the hypergradient over the whole table (the reference differentiates all
+        # N x D of it, several dense passes per Neumann term) equals the one over the touched rows.  Gather them once, remap
+        # the ids (0 stays 0: the padding row), and differentiate with respect to that [rows, D] leaf instead.
+        sm, fi = self.sub_model, self.fiid
+        keys = ('in_' + fi, fi, 'neg_item')
+        used = torch.cat([b[k].reshape(-1) for b in (val_batch, train_batch) for k in keys] + [torch.zeros(1, dtype=torch.int64, device=self.device)])
+        rows = torch.unique(used)                        # sorted, rows[0] == 0
+        sub_table = sm.item_embedding.weight.detach()[rows].requires_grad_(True)
+        val_batch, train_batch = dict(val_batch), dict(train_batch)
+        for b in (val_batch, train_batch):
+            for k in keys:
+                b[k] = torch.searchsorted(rows, b[k])
+        table_ptr = sm.item_embedding.weight.data_ptr()
+        others = [p for p in sm.parameters() if p.data_ptr() != table_ptr]
         with sdpa_kernel(SDPBackend.MATH), torch.backends.cudnn.flags(enabled=False):
-            meta_loss = self._composite_losses(val_batch, weighted=False)
-            meta_train_loss = self._composite_losses(train_batch, weighted=True)
+            meta_loss = self._composite_losses(val_batch, weighted=False, table=sub_table)
+            meta_train_loss = self._composite_losses(train_batch, weighted=True, table=sub_table)
             return self.meta_optimizer.step(val_loss=meta_loss, train_loss=meta_train_loss,
                                             aux_params=list(self.meta_module.parameters()),
-                                            parameters=list(self.sub_model.parameters()), return_grads=return_grads)
+                                            parameters=others + [sub_table], return_grads=return_grads)
 
     def _outter_loop(self, nepoch):
         def one_batch(loader):

@@ -146,14 +146,16 @@ class SASRec(BaseModel):
         if getattr(self, '_dp_group', None) is not None:
             self._reduce_grads(tg, late_loss)
 
-    def composite_forward(self, batch):
+    def composite_forward(self, batch, table=None):
         """Twice-differentiable torch evaluation of the same parameters (MetaModel's outer step only):
-        the reference's own module graph, model/sasrec.py:39-75, 'origin' pooling."""
+        the reference's own module graph, model/sasrec.py:39-75, 'origin' pooling.  `table`: rows to look the ids up in
+        instead of the item table (MetaModel passes the touched rows with remapped ids)."""
         enc = self.query_encoder
         ids = batch['in_' + self.fiid]
         L = ids.size(1)
         ar = torch.arange(L, device=ids.device)
-        x = enc.item_encoder(ids) + enc.position_emb(ar).unsqueeze(0)
+        emb = enc.item_encoder(ids) if table is None else torch.nn.functional.embedding(ids, table, padding_idx=0)
+        x = emb + enc.position_emb(ar).unsqueeze(0)
         causal = torch.triu(torch.ones(L, L, dtype=torch.bool, device=ids.device), 1)
         out = enc.transformer_layer(src=enc.dropout(x), mask=causal, src_key_padding_mask=ids == 0)
         return out.masked_fill(ar.view(1, L, 1) >= batch['seqlen'].view(-1, 1, 1), 0.0)

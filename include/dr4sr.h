@@ -279,6 +279,14 @@ typedef struct {
   int32_t world;
   int32_t rank;
 } dr4sr_shard_map;
+/* Ranking metrics of one eval batch, accumulated on the device: for user u with the relevant item target[u] at position r of
+ * topk_ids[u, 0..k) (absent: no contribution), sums[2 i] += 1 / log2(r + 2) and sums[2 i + 1] += 1 for every cutoff
+ * cutoffs[i] > r (ndcg@c and recall@c numerators; divide by the number of users at the end of the epoch).  `cutoffs` is a HOST
+ * array of n_cutoffs <= 8 values in 1..k; `sums` a device array of 2 * n_cutoffs doubles the caller zeroes once per epoch.
+ * Reference: evaluation/__init__.py:9-36,107-134 via model/basemodel.py:337-352. */
+DR4SR_API int dr4sr_rank_metrics(const int64_t* topk_ids, const int64_t* target, int32_t B, int32_t k, const int32_t* cutoffs,
+                                 int32_t n_cutoffs, double* sums, dr4sr_stream_t stream);
+
 /* Deterministic variant of dr4sr_table_grad: the (item id, source row) entries of the step are sorted by id (stable radix
  * sort) and every run of equal ids is reduced by warps in a fixed order -- a warp-segmented reduction, no float atomics, every
  * row of table_grad has one writer.  Same arguments and result contract; two calls on the same inputs give bit-identical

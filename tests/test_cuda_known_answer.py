@@ -42,6 +42,9 @@ def test_shipped_checkpoint_known_answer_on_cuda(name):
     nd = rc = 0.0
     bad_rows, worst_gap, smax = 0, 0.0, 0.0
     disc = torch.log2(torch.arange(20, dtype=torch.float64) + 2.0)
+    from dr4sr_b200 import engine
+    dev_sums = torch.zeros(4, dtype=torch.float64, device=DEV)          # the eval loop's fused metric kernel, cutoffs (20, 10)
+    nd10 = rc10 = 0.0
     for s in range(0, hist.size(0), 2048):                     # eval batch_size of the reference (configs/basemodel.yaml)
         e = min(s + 2048, hist.size(0))
         b = {'in_item_id': hist[s:e].to(DEV), 'seqlen': slen[s:e].to(DEV), 'user_hist': hist[s:e].to(DEV)}
@@ -66,8 +69,14 @@ def test_shipped_checkpoint_known_answer_on_cuda(name):
         hit = (tgt[s:e].view(-1, 1) == ids[:, :20]).double()
         nd += float((hit / disc).sum())
         rc += float(hit.sum())
+        nd10 += float((hit[:, :10] / disc[:10]).sum())
+        rc10 += float(hit[:, :10].sum())
+        engine.rank_metrics(ids.to(DEV), tgt[s:e].to(DEV), [20, 10], dev_sums)
     n = hist.size(0)
     ndcg, recall = nd / n, rc / n
+    got = dev_sums.tolist()                                              # dr4sr_rank_metrics == the torch hit-matrix arithmetic
+    for a, b in zip(got, (nd, rc, nd10, rc10)):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (got, (nd, rc, nd10, rc10))
     print(f'{name}: {n} users, top-20 id rows differing from the reference: {bad_rows}, top-100 rows differing (first {n100}): {bad100}; '
           f'ndcg@20 {ndcg:.7f} (stored {float(fx["metric"]["ndcg@20"]):.7f}), recall@20 {recall:.7f} '
           f'(stored {float(fx["metric"]["recall@20"]):.7f})')
