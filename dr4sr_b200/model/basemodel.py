@@ -51,6 +51,8 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, table, model, batch, reduce, return_query):
         model._check_flat()
         loss, query, state = model._step_forward(batch, reduce, return_query)
+        if reduce:
+            model._mark_loss(loss)               # (data parallel: marked again once the gradient all-reduce has made it global)
         eng = model.engine
         eng.fwd_token += 1
         ctx.model, ctx.state, ctx.reduce, ctx.token = model, state, reduce, eng.fwd_token
@@ -315,6 +317,31 @@ class BaseModel(nn.Module):
             dist.all_reduce(self._comm[tn:], op=dist.ReduceOp.SUM, group=grp)
         if loss is not None:
             loss.detach().view(1).copy_(self._comm[-1:])
+            self._mark_loss(loss)
+
+    # ---- host read of the loss without draining the stream ---------------------------------------
+    def _mark_loss(self, loss: torch.Tensor) -> None:
+        if getattr(self, '_loss_evt', None) is None:
+            self._loss_evt = torch.cuda.Event()
+        self._loss_ref = loss.detach()
+        self._loss_evt.record()
+
+    def loss_value(self) -> float:
+        """Host value of the most recent `training_step(reduce=True)` loss, read as soon as the kernels that produce it have
+        finished: an event-gated copy on a side stream.  The backward and the optimizer step of the same batch (already
+        enqueued) keep running and the host goes on enqueuing the next batch -- `float(loss)` would wait for all of it.
+        (The reference's trainer never reads the loss inside the epoch, model/basemodel.py:199,217-224.)"""
+        ref = getattr(self, '_loss_ref', None)
+        if ref is None:
+            raise RuntimeError('loss_value(): no training_step(reduce=True) has run yet')
+        if getattr(self, '_read_stream', None) is None:
+            self._read_stream = torch.cuda.Stream(device=ref.device)
+            self._loss_pin = torch.zeros((), dtype=torch.float32).pin_memory()
+        self._read_stream.wait_event(self._loss_evt)
+        with torch.cuda.stream(self._read_stream):
+            self._loss_pin.copy_(ref, non_blocking=True)
+        self._read_stream.synchronize()
+        return float(self._loss_pin)
 
     def _dp_sum(self, *tensors) -> None:
         grp = getattr(self, '_dp_group', None)

@@ -160,3 +160,28 @@ def test_deterministic_training_step_repeats_bit_for_bit():
     assert torch.equal(g1, g2) and torch.equal(w1, w2) and l1 == l2
     g3, w3, _ = run(False)
     check_err('deterministic vs atomic scatter, table gradient', float((g1 - g3).abs().max() / g1.abs().max()), 5e-6)
+
+
+def test_loss_value_reads_the_same_loss_without_draining_the_stream():
+    """BaseModel.loss_value(): the event-gated side-stream read returns exactly float(loss), step after step."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    from dr4sr_b200.model.sasrec import SASRec
+    from dr4sr_b200.utils.config import SyntheticCatalog, default_config
+    N, D, B = 2001, 128, 64
+    cfg = default_config('SASRec', model__embed_dim=D, train__device=DEV)
+    torch.manual_seed(3)
+    m = SASRec(cfg, [SyntheticCatalog(N)] * 3)
+    m._init_model()
+    m.train()
+    with pytest.raises(RuntimeError):
+        m.loss_value()
+    for i in range(4):
+        batch = {k: v.to(DEV) for k, v in synthetic_batch(B, 50, N, seed=30 + i).items()}
+        m.optimizer.zero_grad()
+        loss = m.training_step(batch)
+        loss.backward()
+        m.optimizer.step()
+        early = m.loss_value()
+        assert early == float(loss.detach()) and early > 0.0
