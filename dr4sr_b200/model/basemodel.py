@@ -51,8 +51,6 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, table, model, batch, reduce, return_query):
         model._check_flat()
         loss, query, state = model._step_forward(batch, reduce, return_query)
-        if reduce:
-            model._mark_loss(loss)               # (data parallel: marked again once the gradient all-reduce has made it global)
         eng = model.engine
         eng.fwd_token += 1
         ctx.model, ctx.state, ctx.reduce, ctx.token = model, state, reduce, eng.fwd_token
@@ -317,30 +315,53 @@ class BaseModel(nn.Module):
             dist.all_reduce(self._comm[tn:], op=dist.ReduceOp.SUM, group=grp)
         if loss is not None:
             loss.detach().view(1).copy_(self._comm[-1:])
-            self._mark_loss(loss)
+            if getattr(self, '_loss_late', False):
+                self._loss_evt.record()
+                self._loss_late = False
 
     # ---- host read of the loss without draining the stream ---------------------------------------
-    def _mark_loss(self, loss: torch.Tensor) -> None:
+    def _mark_loss(self, loss: torch.Tensor, final: bool = True) -> None:
+        """Called by the step's forward once the kernels that produce `loss` are enqueued.  `final=False`: data parallel with
+        the rank-local partial (it becomes global inside the backward's gradient all-reduce): the global value for
+        `loss_value()` is formed right away by a 1-float all-reduce on the read stream -- beside the backward, never waited
+        for by the compute stream."""
         if getattr(self, '_loss_evt', None) is None:
+            dev = loss.device
             self._loss_evt = torch.cuda.Event()
-        self._loss_ref = loss.detach()
+            self._read_stream = torch.cuda.Stream(device=dev)
+            self._loss_pin = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self._loss_glob = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._loss_ref = loss.detach().view(1)
         self._loss_evt.record()
+        self._loss_late = False
+        if not final and self.config['train'].get('early_loss_read', False):
+            # (a collective: the switch is configuration, identical on every rank -- never a per-rank decision)
+            import torch.distributed as dist
+            s = self._read_stream
+            s.wait_event(self._loss_evt)
+            with torch.cuda.stream(s):
+                self._loss_glob.copy_(self._loss_ref)
+                dist.all_reduce(self._loss_glob, op=dist.ReduceOp.SUM, group=self._dp_group)
+            self._loss_ref = self._loss_glob
+        elif not final:
+            self._loss_late = True               # _reduce_grads records the event again once the value is global
 
     def loss_value(self) -> float:
-        """Host value of the most recent `training_step(reduce=True)` loss, read as soon as the kernels that produce it have
-        finished: an event-gated copy on a side stream.  The backward and the optimizer step of the same batch (already
-        enqueued) keep running and the host goes on enqueuing the next batch -- `float(loss)` would wait for all of it.
-        (The reference's trainer never reads the loss inside the epoch, model/basemodel.py:199,217-224.)"""
+        """Host value of the most recent `training_step(reduce=True)` loss (the global one under data parallelism), read as
+        soon as the kernels that produce it have finished: an event-gated copy on a side stream.  The backward and the
+        optimizer step of the same batch (already enqueued) keep running and the host goes on enqueuing the next batch --
+        `float(loss)` would wait for all of it.  (The reference's trainer never reads the loss inside the epoch,
+        model/basemodel.py:199,217-224.)  Data parallel: with config['train']['early_loss_read'] the global value is formed by a
+        1-float all-reduce on the read stream right after the forward; without it the value is ready when the backward's
+        gradient all-reduce is (call after `backward()`)."""
         ref = getattr(self, '_loss_ref', None)
         if ref is None:
             raise RuntimeError('loss_value(): no training_step(reduce=True) has run yet')
-        if getattr(self, '_read_stream', None) is None:
-            self._read_stream = torch.cuda.Stream(device=ref.device)
-            self._loss_pin = torch.zeros((), dtype=torch.float32).pin_memory()
-        self._read_stream.wait_event(self._loss_evt)
-        with torch.cuda.stream(self._read_stream):
+        s = self._read_stream
+        s.wait_event(self._loss_evt)
+        with torch.cuda.stream(s):
             self._loss_pin.copy_(ref, non_blocking=True)
-        self._read_stream.synchronize()
+        s.synchronize()
         return float(self._loss_pin)
 
     def _dp_sum(self, *tensors) -> None:

@@ -107,6 +107,7 @@ class FMLP(BaseModel):
         loss = eng.reduce_loss(b) if reduce else b.loss_pos.clone()
         if reduce:
             self._dp_sum(loss)
+            self._mark_loss(loss)
         return loss, (b.q_last.clone() if return_query else None), (b, in_ids, item_id, neg)
 
     def _step_backward(self, state, reduce, dloss, dquery) -> None:

@@ -87,11 +87,13 @@ class SASRec(BaseModel):
         eng = self.engine
         in_ids, item_id, neg = batch['in_' + self.fiid], batch[self.fiid], batch['neg_item']
         neg = neg.view(item_id.shape)
+        # peer-sharded table: rows are read from the other ranks' shards, so every rank's Adam pass of the previous step must be
+        # done first.  The barrier is issued before the rank-local batch preparation and runs beside it on NCCL's stream.
+        tick = self._peer.barrier_async() if self._peer is not None else None
         b = eng.prep(batch['seqlen'], item_id)
-        n_work = self._dp_count_async(b.counts[1:2])   # data parallel: normalise by the global number of valid targets
-        if n_work is not None and self._peer is not None:
-            n_work.wait()                     # peer-sharded table: also the barrier "every rank's Adam pass is done" for the gathers
-            n_work = None
+        n_work = self._dp_count_async(b.counts[1:2])   # data parallel: normalise by the global number of valid targets (needed by
+        if tick is not None:                           # the loss kernel only: its all-reduce runs under the encoder forward)
+            tick.wait()
         if self.training:
             eng.step += 1
         q_dense = None
@@ -111,6 +113,8 @@ class SASRec(BaseModel):
         late = bool(reduce and fused_grad and getattr(self, '_dp_group', None) is not None)
         if reduce and not late:
             self._dp_sum(loss)
+        if reduce:
+            self._mark_loss(loss, final=not late)
         # (a detached alias of the same storage: the returned tensor itself would close the cycle loss -> grad_fn -> ctx.state ->
         # loss, and the step's tensors would then wait for the cyclic GC instead of being freed by reference count -- measured:
         # sporadic cudaMallocs of the growing pool, 2 - 150 ms each with peer mappings enabled)

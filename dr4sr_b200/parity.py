@@ -54,6 +54,7 @@ def sharded_parity_check(group, dev: torch.device, model_name: str = 'SASRec', N
         sh.enable_sharded_table(group)               # (both broadcast rank 0's encoder: identical on every rank, same seed)
     sh._flat.copy_(ref._flat)
     sh.train()
+    sh.config['train']['early_loss_read'] = True     # loss_value(): the global loss right after the forward
     mine = split_batch(full, rank, world)
 
     errs: Dict[str, float] = {}
@@ -64,6 +65,7 @@ def sharded_parity_check(group, dev: torch.device, model_name: str = 'SASRec', N
     lsh = sh.training_step(mine)
     lsh.backward()
     errs['loss_rel'] = abs(float(lsh.detach()) - float(lref.detach())) / abs(float(lref.detach()))
+    errs['loss_value_rel'] = abs(sh.loss_value() - float(lref.detach())) / abs(float(lref.detach()))   # early side-stream read, global
     errs['grad_rel'] = _rel(sh._flat_grad, ref._flat_grad)
     errs['table_grad_rel'] = _rel(sh.item_embedding.weight.grad, ref.item_embedding.weight.grad[lo:hi])
     ref.optimizer.step()

@@ -85,3 +85,9 @@ class PeerTable:
         """Stream-ordered barrier over the ranks (no host sync): kernels enqueued after it start once every rank's kernels
         enqueued before it have finished."""
         dist.all_reduce(self._tick, group=self.group)
+
+    def barrier_async(self):
+        """The same barrier as a Work handle: it is ordered behind everything enqueued on the current stream so far, runs on
+        NCCL's stream beside whatever the caller enqueues next (rank-local kernels), and `.wait()` orders the current stream
+        behind it."""
+        return dist.all_reduce(self._tick, group=self.group, async_op=True)
