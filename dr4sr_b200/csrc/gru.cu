@@ -44,7 +44,7 @@ GruOffsets gru_offsets(int D, int H, int n_layer) {
 
 struct GruWs {
   float* x0;
-  struct Layer { float *gi, *gates, *h, *hprev, *dgi, *dgh; Img ih_f, ih_b; } layer[4];
+  struct Layer { float *gi, *gates, *h, *hprev, *dgi, *dgh; Img ih_f, ih_b, hh_f; } layer[4];
   float *dh, *g0, *dy_mask;        // dh [T,H]: upstream gradient into a layer's outputs; g0 [T,D]
   float *part_w, *part_cs;         // weight-gradient partials [kSplit][max], colsum partials
   Img out_f, out_b;
@@ -66,6 +66,7 @@ GruWs carve(const dr4sr_gru_cfg& c, void* base) {
     y.gi = take(T * 3 * H); y.gates = take(T * 4 * H); y.h = take(T * H); y.hprev = take(T * H);
     y.dgi = take(T * 3 * H); y.dgh = take(T * 3 * H);
     y.ih_f = take_img(3 * H * in); y.ih_b = take_img(3 * H * in);
+    y.hh_f = take_img(3 * H * H);                    // W_hh images: the tcgen05 recurrence copies its 96-row slices out of them
   }
   w.dh = take(T * H); w.g0 = take(T * D); w.dy_mask = nullptr;
   const size_t wmax = 3 * H * (H > D ? H : D);
@@ -423,6 +424,7 @@ int build_images(const dr4sr_gru_cfg& c, const float* params, const GruWs& w, co
     const int in = l == 0 ? D : H;
     add(params + lo.w_ih[l], in, 3 * H, in, 0, w.layer[l].ih_f);      // gi = x W_ih^T
     add(params + lo.w_ih[l], in, in, 3 * H, 1, w.layer[l].ih_b);      // dx = dgi W_ih
+    if (gru_tc_supported(H)) add(params + lo.w_hh[l], H, 3 * H, H, 0, w.layer[l].hh_f);   // gh = h W_hh^T (recurrence)
   }
   add(params + lo.w_out, H, D, H, 0, w.out_f);                        // y = h W_out^T
   add(params + lo.w_out, H, H, D, 1, w.out_b);                        // dh = dy W_out
@@ -472,7 +474,10 @@ extern "C" int dr4sr_gru_fwd(const dr4sr_gru_cfg* c, const float* table, const f
       g.tag = "gru_gemm_gi";
       DR4SR_TRY(gemm_nt(g, y.ih_f, st));
     }
-    DR4SR_TRY(launch_gru_fwd(H, y.gi, params + lo.w_hh[l], tok_off, w.order, c->B, y.h, y.hprev, y.gates, st));
+    if (tc_enabled() && gru_tc_supported(H))
+      DR4SR_TRY(launch_gru_fwd_tc(y.gi, y.hh_f.hi, y.hh_f.lo, tok_off, w.order, c->B, y.h, y.hprev, y.gates, st));
+    else
+      DR4SR_TRY(launch_gru_fwd(H, y.gi, params + lo.w_hh[l], tok_off, w.order, c->B, y.h, y.hprev, y.gates, st));
     x = y.h;
     in = H;
   }

@@ -15,6 +15,11 @@ int bg_join(cudaStream_t st);
 // positional gradient (deterministic column reduction of dx0)  [loss_table.cu]
 int launch_pos_grad(const float* dx0_packed, const int32_t* tok_off, int B, int L, int D, float* pos_grad, void* ws, cudaStream_t sa);
 
+// GRU recurrence on tcgen05 (hidden size 256)  [gru_tc.cu]
+bool gru_tc_supported(int H);
+int launch_gru_fwd_tc(const float* gi, const uint16_t* whh_hi, const uint16_t* whh_lo, const int32_t* tok_off, const int32_t* order, int B,
+                      float* h, float* hprev, float* gates, cudaStream_t st);
+
 constexpr int kLnBwdBlocks = 2 * kNumSMs;   // CTAs (= column-partial slices) of the LayerNorm backward kernels
 
 // attention over packed rows, one CTA per (sequence, head)  [attention.cu]
