@@ -38,6 +38,11 @@ class ShardMap(C.Structure):
                 ('rank', c_i32)]
 
 
+class PeerComm(C.Structure):
+    """Mirror of dr4sr_peer_comm (flag arrays, count slots and staging buffers of every rank, as local / peer pointers)."""
+    _fields_ = [('flags', c_p * MAX_SHARDS), ('slots', c_p * MAX_SHARDS), ('stage', c_p * MAX_SHARDS), ('world', c_i32), ('rank', c_i32)]
+
+
 class SasrecCfg(C.Structure):
     """Mirror of dr4sr_sasrec_cfg."""
     _fields_ = [('B', c_i32), ('L', c_i32), ('D', c_i32), ('F', c_i32), ('n_head', c_i32), ('n_layer', c_i32),
@@ -86,6 +91,8 @@ SIGNATURES = {
     'dr4sr_table_grad_targets_async': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p]),
     'dr4sr_table_grad_targets_async_sharded': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, C.POINTER(ShardMap), c_p]),
     'dr4sr_table_grad_targets_join': (c_i32, [c_p]),
+    'dr4sr_peer_barrier': (c_i32, [C.POINTER(PeerComm), c_i32, c_p, c_p]),
+    'dr4sr_peer_allreduce': (c_i32, [C.POINTER(PeerComm), c_i32, c_i64, c_p, c_p]),
     'dr4sr_rank_metrics': (c_i32, [c_p, c_p, c_i32, c_i32, C.POINTER(c_i32), c_i32, c_p, c_p]),
     'dr4sr_table_grad_sorted_workspace_bytes': (c_sz, [c_i32, c_i32, c_i32, c_i64]),
     'dr4sr_table_grad_sorted': (c_i32, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i64, c_p, c_p, c_p, c_sz, c_p]),

@@ -258,8 +258,17 @@ class BaseModel(nn.Module):
         self._table_grad.zero_()
         if self._table_group is not None:
             self._table_group.dirty = False
-        self._peer = PeerTable(self.num_items, self.embed_dim, group, self.item_embedding.weight.data, self._table_grad)
+        n = self._flat_grad.numel()
+        self._peer = PeerTable(self.num_items, self.embed_dim, group, self.item_embedding.weight.data, self._table_grad, n_stage=n + 1,
+                               collectives=self.config['train'].get('peer_collectives', 'peer'))
         self._peer_eval = ShardedTable(self.num_items, self.embed_dim, group, self.item_embedding.weight.device)   # top-k merge only
+
+    def _grad_out(self) -> torch.Tensor:
+        """Where the backward writes the flat encoder gradient: the optimizer's buffer, or -- peer collectives -- the staging
+        buffer the other ranks read (the all-reduce then lands in the optimizer's buffer)."""
+        if self._peer is not None and self._peer.coll:
+            return self._peer.stage[: self._flat_grad.numel()]
+        return self._flat_grad
 
     def _rows_for(self, bufs, in_ids, item_id, neg):
         """(table, in_ids, item_id, neg) the kernels run on: the parameter itself, the peer-sharded table, or the staged
@@ -302,15 +311,26 @@ class BaseModel(nn.Module):
             return
         import torch.distributed as dist
         tn = self._table_grad.numel()
-        if loss is not None:
-            self._comm[-1:].copy_(loss.detach().view(1))
-        if self._peer is not None:
+        if self._peer is not None and self._peer.coll:
+            # gradient rows were added in their owners' HBM by the scatter kernels; the encoder gradients (and the loss) sit in the
+            # staging buffer: barrier ("every rank's backward and scatter are done") + sum over the ranks' buffers, no NCCL
+            n = self._flat_grad.numel()
+            if loss is not None:
+                self._peer.stage[n:n + 1].copy_(loss.detach().view(1))
+            self._peer.allreduce_stage(n + 1, self._comm[tn:])
+        elif self._peer is not None:
+            if loss is not None:
+                self._comm[-1:].copy_(loss.detach().view(1))
             # the rows were added in their owners' HBM by the scatter kernel; this all-reduce is also the barrier
             # "every rank's scatter has finished" that the Adam pass on the shard needs
             dist.all_reduce(self._comm[tn:], op=dist.ReduceOp.SUM, group=grp)
         elif self._shard is None and tg is self._table_grad:
+            if loss is not None:
+                self._comm[-1:].copy_(loss.detach().view(1))
             dist.all_reduce(self._comm, op=dist.ReduceOp.SUM, group=grp)
         else:
+            if loss is not None:
+                self._comm[-1:].copy_(loss.detach().view(1))
             self._finish_table_grad(tg)
             dist.all_reduce(self._comm[tn:], op=dist.ReduceOp.SUM, group=grp)
         if loss is not None:

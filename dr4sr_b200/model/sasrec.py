@@ -89,11 +89,16 @@ class SASRec(BaseModel):
         neg = neg.view(item_id.shape)
         # peer-sharded table: rows are read from the other ranks' shards, so every rank's Adam pass of the previous step must be
         # done first.  The barrier is issued before the rank-local batch preparation and runs beside it on NCCL's stream.
-        tick = self._peer.barrier_async() if self._peer is not None else None
+        coll = self._peer is not None and self._peer.coll
+        tick = self._peer.barrier_async() if (self._peer is not None and not coll) else None
         b = eng.prep(batch['seqlen'], item_id)
-        n_work = self._dp_count_async(b.counts[1:2])   # data parallel: normalise by the global number of valid targets (needed by
-        if tick is not None:                           # the loss kernel only: its all-reduce runs under the encoder forward)
-            tick.wait()
+        if coll:                                       # one kernel over peer memory: the barrier + the global number of valid targets
+            self._peer.barrier(count=b.counts[1:2])
+            n_work = None
+        else:
+            n_work = self._dp_count_async(b.counts[1:2])   # data parallel: normalise by the global number of valid targets (needed
+            if tick is not None:                           # by the loss kernel only: its all-reduce runs under the encoder forward)
+                tick.wait()
         if self.training:
             eng.step += 1
         q_dense = None
@@ -139,8 +144,9 @@ class SASRec(BaseModel):
         split = not eng.deterministic_scatter          # (the sorted, bit-reproducible reduction takes all three row sets at once)
         if split:
             eng.table_grad_targets_async(b, item_id, neg, tg)
-        eng.encode_bwd(b, table, self._flat, in_ids, self._flat_grad, defer_join=True)
-        pos = self._flat_grad[: eng.L * eng.D].view(eng.L, eng.D)
+        gout = self._grad_out()
+        eng.encode_bwd(b, table, self._flat, in_ids, gout, defer_join=True)
+        pos = gout[: eng.L * eng.D].view(eng.L, eng.D)
         if split:
             eng.table_grad(b, in_ids, None, None, tg, pos)
             eng.table_grad_join()

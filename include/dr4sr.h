@@ -312,6 +312,24 @@ DR4SR_API int dr4sr_table_grad_targets_async(const float* q_packed, const float*
                                              dr4sr_stream_t stream);
 DR4SR_API int dr4sr_table_grad_targets_join(dr4sr_stream_t stream);
 
+/* The per-step synchronisation of the peer-sharded layout as kernels over peer memory (no reference counterpart).
+ * flags[r] / slots[r] / stage[r]: rank r's flag array (DR4SR_MAX_SHARDS int32, zero-initialised), count slots
+ * (DR4SR_MAX_SHARDS int32) and staging buffer (floats), as pointers valid on THIS device (peer mappings for r != rank).
+ * dr4sr_peer_barrier: stream-ordered barrier over the ranks; kernels enqueued after it on any rank start once the kernels
+ *   enqueued before it on every rank have finished.  `epoch` must be positive and increase with every barrier / all-reduce
+ *   call, identically on every rank.  count_inout (nullable): a device int32 that is replaced by its sum over the ranks.
+ * dr4sr_peer_allreduce: the same barrier, then out[i] = sum_r stage[r][i] for i < n, added in rank order (bit-identical on
+ *   every rank).  The staging buffers may be overwritten again after the NEXT barrier.
+ * A rank that never arrives makes the others trap after 20 s instead of hanging. */
+typedef struct dr4sr_peer_comm {
+  int32_t* flags[DR4SR_MAX_SHARDS];
+  int32_t* slots[DR4SR_MAX_SHARDS];
+  float* stage[DR4SR_MAX_SHARDS];
+  int32_t world, rank;
+} dr4sr_peer_comm;
+DR4SR_API int dr4sr_peer_barrier(const dr4sr_peer_comm* comm, int32_t epoch, int32_t* count_inout, dr4sr_stream_t stream);
+DR4SR_API int dr4sr_peer_allreduce(const dr4sr_peer_comm* comm, int32_t epoch, int64_t n, float* out, dr4sr_stream_t stream);
+
 /* dr4sr_sasrec_fwd / dr4sr_score_loss / dr4sr_table_grad with the table (resp. its gradient) given as a shard map. */
 DR4SR_API int dr4sr_sasrec_fwd_sharded(const dr4sr_sasrec_cfg* cfg, const dr4sr_shard_map* map, const float* params,
                      const int64_t* in_item_id, const int32_t* tok_off, const int32_t* row_seq,
