@@ -11,7 +11,7 @@
 // the step 40-100 us (launch + protocol latency at 8 ranks, and c10d's host path when the loop is host-bound), three of them per
 // step; a flag exchange over NVLink is a few microseconds and one kernel launch.  Epochs increase monotonically (host counter,
 // identical call sequence on every rank), so a fast rank's next signal never confuses a slow one (the wait is `>= epoch`).
-// Every spin is bounded by a wall-clock timeout (a missing rank traps instead of hanging the GPU).
+// Every spin is bounded by a wall-clock timeout (a missing rank traps after 60 s instead of hanging the GPU).
 #include "internal.cuh"
 
 namespace dr4sr {
@@ -41,7 +41,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-constexpr unsigned long long kBarrierTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;   // 20 s: a rank is missing
+constexpr unsigned long long kBarrierTimeoutNs = 60ull * 1000ull * 1000ull * 1000ull;   // 60 s: a rank is missing
 
 // one CTA of 32 threads; thread p talks to rank p
 __global__ void __launch_bounds__(32) peer_barrier_kernel(const PeerComm c, int32_t epoch, int32_t* count_inout) {

@@ -320,7 +320,7 @@ DR4SR_API int dr4sr_table_grad_targets_join(dr4sr_stream_t stream);
  *   call, identically on every rank.  count_inout (nullable): a device int32 that is replaced by its sum over the ranks.
  * dr4sr_peer_allreduce: the same barrier, then out[i] = sum_r stage[r][i] for i < n, added in rank order (bit-identical on
  *   every rank).  The staging buffers may be overwritten again after the NEXT barrier.
- * A rank that never arrives makes the others trap after 20 s instead of hanging. */
+ * A rank that never arrives makes the others trap after 60 s instead of hanging. */
 typedef struct dr4sr_peer_comm {
   int32_t* flags[DR4SR_MAX_SHARDS];
   int32_t* slots[DR4SR_MAX_SHARDS];
