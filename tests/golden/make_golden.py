@@ -231,7 +231,7 @@ def checkpoint_case(out: str, dataset: str, domain: str, n_users_topk: int = 256
     print(out, 'written', os.path.getsize(os.path.join(HERE, out)) / 1e6, 'MB')
 
 
-def metamodel_case(out: str, N: int, D: int, B: int, seed: int):
+def metamodel_case(out: str, N: int, D: int, B: int, seed: int, sub: str = 'SASRec'):
     """MetaModel (DR4SR+, sub_model = SASRec): the weighted inner step (model/metamodel.py:169-194) and one outer
     hypergradient step (metamodel.py:123-166 else-branch, utils/utils.py:145-255) of the UNMODIFIED reference, dropout 0.
     The only randomness left is F.gumbel_softmax's noise: it is drawn from a known seed right before the call, and the
@@ -256,12 +256,15 @@ def metamodel_case(out: str, N: int, D: int, B: int, seed: int):
 
     cfg = load_config({'model': 'MetaModel', 'dataset': 'amazon-toys'})
     cfg['train']['device'] = 'cpu'
-    cfg['model']['sub_model'] = 'SASRec'
+    cfg['model']['sub_model'] = sub
     cfg['model']['embed_dim'] = D
     cfg['model']['dropout_rate'] = 0.0
     seed_everything(seed)
     ref = CpuMetaModel(cfg, [fake] * 3)
     ref._init_model(None)
+    for mod in ref.sub_model.modules():              # FMLP hard-codes nn.Dropout(0.5) (model/fmlp.py:13, module/layers.py:740-808)
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
     ref.train()
     # make the meta module non-trivial: the reference initialises it N(0, 0.02), which makes every weight ~0.5
     with torch.no_grad():
@@ -279,11 +282,14 @@ def metamodel_case(out: str, N: int, D: int, B: int, seed: int):
         torch.manual_seed(s)
         return -torch.empty(shape, dtype=torch.float32).exponential_().log()    # F.gumbel_softmax's first statement
 
-    tr = synthetic_batch(B, L, N, seed=seed)
+    layout = 'pre' if sub == 'FMLP' else 'post'          # FMLP: pre-padded inputs, one target per sequence (README.md:78)
+    gshape = (B, 2) if sub == 'FMLP' else (B, L, 2)
+    tr = synthetic_batch(B, L, N, seed=seed, layout=layout)
     tr['user_id'][::3] = 0            # mined patterns keep weight 1 (metamodel.py:180-183)
-    va = synthetic_batch(B, L, N, seed=seed + 1)
+    va = synthetic_batch(B, L, N, seed=seed + 1, layout=layout)
     fx.update(pack('batch', tr)); fx.update(pack('valbatch', va))
-    g_in = gumbel_like((B, L, 2), 1234)
+    fx['meta_cfg/sub_model'] = np.asarray(sub)
+    g_in = gumbel_like(gshape, 1234)
     fx['inner/gumbel'] = g_in.numpy()
 
     # ---- inner weighted step ----
@@ -292,7 +298,7 @@ def metamodel_case(out: str, N: int, D: int, B: int, seed: int):
         torch.manual_seed(1234)
         loss = ref.training_step(batch={k: v.clone() for k, v in tr.items()}, align=False)
         # oracle restatement with the injected noise must agree
-        o = orc.OracleSASRec(N, embed_dim=D, dropout_rate=0.0).train()
+        o = (orc.OracleFMLP if sub == 'FMLP' else orc.OracleSASRec)(N, embed_dim=D, dropout_rate=0.0).train()
         o.load_state_dict(ref.sub_model.state_dict())
         per_o, q_o = o.training_step(tr, reduce=False, return_query=True)
         mm = ref.meta_module
@@ -307,7 +313,7 @@ def metamodel_case(out: str, N: int, D: int, B: int, seed: int):
                                        for k, p in ref.meta_module.named_parameters()}))
 
     # ---- one outer step: the else-branch of _outter_loop on (va, tr) with known Gumbel noise ----
-    g_out = gumbel_like((B, L, 2), 4321)
+    g_out = gumbel_like(gshape, 4321)
     fx['outer/gumbel'] = g_out.numpy()
     with sdpa_kernel(SDPBackend.MATH):
         meta_loss = ref.sub_model.training_step(batch={k: v.clone() for k, v in va.items()}, align=False)
@@ -342,3 +348,4 @@ if __name__ == '__main__':
         checkpoint_case(_out, _ds, _dom)
     metamodel_case('metamodel_sasrec_d64.npz', N=300, D=64, B=6, seed=21)
     metamodel_case('metamodel_sasrec_d128.npz', N=1000, D=128, B=16, seed=22)
+    metamodel_case('metamodel_fmlp_d64.npz', N=300, D=64, B=12, seed=23, sub='FMLP')    # the reference's default sub-model (configs/metamodel.yaml)

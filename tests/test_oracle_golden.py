@@ -131,12 +131,12 @@ def test_shipped_checkpoint_known_answer(ckpt):
     assert abs(float(torch.cat(rc).mean()) - float(fx['metric']['recall@20'])) < 5e-7
 
 
-@pytest.mark.parametrize('name', ['metamodel_sasrec_d64.npz', 'metamodel_sasrec_d128.npz'])
+@pytest.mark.parametrize('name', ['metamodel_sasrec_d64.npz', 'metamodel_sasrec_d128.npz', 'metamodel_fmlp_d64.npz'])
 def test_metamodel_inner_step_oracle_matches_reference_golden(name):
     """orc.meta_weighted_loss (+ the oracle SASRec under it) against the loss and sub-model gradients the UNMODIFIED
     reference MetaModel.training_step produced with the same Gumbel noise (model/metamodel.py:169-194)."""
     fx = load_fixture(name)
-    o = oracle_from_fixture('sasrec', fx).train()
+    o = oracle_from_fixture('fmlp' if 'fmlp' in name else 'sasrec', fx).train()      # (FMLP: the reference's default sub-model)
     batch = fx['batch']
     mm = {k: v.clone().requires_grad_(True) for k, v in fx['meta'].items()}
     per, q = o.training_step(batch, reduce=False, return_query=True)
