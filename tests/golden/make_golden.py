@@ -343,6 +343,8 @@ if __name__ == '__main__':
              out='gru4rec_d128.npz')
     run_case('FMLP', orc.OracleFMLP, dict(dropout_rate=0.0), N=300, D=64, B=6, layout='pre', seed=15,
              out='fmlp_d64.npz')
+    run_case('GRU4Rec', orc.OracleGRU4Rec, dict(dropout_rate=0.0, hidden_size=256), N=300, D=64, B=6, layout='post', seed=16,
+             out='gru4rec_h256.npz')       # hidden 256 = configs/gru4rec.yaml; the size the tcgen05 recurrence serves
     bpr_case()
     for _out, (_ds, _dom) in CKPTS.items():
         checkpoint_case(_out, _ds, _dom)

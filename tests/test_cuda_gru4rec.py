@@ -5,10 +5,12 @@ import pytest
 import torch
 
 from oracle import dr4sr_oracle as orc
-from tests.helpers import load_fixture, rel_err, load_params
+from tests.helpers import check_err, load_fixture, rel_err, load_params
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
+# measured against the reference goldens (profiles/r2_parity_errors.json): tc query 7.5e-6, gradients 8.2e-6 (h256, the tcgen05
+# recurrence: 5.3e-6 / 6.6e-6); ffma 3.6e-7 / 5.7e-7; loss 8.6e-8 on both.  The bars below are the north star's (1e-4 relative).
 TOL = {'tc': dict(fwd=1e-4, loss=1e-4, grad=1e-3, adam=1e-4), 'ffma': dict(fwd=1e-5, loss=1e-5, grad=1e-4, adam=2e-5)}
 
 
@@ -37,7 +39,7 @@ def to_dev(batch):
     return {k: v.to(DEV) for k, v in batch.items()}
 
 
-@pytest.mark.parametrize('name', ['gru4rec_d64.npz', 'gru4rec_d128.npz'])
+@pytest.mark.parametrize('name', ['gru4rec_d64.npz', 'gru4rec_d128.npz', 'gru4rec_h256.npz'])   # h256: the tcgen05 recurrence (csrc/gru_tc.cu)
 def test_gru4rec_matches_reference_golden(name, backend):
     tol = TOL[backend]
     fx = load_fixture(name)
@@ -47,14 +49,19 @@ def test_gru4rec_matches_reference_golden(name, backend):
     load_params(m, {k: v.to(DEV) for k, v in fx['param'].items()})
     batch = to_dev(fx['batch'])
     q = m.forward(batch).cpu()
-    assert rel_err(q, fx['train']['query']) < tol['fwd']
+    check_err(f'gru4rec[{backend}] {name} query vs reference', rel_err(q, fx['train']['query']), tol['fwd'])
     m.optimizer.zero_grad()
     loss = m.training_step(batch)
     loss.backward()
-    assert abs(float(loss.detach()) - float(fx['train']['loss'])) / abs(float(fx['train']['loss'])) < tol['loss']
+    check_err(f'gru4rec[{backend}] {name} loss vs reference',
+              abs(float(loss.detach()) - float(fx['train']['loss'])) / abs(float(fx['train']['loss'])), tol['loss'])
+    worst = 0.0
     for k, p in m.named_parameters():
         assert p.grad is not None, k
-        assert rel_err(p.grad.cpu(), fx['grad'][k]) < tol['grad'], k
+        e = rel_err(p.grad.cpu(), fx['grad'][k])
+        assert e < tol['grad'], k
+        worst = max(worst, e)
+    check_err(f'gru4rec[{backend}] {name} worst gradient vs reference', worst, tol['grad'])
     # three Adam steps with the reference's weight decay (configs/gru4rec.yaml: 1e-4)
     load_params(m, {k: v.to(DEV) for k, v in fx['param'].items()})
     for want in fx['adam']['losses'].tolist():

@@ -9,7 +9,7 @@ from oracle import dr4sr_oracle as orc
 from tests.helpers import load_fixture, oracle_from_fixture, rel_err, load_params
 
 CASES = [('sasrec', 'sasrec_d64.npz'), ('sasrec', 'sasrec_d128.npz'), ('gru4rec', 'gru4rec_d64.npz'),
-         ('gru4rec', 'gru4rec_d128.npz'), ('fmlp', 'fmlp_d64.npz')]
+         ('gru4rec', 'gru4rec_d128.npz'), ('gru4rec', 'gru4rec_h256.npz'), ('fmlp', 'fmlp_d64.npz')]
 
 
 @pytest.mark.parametrize('kind,name', CASES)
