@@ -66,6 +66,13 @@ class _TrainStep(torch.autograd.Function):
                                'most recent forward only)')
         if dloss is None:
             raise RuntimeError('dr4sr_b200: training_step loss received no gradient')
+        opt = getattr(model, 'optimizer', None)
+        if hasattr(opt, 'pending_backwards'):
+            if opt.pending_backwards >= 1:
+                raise RuntimeError('dr4sr_b200: a second backward() without optimizer.step() or optimizer.zero_grad() in between: the '
+                                   'kernels overwrite the gradient buffers, they do not accumulate across backward() calls '
+                                   '(torch would); step or zero_grad first')
+            opt.pending_backwards += 1
         model._step_backward(ctx.state, ctx.reduce, dloss.contiguous(), dquery)
         model._publish_grads()
         return None, None, None, None, None

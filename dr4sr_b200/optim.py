@@ -33,17 +33,22 @@ class FusedAdam(torch.optim.Optimizer):
         self.flat_groups = groups
         self.step_count = 0
         self._on_step = on_step
+        self.pending_backwards = 0      # backward() calls since the last step() / zero_grad() (see BaseModel: at most one)
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         """No work to do, by construction: every backward OVERWRITES the flat encoder gradient, and the table gradient
         accumulator is cleared by the Adam pass that consumes it (zero_grad_in_step), so nothing can carry over from the
         previous step.  `.grad` keeps pointing at those persistent buffers (torch's loop over ~30 parameters setting
-        them to None costs 25 us of host time per step and would be re-done by the next backward anyway)."""
+        them to None costs 25 us of host time per step and would be re-done by the next backward anyway).
+        Unlike torch, gradients do NOT accumulate across backward() calls: a second backward() without a step() or
+        zero_grad() in between raises (dr4sr_b200/model/basemodel.py::_TrainStep.backward) instead of silently overwriting."""
+        self.pending_backwards = 0
         return None
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        self.pending_backwards = 0
         self.step_count += 1
         h = self.param_groups[0]
         for g in self.flat_groups:

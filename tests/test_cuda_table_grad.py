@@ -185,3 +185,30 @@ def test_loss_value_reads_the_same_loss_without_draining_the_stream():
         m.optimizer.step()
         early = m.loss_value()
         assert early == float(loss.detach()) and early > 0.0
+
+
+def test_second_backward_without_step_or_zero_grad_is_refused():
+    """The kernels overwrite the gradient buffers; torch would accumulate.  Instead of silently differing, a second backward()
+    without optimizer.step() / zero_grad() raises; after zero_grad() the next backward is accepted."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    from dr4sr_b200.model.sasrec import SASRec
+    from dr4sr_b200.utils.config import SyntheticCatalog, default_config
+    N, D, B = 501, 64, 8
+    cfg = default_config('SASRec', model__embed_dim=D, model__dropout_rate=0.0, train__device=DEV)
+    torch.manual_seed(4)
+    m = SASRec(cfg, [SyntheticCatalog(N)] * 3)
+    m._init_model()
+    m.train()
+    batch = {k: v.to(DEV) for k, v in synthetic_batch(B, 50, N, seed=9).items()}
+    m.optimizer.zero_grad()
+    m.training_step(batch).backward()
+    g1 = m.item_embedding.weight.grad.clone()
+    with pytest.raises(RuntimeError, match='second backward'):
+        m.training_step(batch).backward()
+    m.optimizer.zero_grad()                                # an explicit discard: the next backward starts from zero again
+    m.training_step(batch).backward()
+    assert torch.allclose(m.item_embedding.weight.grad, g1, rtol=0, atol=1e-7 * float(g1.abs().max()) + 1e-12)
+    m.optimizer.step()
+    m.training_step(batch).backward()                      # step() consumed the gradient: accepted
