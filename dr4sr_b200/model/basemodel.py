@@ -257,6 +257,9 @@ class BaseModel(nn.Module):
         from ..sharded import ShardedTable
         if self._shard_rows is None:
             raise _engine._lib.Dr4srError("enable_peer_table needs config['train']['table_shard'] = (rank, world)")
+        if getattr(self.engine, '_name', '') != 'dr4sr_sasrec':
+            raise _engine._lib.Dr4srError(f'the peer-memory table is implemented for SASRec; use enable_sharded_table (all-to-all) for '
+                                          f'{type(self).__name__}')
         if self.engine.deterministic_scatter:
             raise _engine._lib.Dr4srError('deterministic_scatter is not available with the peer-memory table (gradient rows of several '
                                           'ranks meet in the owner\'s HBM through float atomics); use the all-to-all or replicated layout')
