@@ -16,7 +16,11 @@ NAMES = [('sasrec_fwd_fused_kernel', 'sasrec_fwd_fused'), ('sasrec_bwd_ffn_fused
          ('prep_scan_kernel', 'prep_batch'), ('pos_grad_kernel', 'pos_grad'), ('colsum_kernel', 'colsum'),
          ('reduce_segments_kernel', 'reduce_partials'), ('fused_tiles_kernel', 'fused_tiles'), ('weight_image_kernel', 'weight_images'),
          ('neg_sample_kernel', 'neg_sample'), ('sum_kernel', 'loss_sum'), ('scale_grads_kernel', 'scale_grads'),
-         ('logits_topk_kernel', 'topk_logits_tc'), ('select_kernel', 'topk_select'), ('table_image_kernel', 'topk_table_images')]
+         ('logits_topk_kernel', 'topk_logits_tc'), ('select_kernel', 'topk_select'), ('table_image_kernel', 'topk_table_images'),
+         ('gru_fwd_tc_kernel', 'gru_recurrence_fwd_tc'), ('gru_fwd_kernel', 'gru_recurrence_fwd'), ('gru_bwd_kernel', 'gru_recurrence_bwd'),
+         ('gru_order_kernel', 'gru_order'), ('filter_fwd_kernel', 'fmlp_filter_fwd'), ('filter_bwd_dx_kernel', 'fmlp_filter_bwd_dx'),
+         ('filter_bwd_dh_kernel', 'fmlp_filter_bwd_dh'), ('filter_wgrad_kernel', 'fmlp_filter_wgrad'), ('filter_taps_kernel', 'fmlp_filter_taps'),
+         ('embed_dense_kernel', 'fmlp_embed'), ('ln_fwd_kernel', 'ln_fwd'), ('ln_bwd_kernel', 'ln_bwd'), ('embed_fwd_kernel', 'embed_fwd')]
 COLS = {'gpu__time_duration.sum': 'dur', 'dram__bytes_read.sum': 'rd', 'dram__bytes_write.sum': 'wr',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed': 'dram_pct',
         'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active': 'tensor_pct',
