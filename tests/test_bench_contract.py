@@ -51,3 +51,19 @@ def test_reference_arm_prints_one_contract_line():
     assert d['impl'] == 'reference' and d['metric'] == bench.METRIC and d['unit'] == bench.UNIT and d['higher_is_better'] is True
     assert d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['e2e'] == {'value': d['value'], 'unit': bench.UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_cfg1_shapes_and_identical_workload_strings():
+    """`--config cfg1`: amazon-toys sizes with the shipped data's sequence-length profile (mean 2.25); both arms print the same
+    `config.workload` string (the driver compares them)."""
+    import torch
+    from dr4sr_b200.data.synthetic import synthetic_batch
+    c = bench.CFG1
+    assert (c['num_items'], c['embed_dim'], c['batch_per_gpu'], c['max_seq_len']) == (11_925, 64, 256, 50)
+    b = synthetic_batch(4096, 50, c['num_items'], seed=1, with_neg=False, mean_len=c['mean_len'])
+    sl = b['seqlen'].double()
+    assert 2.1 < float(sl.mean()) < 2.4 and int(sl.min()) >= 1 and int(sl.max()) <= 50
+    live = torch.arange(50).view(1, -1) < b['seqlen'].view(-1, 1)
+    assert bool((b['in_item_id'][live] > 0).all()) and bool((b['in_item_id'][~live] == 0).all())
+    assert bench.workload_label(c) == bench.workload_label(dict(c)) and 'configs[0]' in bench.workload_label(c)
+    assert 'configs[1]' in bench.workload_label(bench.CFG2)
